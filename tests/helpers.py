@@ -1,0 +1,80 @@
+"""Shared helpers for the parity tests (golden replay, comparisons)."""
+import os
+
+import numpy as np
+
+from oracle import bpv_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+METHOD = dict(DIFF_1=orc.DIFF_1, DIFF_2=orc.DIFF_2, INTERP_LINEAR=orc.INTERP_LINEAR, INTERP_CUBIC=orc.INTERP_CUBIC,
+              DETREND_CONST=orc.DETREND_CONST, DETREND_LINEAR=orc.DETREND_LINEAR, FILTER_BUTTER=orc.FILTER_BUTTER,
+              FILTER_FIR=orc.FILTER_FIR)
+TRANSFORM = dict(DFT_RFFT=orc.DFT_RFFT, PGRAM_WELCH=orc.PGRAM_WELCH, PGRAM_LS=orc.PGRAM_LS)
+CHANNEL = dict(GREEN=orc.GREEN, CHROM_GREEN=orc.CHROM_GREEN)
+
+# golden case table (also imported by tests/golden/make_golden.py):
+# name: (channel, methods, transform, window, n_frames, fps, irregular, p_none, roi_max_samples, kwargs)
+CASES = {
+    'c1_butter_ls':      ('GREEN', ['FILTER_BUTTER'], 'PGRAM_LS', 48, 70, 30, False, 0.03, 1, dict(min_freq=0.7)),
+    'c2_detrend_fir_welch': ('CHROM_GREEN', ['DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_WELCH', 48, 70, 30, False, 0.03, 1, {}),
+    'c4_cubic_butter_ls': ('GREEN', ['INTERP_CUBIC', 'FILTER_BUTTER'], 'PGRAM_LS', 56, 72, 120, True, 0.05, 1, {}),
+    'diff1_dft':         ('GREEN', ['DIFF_1'], 'DFT_RFFT', 40, 60, 30, False, 0.02, 1, {}),
+    'diff2_welch':       ('CHROM_GREEN', ['DIFF_2'], 'PGRAM_WELCH', 40, 60, 30, True, 0.02, 2, {}),
+    'lin_const_fir_dft': ('GREEN', ['INTERP_LINEAR', 'DETREND_CONST', 'FILTER_FIR'], 'DFT_RFFT', 40, 60, 25, True, 0.05, 3, {}),
+    'none_ls':           ('CHROM_GREEN', [], 'PGRAM_LS', 40, 60, 30, True, 0.05, 1, {}),
+    'lowfs_butter_ls':   ('GREEN', ['DETREND_LINEAR', 'FILTER_BUTTER'], 'PGRAM_LS', 40, 56, 7.5, False, 0.0, 1, {}),
+    'long_window_c2':    ('CHROM_GREEN', ['DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_WELCH', 300, 306, 30, False, 0.01, 1, {}),
+    'long_window_c1':    ('GREEN', ['FILTER_BUTTER'], 'PGRAM_LS', 300, 306, 30, False, 0.01, 1, dict(min_freq=0.7)),
+}
+IMG_H, IMG_W = 60, 80
+REL = [(-0.00, -0.10, 0.20, 0.05), (-0.10, -0.10, 0.10, 0.10)]  # roi.py:26,28
+LMK = [[151], [0, 9]]                                            # roi.py:19,21-22
+
+
+def load_case(name):
+    g = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    return {k: g[k] for k in g.files}
+
+
+def case_frames(g):
+    from bpv import synth
+    return synth.frames(np.random.default_rng(int(g['seed']) + 1000), g['ts'], IMG_H, IMG_W, f_pulse=1.3)
+
+
+def case_rois(g, i):
+    """The reference's calc_rois (via the oracle restatement) on the stored detections."""
+    rois = []
+    for r in range(2):
+        if not g['present'][i, r]:
+            rois.append((np.nan,) * 6)
+            continue
+        if r == 0:
+            pts = np.zeros((478, 2), np.int64)
+            pts[151] = g['face_pt'][i]
+            det = [(tuple(int(v) for v in g['face_bbox'][i]), pts)]
+        else:
+            pts = np.zeros((21, 2), np.int64)
+            pts[0], pts[9] = g['hand_pts'][i, 0], g['hand_pts'][i, 1]
+            det = [(tuple(int(v) for v in g['hand_bbox'][i]), pts)]
+        rois.append(orc.calc_roi(det, LMK[r], REL[r]))
+    return rois
+
+
+def same(a, b):
+    """Exact equality with NaN == NaN."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def close(a, b, rtol=1e-4, atol_frac=1e-5):
+    """|a-b| <= rtol*|b| + atol_frac*max|b|  with NaN == NaN (north_star: rtol 1e-4)."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    if b.size == 0 or nb.all():
+        return True
+    scale = np.nanmax(np.abs(b))
+    return bool(np.all(np.abs(a - b)[~nb] <= rtol * np.abs(b)[~nb] + atol_frac * scale))

@@ -1,0 +1,49 @@
+"""CPU: the oracle (oracle/bpv_oracle.py) must reproduce, bit for bit, what the unmodified
+reference produced for the committed golden fixtures (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bpv_oracle as orc
+from tests import helpers as h
+
+
+@pytest.mark.parametrize('name', list(h.CASES))
+def test_process_matches_reference(name):
+    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = h.CASES[name]
+    g = h.load_case(name)
+    frames = h.case_frames(g)
+    st = orc.OracleStream(2, roi_ms, window, 50, h.CHANNEL[channel], [h.METHOD[m] for m in methods],
+                          h.TRANSFORM[transform], **kw)
+    full_at = set(int(i) for i in g['full_at'])
+    for i in range(n):
+        out = st.process(frames[i], float(g['ts'][i]), h.case_rois(g, i))
+        assert h.same(np.array([np.asarray(b, dtype=float) for b in out['boxes']]), g['boxes'][i]), (name, i)
+        assert h.same(out['samples'], g['raw'][i]), (name, i)
+        assert h.same(out['bpm'], g['bpm'][i]), (name, i)
+        assert h.same(out['ptt'], g['ptt'][i]), (name, i)
+        if i in full_at:
+            for r in range(2):
+                assert h.same(out['proc_x'][r], g[f'f{i}_proc_x{r}'])
+                assert h.same(out['proc_y'][r], g[f'f{i}_proc_y{r}'])
+                assert h.same(out['freqs'][r], g[f'f{i}_spec_x{r}'])
+                assert h.same(out['mags'][r], g[f'f{i}_spec_y{r}'])
+            assert h.same(out['lags'][0], g[f'f{i}_corr_x0'])
+            assert h.same(out['corr'][0], g[f'f{i}_corr_y0'])
+
+
+def test_roi_sample_matches_reference():
+    g = np.load(os.path.join(h.GOLDEN, 'roi_sample.npz'))
+    rng = np.random.default_rng(int(g['seed']))
+    frame = rng.integers(0, 256, (int(g['H']), int(g['W']), 3), dtype=np.uint8)
+    n_empty = 0
+    for k, box in enumerate(g['boxes']):
+        sroi = (0, 0, *[int(v) for v in box])
+        sB, sG, sR, n = orc.roi_sums(frame, box)
+        n_empty += n == 0
+        for c in (orc.GREEN, orc.CHROM_GREEN):
+            ref = g['values'][c, k]
+            assert h.same(orc.roi_sample(frame, sroi, c), ref)
+            assert h.same(orc.value_from_sums(sB, sG, sR, n, c), ref), (k, box, c)
+    assert 0 < n_empty < len(g['boxes'])
