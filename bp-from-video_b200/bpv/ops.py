@@ -1,0 +1,156 @@
+"""Launchers: torch tensors (device memory + stream plumbing only) -> libbpv C-ABI calls.
+
+Every function enqueues on torch's current CUDA stream and returns device tensors; nothing here
+computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import WindowParams, check, lib, ptr, stream_handle
+
+
+def _dev_accessible(t: torch.Tensor) -> bool:
+    return t.is_cuda or t.is_pinned()
+
+
+def roi_sample(frames: torch.Tensor, boxes: torch.Tensor, mode: int, *, want_sums: bool = False,
+               roi_pixels_hint: int = 0, out_value: torch.Tensor | None = None):
+    """F1.  frames uint8 [N,H,W,3] (CUDA, or pinned host memory for the zero-copy path; rows may be
+    strided), boxes int32 [N,R,4] (CUDA).  Returns (value f64 [N,R], sums u64-as-int64 [N,R,4] | None).
+    Reference: signal_processor.py:176-193."""
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3
+    assert _dev_accessible(frames), 'frames must live in CUDA or pinned host memory'
+    assert frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR'
+    N, H, W, _ = frames.shape
+    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4
+    R = boxes.shape[1]
+    dev = boxes.device
+    if out_value is None:
+        out_value = torch.empty((N, R), dtype=torch.float64, device=dev)
+    sums = torch.empty((N, R, 4), dtype=torch.int64, device=dev) if want_sums else None
+    fstride = frames.stride(0) if N > 1 else H * frames.stride(1)
+    check(lib().bpv_roi_sample_u8(ptr(frames), None, fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode),
+                                  ptr(sums), ptr(out_value), int(roi_pixels_hint), stream_handle()),
+          'bpv_roi_sample_u8')
+    return out_value, sums
+
+
+def roi_sample_ptrs(frame_ptrs: torch.Tensor, H: int, W: int, row_stride: int, boxes: torch.Tensor, mode: int, *,
+                    want_sums: bool = False, roi_pixels_hint: int = 0):
+    """F1 over frames living in separate allocations: frame_ptrs int64 [N] (CUDA) of device-accessible
+    addresses."""
+    N = frame_ptrs.numel()
+    R = boxes.shape[1]
+    out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
+    sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
+    check(lib().bpv_roi_sample_u8(None, ptr(frame_ptrs), 0, row_stride, H, W, N, ptr(boxes), R, int(mode),
+                                  ptr(sums), ptr(out_value), int(roi_pixels_hint), stream_handle()),
+          'bpv_roi_sample_u8')
+    return out_value, sums
+
+
+def ring_push(ring_t: torch.Tensor, ring_y: torch.Tensor, g0: int, ts: torch.Tensor, values: torch.Tensor):
+    """Append T samples per stream (signal_data.py:31-35, 94-98).  ring_t f64 [S,cap], ring_y f64 [S,R,cap],
+    ts f64 [S,T], values f64 [S,T,R]."""
+    S, R, cap = ring_y.shape
+    T = ts.shape[1]
+    assert ts.shape == (S, T) and values.shape == (S, T, R) and ts.is_contiguous() and values.is_contiguous()
+    check(lib().bpv_ring_push(ptr(ring_t), ptr(ring_y), S, R, cap, int(g0), T, ptr(ts), ptr(values), stream_handle()),
+          'bpv_ring_push')
+
+
+def make_params(S, R, cap, window, head0, head_step, jobs_per_stream, methods, transform, *, butter_order=16,
+                butter_min_bw=0.1, fir_taps=127, fir_df=0.3, min_freq=0.8, max_freq=4.0, ls_num_freqs=0) -> WindowParams:
+    p = WindowParams()
+    p.S, p.R, p.cap, p.window = S, R, cap, window
+    p.head0, p.head_step, p.jobs_per_stream = head0, head_step, jobs_per_stream
+    if len(methods) > _cabi.MAX_METHODS:
+        raise ValueError('too many processing methods')
+    p.num_methods = len(methods)
+    for i, m in enumerate(methods):
+        p.methods[i] = int(m)
+    p.transform = int(transform)
+    p.butter_order, p.fir_taps, p.ls_num_freqs = butter_order, fir_taps, int(ls_num_freqs or 0)
+    p.butter_min_bw, p.fir_df, p.min_freq, p.max_freq = butter_min_bw, fir_df, min_freq, max_freq
+    return p
+
+
+def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None, status=None):
+    """F2 (signal_processor.py:196-245).  Returns proc_x, proc_y f64 [J,R,window], status i32 [J,R]."""
+    J = p.S * p.jobs_per_stream
+    dev = ring_y.device
+    proc_x = torch.empty((J, p.R, p.window), dtype=torch.float64, device=dev) if proc_x is None else proc_x
+    proc_y = torch.empty((J, p.R, p.window), dtype=torch.float64, device=dev) if proc_y is None else proc_y
+    status = torch.empty((J, p.R), dtype=torch.int32, device=dev) if status is None else status
+    check(lib().bpv_window_preprocess(ptr(ring_t), ptr(ring_y), C.byref(p), ptr(proc_x), ptr(proc_y), ptr(status),
+                                      stream_handle()), 'bpv_window_preprocess')
+    return proc_x, proc_y, status
+
+
+def max_bins(p: WindowParams) -> int:
+    if p.transform == _cabi.PGRAM_LS:
+        return p.ls_num_freqs if p.ls_num_freqs > 0 else p.window
+    if p.transform == _cabi.DFT_RFFT:
+        return p.window // 2 + 1
+    return min(256, p.window) // 2 + 1
+
+
+def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
+    """F3 + HR peak (signal_processor.py:248-277, 310).  Returns dict(freqs, mags f32 [J,R,max_bins] | None,
+    num_bins i32, peak_idx i32, peak_freq f64, peak_mag f64 [J,R])."""
+    J = p.S * p.jobs_per_stream
+    dev = proc_y.device
+    mb = max_bins(p)
+    o = out or {}
+    if store:
+        o.setdefault('freqs', torch.empty((J, p.R, mb), dtype=torch.float32, device=dev))
+        o.setdefault('mags', torch.empty((J, p.R, mb), dtype=torch.float32, device=dev))
+    else:
+        o['freqs'] = o['mags'] = None
+    o.setdefault('num_bins', torch.empty((J, p.R), dtype=torch.int32, device=dev))
+    o.setdefault('peak_idx', torch.empty((J, p.R), dtype=torch.int32, device=dev))
+    o.setdefault('peak_freq', torch.empty((J, p.R), dtype=torch.float64, device=dev))
+    o.setdefault('peak_mag', torch.empty((J, p.R), dtype=torch.float64, device=dev))
+    check(lib().bpv_window_spectrum(ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(o['freqs']), ptr(o['mags']),
+                                    ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']),
+                                    stream_handle()), 'bpv_window_spectrum')
+    return o
+
+
+def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
+    """F4 pairwise xcorr + lag peak (signal_processor.py:280-299, 312)."""
+    J = p.S * p.jobs_per_stream
+    P = p.R * (p.R - 1) // 2
+    dev = proc_y.device
+    L = 2 * p.window - 1
+    o = out or {}
+    if store:
+        o.setdefault('lags', torch.empty((J, P, L), dtype=torch.float32, device=dev))
+        o.setdefault('corr', torch.empty((J, P, L), dtype=torch.float32, device=dev))
+    else:
+        o['lags'] = o['corr'] = None
+    o.setdefault('num_lags', torch.empty((J, P), dtype=torch.int32, device=dev))
+    o.setdefault('lag_idx', torch.empty((J, P), dtype=torch.int32, device=dev))
+    o.setdefault('lag_sec', torch.empty((J, P), dtype=torch.float64, device=dev))
+    o.setdefault('lag_corr', torch.empty((J, P), dtype=torch.float64, device=dev))
+    if P > 0:
+        check(lib().bpv_window_xcorr(ptr(proc_x), ptr(proc_y), C.byref(p), ptr(o['lags']), ptr(o['corr']),
+                                     ptr(o['num_lags']), ptr(o['lag_idx']), ptr(o['lag_sec']), ptr(o['lag_corr']),
+                                     stream_handle()), 'bpv_window_xcorr')
+    return o
+
+
+def butter_sos_design(fs: torch.Tensor, p: WindowParams):
+    out = torch.empty((fs.numel(), p.butter_order, 6), dtype=torch.float64, device=fs.device)
+    check(lib().bpv_butter_sos_design(ptr(fs), fs.numel(), C.byref(p), ptr(out), stream_handle()), 'bpv_butter_sos_design')
+    return out
+
+
+def firls_design(fs: torch.Tensor, p: WindowParams):
+    out = torch.empty((fs.numel(), p.fir_taps), dtype=torch.float64, device=fs.device)
+    check(lib().bpv_firls_design(ptr(fs), fs.numel(), C.byref(p), ptr(out), stream_handle()), 'bpv_firls_design')
+    return out

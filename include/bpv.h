@@ -1,0 +1,154 @@
+/* libbpv — C ABI of the B200-native signal path of bp-from-video.
+ *
+ * The reference has no FFI: its boundary is three Python modules (roi.py, signal_data.py,
+ * signal_processor.py).  Our drop-in modules of the same names (bp-from-video_b200/) keep that
+ * Python surface and bind THIS library through ctypes; each entry point below names the reference
+ * code it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns int: 0 = OK, <0 = bpv error (BPV_E_*), >0 = cudaError_t.
+ *     bpv_last_error() returns a thread-local message for the last non-zero return.
+ *   - no allocation, no ownership transfer: every buffer is caller-owned, device-accessible memory
+ *     (device memory, or pinned/mapped host memory for the zero-copy ROI path).
+ *   - every call enqueues work on the caller's cudaStream_t (passed as void*; NULL = default stream)
+ *     and returns without synchronising.
+ *   - "signal" = one (stream, ROI) time series; "window job" = one evaluation of the sliding window
+ *     of one stream (all R ROIs + C(R,2) pairs), i.e. one SignalProcessor.process() call.
+ */
+#ifndef BPV_H
+#define BPV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPV_VERSION 100
+
+/* error codes (negative) */
+#define BPV_E_INVALID   (-1)   /* bad argument */
+#define BPV_E_UNSUPPORTED (-2) /* NotImplementedError in the reference (unknown enum value) */
+#define BPV_E_TOO_LARGE (-3)   /* window does not fit the kernel's shared-memory plan */
+
+/* SignalColorChannel (signal_processor.py:23-25) */
+#define BPV_GREEN       0
+#define BPV_CHROM_GREEN 1
+
+/* SignalProcessingMethod (signal_processor.py:28-36) */
+#define BPV_DIFF_1         1
+#define BPV_DIFF_2         2
+#define BPV_INTERP_LINEAR  3
+#define BPV_INTERP_CUBIC   4
+#define BPV_DETREND_CONST  5
+#define BPV_DETREND_LINEAR 6
+#define BPV_FILTER_BUTTER  7
+#define BPV_FILTER_FIR     8
+#define BPV_MAX_METHODS    8
+
+/* SignalSpectrumTransform (signal_processor.py:39-42) */
+#define BPV_DFT_RFFT    1
+#define BPV_PGRAM_WELCH 2
+#define BPV_PGRAM_LS    3
+
+/* x0 sentinel for "no detection": the reference's (nan,)*6 Location (signal_processor.py:154) */
+#define BPV_NO_BOX INT32_MIN
+
+int bpv_version(void);
+const char* bpv_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * F1  ROI sampling — replaces SignalProcessor.sample_signal / sample_signals
+ *     (signal_processor.py:176-193).
+ *
+ * frames      uint8 HWC BGR images.  Image f starts at frames + f*frame_stride_bytes (dense batch),
+ *             or at frame_ptrs[f] when frame_ptrs != NULL (then frames may be NULL).  Rows are
+ *             row_stride_bytes apart (>= 3*W; supports the reference's cropped views,
+ *             video_reader.py:101).  No alignment requirement.
+ * boxes       int32 [num_frames, R, 4] = (x0, y0, x1, y1) exactly as the reference slices them:
+ *             frame[y0:y1, x0:x1] with Python slice semantics (negative indices wrap, stops clamp,
+ *             empty -> NaN).  x0 == BPV_NO_BOX -> NaN sample.
+ * mode        BPV_GREEN: mean(G).  BPV_CHROM_GREEN: mean(G/2 - B/4 - R/4 + 0.5).
+ * out_sums    uint64 [num_frames, R, 4] = (sumB, sumG, sumR, N) exact integers; may be NULL.
+ * out_value   float64 [num_frames, R]: bit-identical to the reference's np.mean.
+ * roi_pixels_hint  typical ROI area in pixels (0 = unknown); only selects threads-per-ROI.
+ */
+int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
+                      int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                      int32_t H, int32_t W, int64_t num_frames,
+                      const int32_t* boxes, int32_t R, int32_t mode,
+                      uint64_t* out_sums, double* out_value,
+                      int64_t roi_pixels_hint, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ring buffers — replaces Signal.add_sample / SignalGroup.add_samples for sg_raw
+ *     (signal_data.py:31-35, 94-98; deque(maxlen) prefilled with NaN, signal_data.py:18-19).
+ *
+ * ring_t float64 [S, cap], ring_y float64 [S, R, cap]: sample with global index g (0-based count
+ * since the stream started) lives at slot g % cap.  Pushes T samples per stream with global
+ * indices g0 .. g0+T-1.  ts float64 [S, T]; values float64 [S, T, R] (F1's out_value).
+ */
+int bpv_ring_push(double* ring_t, double* ring_y, int32_t S, int32_t R, int32_t cap,
+                  int64_t g0, int32_t T, const double* ts, const double* values, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Window jobs.  A window job j of stream s looks at the `window` samples whose newest global
+ * index is head(j) = head0 + j*head_step (samples with negative global index read as NaN,
+ * exactly the NaN prefill of the reference's deque).  J = S * jobs_per_stream jobs in all, job id
+ * = s*jobs_per_stream + j.  All per-job outputs are laid out [J, R, ...] / [J, P, ...].
+ */
+typedef struct bpv_window_params {
+  int32_t S, R, cap, window;        /* ring geometry; window = signal_max_samples (<= cap)        */
+  int64_t head0;                    /* global index of the newest sample of job 0 of each stream  */
+  int32_t head_step;                /* global-index step between consecutive jobs of a stream     */
+  int32_t jobs_per_stream;
+  int32_t num_methods;              /* processing_methods, applied in order                       */
+  int32_t methods[BPV_MAX_METHODS];
+  int32_t transform;                /* BPV_DFT_RFFT / BPV_PGRAM_WELCH / BPV_PGRAM_LS              */
+  int32_t butter_order;             /* signal_processor.py:57 (even, <= 16)                       */
+  int32_t fir_taps;                 /* signal_processor.py:59 (odd, <= 127)                       */
+  int32_t ls_num_freqs;             /* 0 = reference behaviour (F = n valid); >0 fixed grid       */
+  double butter_min_bw, fir_df, min_freq, max_freq;   /* signal_processor.py:58,60,64,65          */
+} bpv_window_params;
+
+/* F2 preprocessing — replaces SignalProcessor.process_signal(s) + make_filter
+ *     (signal_processor.py:158-173, 196-245).
+ * proc_x, proc_y float64 [J, R, window]: the processed window, position-preserving (NaN where the
+ * reference's arrays hold NaN).  status int32 [J, R]: 0 ok, 1 = guard failed (copied through
+ * unprocessed, signal_processor.py:200), 2 = INTERP_CUBIC saw non-increasing x (the reference
+ * raises ValueError there).
+ */
+int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
+                          double* proc_x, double* proc_y, int32_t* status, void* stream);
+
+/* F3 + F4(a) spectrum and HR peak — replaces transform_signal(s) + SignalGroup.get_peaks on
+ *     sg_spec (signal_processor.py:248-277, 310; signal_data.py:65-70 with the range reset of
+ *     signal_data.py:82-86 => search over every finite bin).
+ * spec_f, spec_mag float32 [J, R, max_bins] (first num_bins[j,r] entries valid; may be NULL to skip
+ * storing the spectrum); num_bins int32 [J, R]; peak_idx int32 [J, R] (-1 = none);
+ * peak_freq, peak_mag float64 [J, R] (NaN = none).  The peak is decided in float64.
+ */
+int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,
+                        int32_t max_bins, float* spec_f, float* spec_mag, int32_t* num_bins,
+                        int32_t* peak_idx, double* peak_freq, double* peak_mag, void* stream);
+
+/* F4(b) pairwise cross-correlation lag search — replaces correlate_signal_pair / correlate_signals
+ *     + get_peaks on sg_corr (signal_processor.py:280-299, 312).  Pairs in
+ *     itertools.combinations order, P = R*(R-1)/2.
+ * corr_lag, corr_val float32 [J, P, 2*window-1] (first num_lags[j,p] valid; may be NULL);
+ * lag_idx int32 [J, P] index into the 2n-1 lags (-1 = none); lag_sec, lag_corr float64 [J, P].
+ */
+int bpv_window_xcorr(const double* proc_x, const double* proc_y, const bpv_window_params* p,
+                     float* corr_lag, float* corr_val, int32_t* num_lags,
+                     int32_t* lag_idx, double* lag_sec, double* lag_corr, void* stream);
+
+/* Filter design alone (debug / parity of make_filter, signal_processor.py:158-173).
+ * fs float64 [n]; sos_out float64 [n, order, 6]; taps_out float64 [n, fir_taps]. */
+int bpv_butter_sos_design(const double* fs, int32_t n, const bpv_window_params* p, double* sos_out, void* stream);
+int bpv_firls_design(const double* fs, int32_t n, const bpv_window_params* p, double* taps_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPV_H */

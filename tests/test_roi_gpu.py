@@ -1,0 +1,95 @@
+"""GPU parity of F1 (ROI sampling) through the C-ABI: integer sums and float64 samples must be
+bit-exact against the oracle / the reference's golden values."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bpv_oracle as orc
+from tests import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(frames_np, boxes_np, mode, hint, want_sums=True, offset=0, row_pad=0):
+    from bpv import ops
+    N, H, W, _ = frames_np.shape
+    if offset or row_pad:  # unaligned base address and padded rows (cropped-view case, video_reader.py:101)
+        buf = torch.zeros(offset + N * H * (W * 3 + row_pad) + 64, dtype=torch.uint8, device='cuda')
+        view = buf[offset:offset + N * H * (W * 3 + row_pad)].view(N, H, W * 3 + row_pad)[:, :, :W * 3].unflatten(2, (W, 3))
+        view.copy_(torch.from_numpy(frames_np).cuda())
+        frames = view
+    else:
+        frames = torch.from_numpy(frames_np).cuda()
+    boxes = torch.from_numpy(boxes_np.astype(np.int32)).cuda().contiguous()
+    val, sums = ops.roi_sample(frames, boxes, mode, want_sums=want_sums, roi_pixels_hint=hint)
+    torch.cuda.synchronize()
+    return val.cpu().numpy(), None if sums is None else sums.cpu().numpy()
+
+
+def _check(frames_np, boxes_np, mode, val, sums):
+    N, R = boxes_np.shape[:2]
+    for f in range(N):
+        for r in range(R):
+            b = boxes_np[f, r]
+            if b[0] == orc.np.iinfo(np.int32).min:
+                assert np.isnan(val[f, r])
+                continue
+            exp = orc.roi_sums(frames_np[f], b)
+            if sums is not None:
+                assert tuple(int(v) for v in sums[f, r]) == exp, (f, r, b)
+            ref = orc.roi_sample(frames_np[f], (0, 0, *[int(v) for v in b]), mode)
+            assert h.same(val[f, r], ref), (f, r, b, val[f, r], ref)
+
+
+@pytest.mark.parametrize('mode', [orc.GREEN, orc.CHROM_GREEN])
+def test_golden_values(mode):
+    g = np.load(os.path.join(h.GOLDEN, 'roi_sample.npz'))
+    rng = np.random.default_rng(int(g['seed']))
+    frame = rng.integers(0, 256, (int(g['H']), int(g['W']), 3), dtype=np.uint8)
+    boxes = g['boxes'].astype(np.int32)[None]           # one frame, R = len(boxes) ROIs
+    for hint in (64, 2000, 100000):
+        val, _ = _run(frame[None], boxes, mode, hint)
+        assert h.same(val[0], g['values'][mode]), hint
+
+
+@pytest.mark.parametrize('hint', [100, 4000, 60000])
+@pytest.mark.parametrize('shape', [(37, 53), (60, 80), (120, 67)])
+def test_random_boxes_exact(hint, shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W + hint)
+    N, R = 6, 5
+    frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    boxes = np.stack([rng.integers(-W - 5, W + 9, (N, R)), rng.integers(-H - 5, H + 9, (N, R)),
+                      rng.integers(-W - 5, W + 9, (N, R)), rng.integers(-H - 5, H + 9, (N, R))], axis=-1).astype(np.int32)
+    boxes[0, 0] = (0, 0, W, H)
+    boxes[1, 1] = (np.iinfo(np.int32).min, 0, 0, 0)
+    boxes[2, 2] = (3, 3, 3, 9)
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        for offset, pad in ((0, 0), (5, 7), (1, 0)):
+            val, sums = _run(frames, boxes, mode, hint, offset=offset, row_pad=pad)
+            _check(frames, boxes, mode, val, sums)
+
+
+def test_full_hd_boxes_exact():
+    """BASELINE config-2 geometry: 1080p, forehead/palm-sized boxes incl. out-of-frame ones."""
+    from bpv import synth
+    H, W, N = 1080, 1920, 4
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    boxes = synth.roi_boxes(rng, N, H, W, p_none=0.2, p_oob=0.3)
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        val, sums = _run(frames, boxes, mode, 96 * 65)
+        _check(frames, boxes, mode, val, sums)
+    big = np.array([[[0, 0, W, H], [-W, -H, W, H]]] * N, dtype=np.int32)   # max-size ROI: whole frame
+    val, sums = _run(frames, big, orc.CHROM_GREEN, H * W)
+    _check(frames, big, orc.CHROM_GREEN, val, sums)
+
+
+def test_unknown_channel_raises():
+    from bpv import ops
+    frames = torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device='cuda')
+    boxes = torch.zeros((1, 1, 4), dtype=torch.int32, device='cuda')
+    with pytest.raises(NotImplementedError):
+        ops.roi_sample(frames, boxes, 7)

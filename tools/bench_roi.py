@@ -1,0 +1,58 @@
+"""Micro-benchmark of the F1 kernel alone (development aid; bench.py is the judged harness)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'bp-from-video_b200'))
+from bpv import ops, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--frames', type=int, default=2048)
+ap.add_argument('--H', type=int, default=1080)
+ap.add_argument('--W', type=int, default=1920)
+ap.add_argument('--iters', type=int, default=20)
+ap.add_argument('--hint', type=int, default=0)
+ap.add_argument('--mode', type=int, default=1)
+a = ap.parse_args()
+N, H, W = a.frames, a.H, a.W
+frames = torch.empty((N, H, W, 3), dtype=torch.uint8, device='cuda')
+for i in range(0, N, 64):
+    frames[i:i + 64].random_(0, 256)
+rng = np.random.default_rng(0)
+boxes_np = synth.roi_boxes(rng, N, H, W)
+boxes = torch.from_numpy(boxes_np).cuda()
+
+
+def _sl(a, b, n):
+    a, b, _ = slice(int(a), int(b)).indices(n)
+    return a, max(a, b)
+
+
+nbytes = 0
+for f in range(N):
+    for r in range(2):
+        b = boxes_np[f, r]
+        if b[0] == synth.NO_BOX:
+            continue
+        xa, xb = _sl(b[0], b[2], W)
+        ya, yb = _sl(b[1], b[3], H)
+        nbytes += 3 * (xb - xa) * (yb - ya)
+hint = a.hint or int(nbytes / 3 / (2 * N))
+out = torch.empty((N, 2), dtype=torch.float64, device='cuda')
+for _ in range(3):
+    ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
+ev[0].record()
+for i in range(a.iters):
+    ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
+t = float(np.median(ts))
+print(f'frames={N} {W}x{H} hint={hint} roi_bytes={nbytes/1e6:.1f} MB  median {t*1e3:.1f} us  min {min(ts)*1e3:.1f} us '
+      f'-> {nbytes/t/1e6:.1f} GB/s median, {nbytes/min(ts)/1e6:.1f} GB/s best, {N/t*1e3:.0f} frames/s')
