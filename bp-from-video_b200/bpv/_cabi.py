@@ -33,11 +33,15 @@ _P = C.c_void_p
 _SIGS = {
     'bpv_version': (C.c_int, []),
     'bpv_last_error': (C.c_char_p, []),
+    'bpv_set_l2_fetch_granularity': (C.c_int, [C.c_int]),
+    'bpv_get_l2_fetch_granularity': (C.c_int, []),
     'bpv_roi_sample_u8': (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, C.c_int32,
                                     C.c_int32, _P, _P, C.c_int64, _P]),
     'bpv_ring_push': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P]),
-    'bpv_window_preprocess': (C.c_int, [_P, _P, C.POINTER(WindowParams), _P, _P, _P, _P]),
-    'bpv_window_spectrum': (C.c_int, [_P, _P, C.POINTER(WindowParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'bpv_window_workspace_bytes': (C.c_int64, [C.POINTER(WindowParams)]),
+    'bpv_window_preprocess': (C.c_int, [_P, _P, C.POINTER(WindowParams), _P, C.c_int64, _P, _P, _P, _P]),
+    'bpv_spectrum_workspace_bytes': (C.c_int64, [C.POINTER(WindowParams), C.c_int32]),
+    'bpv_window_spectrum': (C.c_int, [_P, _P, C.POINTER(WindowParams), C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     'bpv_window_xcorr': (C.c_int, [_P, _P, C.POINTER(WindowParams), _P, _P, _P, _P, _P, _P, _P]),
     'bpv_butter_sos_design': (C.c_int, [_P, C.c_int32, C.POINTER(WindowParams), _P, _P]),
     'bpv_firls_design': (C.c_int, [_P, C.c_int32, C.POINTER(WindowParams), _P, _P]),

@@ -79,15 +79,18 @@ def make_params(S, R, cap, window, head0, head_step, jobs_per_stream, methods, t
     return p
 
 
-def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None, status=None):
+def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None, status=None, workspace=None):
     """F2 (signal_processor.py:196-245).  Returns proc_x, proc_y f64 [J,R,window], status i32 [J,R]."""
     J = p.S * p.jobs_per_stream
     dev = ring_y.device
     proc_x = torch.empty((J, p.R, p.window), dtype=torch.float64, device=dev) if proc_x is None else proc_x
     proc_y = torch.empty((J, p.R, p.window), dtype=torch.float64, device=dev) if proc_y is None else proc_y
     status = torch.empty((J, p.R), dtype=torch.int32, device=dev) if status is None else status
-    check(lib().bpv_window_preprocess(ptr(ring_t), ptr(ring_y), C.byref(p), ptr(proc_x), ptr(proc_y), ptr(status),
-                                      stream_handle()), 'bpv_window_preprocess')
+    need = lib().bpv_window_workspace_bytes(C.byref(p))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib().bpv_window_preprocess(ptr(ring_t), ptr(ring_y), C.byref(p), ptr(workspace), workspace.numel(),
+                                      ptr(proc_x), ptr(proc_y), ptr(status), stream_handle()), 'bpv_window_preprocess')
     return proc_x, proc_y, status
 
 
@@ -99,7 +102,7 @@ def max_bins(p: WindowParams) -> int:
     return min(256, p.window) // 2 + 1
 
 
-def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
+def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=None, workspace=None):
     """F3 + HR peak (signal_processor.py:248-277, 310).  Returns dict(freqs, mags f32 [J,R,max_bins] | None,
     num_bins i32, peak_idx i32, peak_freq f64, peak_mag f64 [J,R])."""
     J = p.S * p.jobs_per_stream
@@ -115,7 +118,11 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
     o.setdefault('peak_idx', torch.empty((J, p.R), dtype=torch.int32, device=dev))
     o.setdefault('peak_freq', torch.empty((J, p.R), dtype=torch.float64, device=dev))
     o.setdefault('peak_mag', torch.empty((J, p.R), dtype=torch.float64, device=dev))
-    check(lib().bpv_window_spectrum(ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(o['freqs']), ptr(o['mags']),
+    need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if not store else 0
+    if need and (workspace is None or workspace.numel() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib().bpv_window_spectrum(ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
+                                    ptr(o['freqs']), ptr(o['mags']),
                                     ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']),
                                     stream_handle()), 'bpv_window_spectrum')
     return o

@@ -20,7 +20,7 @@ def timestamps(rng, n, fps, irregular=False, drop=0.0, origin=None):
     removed; per-stream origin U(0,1000) s when `origin` is None and irregular."""
     if not irregular:
         return (np.arange(n) + 1.0) / fps + (0.0 if origin is None else origin)
-    m = int(np.ceil(n / max(1e-9, 1.0 - drop))) + 8
+    m = int(np.ceil(1.25 * n / max(1e-9, 1.0 - drop))) + 32
     t = np.cumsum((1.0 / fps) * (1.0 + rng.uniform(-0.3, 0.3, m)))
     keep = rng.uniform(size=m) >= drop
     t = t[keep][:n]

@@ -14,3 +14,16 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int bpv_version(void) { return BPV_VERSION; }
 extern "C" const char* bpv_last_error(void) { return bpv::g_err; }
+
+// L2 -> DRAM fetch granularity hint (32/64/128 B).  ROI rows are short, unaligned spans: a smaller
+// granularity cuts the DRAM over-fetch around every row.  Device-wide limit of the primary context.
+extern "C" int bpv_set_l2_fetch_granularity(int bytes) {
+  cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+  if (e != cudaSuccess) { bpv::set_error("cudaDeviceSetLimit(L2 fetch granularity): %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+extern "C" int bpv_get_l2_fetch_granularity(void) {
+  size_t v = 0;
+  if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) return -1;
+  return (int)v;
+}

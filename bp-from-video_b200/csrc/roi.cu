@@ -7,6 +7,7 @@
 // bytes whose channel phase depends on its offset from the row's first pixel; the three channel
 // sums come from 12 dp4a against constant 0/1 byte selectors and are rotated by the phase.
 // Head/tail vectors are byte-masked.  Integer partials are reduced with warp shuffles (uint64).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bpv {
@@ -31,9 +32,21 @@ __device__ __forceinline__ void py_slice(int a, int b, int L, int& s, int& e) {
   s = (int)aa; e = (int)bb;
 }
 
+template <int MODE>
+__device__ __forceinline__ uint4 ld_v4(const void* p) {
+  uint4 v;
+  if (MODE == 0) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (MODE == 1) asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (MODE == 2) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (MODE == 3) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (MODE == 4) asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
@@ -150,6 +163,141 @@ __global__ void __launch_bounds__(256) roi_sample_kernel(const RoiArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (row_stride % 16 == 0, i.e. every standard frame width): the 16-byte alignment offset
+// of a ROI row is the same for all rows, so a thread that always visits the same vector column
+// has a loop-invariant channel phase and head/tail mask.  Both are folded into per-thread dp4a
+// selector registers before the row loop; the loop body is pointer bump + LDG.128 + 8 (12) dp4a.
+// Threads are laid out (rows_per_step x vectors_per_row) over the group.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sel_word(int q, int j) {  // selector q, word j (see channel_sums)
+  const int k = (q + j) % 3;
+  return k == 0 ? 0x01000001u : (k == 1 ? 0x00010000u : 0x00000100u);
+}
+
+template <int GROUP, int UNROLL, bool WANT_SUMS, int LDMODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) roi_rows_kernel(const RoiArgs a) {
+  constexpr int GROUPS_PER_BLOCK = 256 / GROUP;
+  constexpr int WARPS_PER_GROUP = GROUP / 32;
+  const int grp = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+  const long long roi = (long long)blockIdx.x * GROUPS_PER_BLOCK + grp;
+  const bool live = roi < a.num_rois;
+
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  bool has_box = false;
+  uintptr_t base = 0;
+  if (live) {
+    const int4 b = __ldg(reinterpret_cast<const int4*>(a.boxes) + roi);
+    has_box = b.x != BPV_NO_BOX;
+    if (has_box) {
+      py_slice(b.x, b.z, a.W, xs, xe);
+      py_slice(b.y, b.w, a.H, ys, ye);
+      const long long f = roi / a.R;
+      const uint8_t* fp = a.frame_ptrs ? a.frame_ptrs[f] : a.frames + f * a.frame_stride;
+      base = reinterpret_cast<uintptr_t>(fp) + (uintptr_t)((long long)ys * a.row_stride + (long long)xs * 3);
+    }
+  }
+  const int nrows = ye - ys, row_bytes = (xe - xs) * 3;
+  uint32_t sG = 0, sT = 0, sB = 0;  // per-thread partial sums: green, all bytes, blue
+  if (nrows > 0 && row_bytes > 0) {
+    const int off = (int)(base & 15);
+    const int vpr = (off + row_bytes + 15) >> 4;  // aligned vectors per row (same for every row)
+    int rps, r0, v0;
+    if (vpr >= GROUP) { rps = 1; r0 = 0; v0 = gt; }
+    else { rps = GROUP / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
+    const long long step = (long long)rps * a.row_stride;
+    for (int v = v0; v < vpr; v += GROUP) {
+      const int rel = 16 * v - off;
+      const int lo = rel < 0 ? -rel : 0;
+      const int e = row_bytes - rel;
+      const int hi = e < 16 ? e : 16;
+      const int ph = (rel + 15) % 3;
+      uint32_t cT[4], cG[4], cB[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = byte_mask(lo - 4 * j, hi - 4 * j);
+        cT[j] = m & 0x01010101u;
+        cG[j] = m & sel_word((ph + 2) % 3, j);
+        cB[j] = m & sel_word(ph, j);
+      }
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(base - off) + (long long)r0 * a.row_stride + 16 * v;
+      for (int r = r0; r < nrows; r += rps * UNROLL) {
+        uint4 d[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (r + u * rps < nrows) d[u] = ld_v4<LDMODE>(p + u * step);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (r + u * rps < nrows) {
+            sT = __dp4a(d[u].x, cT[0], __dp4a(d[u].y, cT[1], __dp4a(d[u].z, cT[2], __dp4a(d[u].w, cT[3], sT))));
+            sG = __dp4a(d[u].x, cG[0], __dp4a(d[u].y, cG[1], __dp4a(d[u].z, cG[2], __dp4a(d[u].w, cG[3], sG))));
+            if (WANT_SUMS)
+              sB = __dp4a(d[u].x, cB[0], __dp4a(d[u].y, cB[1], __dp4a(d[u].z, cB[2], __dp4a(d[u].w, cB[3], sB))));
+          }
+        }
+        p += UNROLL * step;
+      }
+    }
+  }
+
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(xe - xs);
+  unsigned long long tG, tT, tB = 0;
+  // 32-bit shuffles are enough while 3*255*N fits (group-uniform choice: N is per ROI; a warp never
+  // straddles ROIs with GROUP >= 32)
+  if (N < 5600000ull) {
+    tG = warp_sum<uint32_t>(sG); tT = warp_sum<uint32_t>(sT);
+    if (WANT_SUMS) tB = warp_sum<uint32_t>(sB);
+  } else {
+    tG = warp_sum_u64(sG); tT = warp_sum_u64(sT);
+    if (WANT_SUMS) tB = warp_sum_u64(sB);
+  }
+  if (WARPS_PER_GROUP > 1) {
+    __shared__ unsigned long long part[8][3];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { part[wid][0] = tG; part[wid][1] = tT; part[wid][2] = tB; }
+    __syncthreads();
+    if (gt == 0) {
+      tG = tT = tB = 0;
+      const int w0 = grp * WARPS_PER_GROUP;
+#pragma unroll
+      for (int w = 0; w < WARPS_PER_GROUP; ++w) { tG += part[w0 + w][0]; tT += part[w0 + w][1]; tB += part[w0 + w][2]; }
+    }
+  }
+  if (live && gt == 0) {
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tT - tG - tB; o.w = N;
+      *reinterpret_cast<ulonglong4*>(a.out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (a.mode == BPV_GREEN) val = (double)tG / (double)N;
+    // 2G - B - R + 2N = 3G - (B+G+R) + 2N
+    else val = (double)(3 * (long long)tG - (long long)tT + 2 * (long long)N) / (double)(4 * N);
+    a.out_value[roi] = val;
+  }
+}
+
+template <int GROUP>
+static void launch_rows(const RoiArgs& a, unsigned grid, cudaStream_t st) {
+  // LDMODE 5 = ld.global.nc.L1::no_allocate.L2::64B: the default L2 fill granule on B200 is the whole
+  // 128-byte line; asking for 64 B cuts the DRAM over-fetch around short unaligned ROI rows from 1.50x
+  // to 1.17x of the algorithmic bytes (ncu dram__bytes_read, profiles/roi_r1_notes.md).
+  if (a.out_sums) roi_rows_kernel<GROUP, 4, true, 5, 4><<<grid, 256, 0, st>>>(a);
+  else roi_rows_kernel<GROUP, 4, false, 5, 4><<<grid, 256, 0, st>>>(a);
+}
+
+// development-only tuning variants (BPV_ROI_VARIANT=<ldmode><unroll><minblocks>, e.g. "084"), GROUP=128
+static bool launch_variant(const RoiArgs& a, unsigned grid, cudaStream_t st) {
+  static const char* v = getenv("BPV_ROI_VARIANT");
+  if (!v || a.out_sums) return false;
+#define V(ld, un, mb) if (v[0] == '0' + ld && v[1] == '0' + un && v[2] == '0' + mb) { roi_rows_kernel<128, un, false, ld, mb><<<grid, 256, 0, st>>>(a); return true; }
+  V(0, 4, 3) V(0, 4, 4) V(0, 8, 3) V(0, 8, 4) V(0, 2, 4) V(0, 2, 6)
+  V(1, 4, 4) V(2, 4, 4) V(3, 4, 4) V(4, 4, 4) V(5, 4, 3) V(5, 8, 4) V(5, 2, 6) V(5, 2, 8) V(5, 4, 6)
+#undef V
+  return false;
+}
+
 }  // namespace bpv
 
 extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
@@ -173,12 +321,16 @@ extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* fr
   const long long n = a.num_rois;
   // threads per ROI: ~>= 4 vectors per thread before widening the group
   const long long px = roi_pixels_hint > 0 ? roi_pixels_hint : 4096;
-  if (px * 3 <= 32 * 16 * 8) {
-    roi_sample_kernel<32, 4><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
-  } else if (px * 3 <= 128 * 16 * 16) {
-    roi_sample_kernel<128, 4><<<(unsigned)((n + 1) / 2), 256, 0, st>>>(a);
-  } else {
-    roi_sample_kernel<256, 4><<<(unsigned)n, 256, 0, st>>>(a);
+  const int g = px * 3 <= 32 * 16 * 8 ? 32 : (px * 3 <= 128 * 16 * 16 ? 128 : 256);
+  const unsigned grid = (unsigned)((n + 256 / g - 1) / (256 / g));
+  if (row_stride_bytes % 16 == 0) {  // fast path: loop-invariant alignment per ROI
+    if (g == 32) launch_rows<32>(a, grid, st);
+    else if (g == 128) { if (!launch_variant(a, grid, st)) launch_rows<128>(a, grid, st); }
+    else launch_rows<256>(a, grid, st);
+  } else {                           // generic path: alignment changes row by row
+    if (g == 32) roi_sample_kernel<32, 4><<<grid, 256, 0, st>>>(a);
+    else if (g == 128) roi_sample_kernel<128, 4><<<grid, 256, 0, st>>>(a);
+    else roi_sample_kernel<256, 4><<<grid, 256, 0, st>>>(a);
   }
   return check_launch("bpv_roi_sample_u8");
 }

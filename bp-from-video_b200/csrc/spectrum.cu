@@ -1,0 +1,465 @@
+// F3 spectra + F4(a) heart-rate peak (SignalProcessor.transform_signal(s) and the get_peaks() that
+// follows it: signal_processor.py:248-277, 310; signal_data.py:65-70).
+//
+//   DFT_RFFT / PGRAM_WELCH  one CTA per signal, float64 direct DFT against a shared-memory twiddle
+//                           table (n <= window, so the whole problem is shared-memory resident);
+//                           argmax fused into the same kernel.
+//   PGRAM_LS                signal x frequency-tile grid.  Coarse pass in fp32: each thread owns one
+//                           frequency, loops over the shared-memory time tile, phase reduced to
+//                           [-0.5, 0.5) turns with an exact two-float product, MUFU sin/cos, six
+//                           running sums (C, S, CC, CS, YC, YS); the tau rotation and the
+//                           floating-mean corrections are applied once per frequency in closed form
+//                           (scipy/signal/_spectral_py.py:284-349).  Peak pass: candidates within
+//                           LS_DELTA of the fp32 maximum are re-evaluated in float64 with scipy's own
+//                           two-pass formulation so that the winning bin is decided in float64.
+#include "filters.cuh"
+
+namespace bpv {
+
+constexpr float LS_DELTA = 1.0e-4f;     // candidate band below the fp32 maximum (PSD is in [0, 1])
+constexpr int LS_SMALL_N = 24;          // below this every bin is evaluated in float64
+constexpr double EPSNEG = 1.1102230246251565e-16;  // np.finfo(float64).epsneg
+
+__device__ __forceinline__ double shfl_dd(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+struct SigInfo { int n, m; double fs, xfirst; };
+
+// Block-cooperative gather of one processed signal: compacts samples with finite y into ys[] (and their
+// x into xs[] when xs != nullptr).  Returns n (finite y), m (finite x), fs = (m-1)/(x_last - x_first).
+// Signal.get_fs (signal_data.py:55-58) uses the finite-x mask v.
+__device__ SigInfo gather_signal(const double* __restrict__ px, const double* __restrict__ py, int W,
+                                 double* xs, double* ys, int* s_cnt /* >= 4 ints smem */, double* s_d /* >= 2 doubles */) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0x7fffffff; s_cnt[3] = -1; }
+  __syncthreads();
+  // ordered compaction: one warp walks the window (window <= a few thousand samples)
+  if (tid < 32) {
+    int n = 0, m = 0, kfirst = 0x7fffffff, klast = -1;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k0 = 0; k0 < W; k0 += 32) {
+      const int k = k0 + lane;
+      double x = nan_f64(), y = nan_f64();
+      if (k < W) { x = px[k]; y = py[k]; }
+      const bool fx = isfinite(x), fy = isfinite(y);
+      const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+      if (fy) {
+        const int idx = n + __popc(by & lt);
+        ys[idx] = y;
+        if (xs) xs[idx] = x;
+      }
+      if (bx) {
+        if (kfirst == 0x7fffffff) kfirst = k0 + __ffs(bx) - 1;
+        klast = k0 + 31 - __clz(bx);
+      }
+      n += __popc(by); m += __popc(bx);
+    }
+    if (lane == 0) {
+      s_cnt[0] = n; s_cnt[1] = m;
+      s_d[0] = m >= 1 ? px[kfirst] : nan_f64();
+      s_d[1] = m >= 1 ? px[klast] : nan_f64();
+    }
+  }
+  __syncthreads();
+  SigInfo si;
+  si.n = s_cnt[0]; si.m = s_cnt[1];
+  si.xfirst = s_d[0];
+  si.fs = si.m >= 2 ? 1.0 / ((s_d[1] - s_d[0]) / (double)(si.m - 1)) : nan_f64();
+  return si;
+}
+
+// Block argmax with numpy's first-max rule over finite values; also counts finite entries.
+// vals in shared/global memory (double).  Result broadcast through smem.
+struct Peak { int idx; double val; int nfinite; };
+__device__ Peak block_argmax(const double* vals, int F, double* s_val, int* s_idx) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  double bv = -INFINITY; int bi = 0x7fffffff, cnt = 0;
+  for (int k = tid; k < F; k += blockDim.x) {
+    const double v = vals[k];
+    if (isfinite(v)) { ++cnt; if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; } }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; s_idx[32 + wid] = cnt; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < nw; ++w) {
+      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+      cnt += s_idx[32 + w];
+    }
+    s_val[0] = bv; s_idx[0] = bi; s_idx[32] = cnt;
+  }
+  __syncthreads();
+  Peak p; p.val = s_val[0]; p.idx = s_idx[0]; p.nfinite = s_idx[32];
+  __syncthreads();
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DFT_RFFT and PGRAM_WELCH: one CTA per signal.
+// smem doubles: ys[W] | tw_c[N] | tw_s[N] | z[N] | mags[F]   (N = n or nperseg <= W, F <= W/2+1)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __restrict__ proc_x,
+                                                             const double* __restrict__ proc_y,
+                                                             const bpv_window_params p, int max_bins,
+                                                             float* __restrict__ spec_f, float* __restrict__ spec_mag,
+                                                             int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
+                                                             double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_cnt[4];
+  __shared__ double s_d[2];
+  __shared__ double s_val[33];
+  __shared__ int s_idx[64];
+  const int W = p.window, tid = threadIdx.x;
+  const long long sig = blockIdx.x;
+  double* ys = sm;
+  double* twc = ys + W;
+  double* tws = twc + W;
+  double* z = tws + W;
+  double* mags = z + W;
+  const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, nullptr, ys, s_cnt, s_d);
+  const int n = si.n;
+  if (!(n >= 2 && isfinite(si.fs))) {        // guard signal_processor.py:252 -> empty spectrum
+    if (tid == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    return;
+  }
+  const double fs = si.fs;
+  int N, F;
+  if (p.transform == BPV_DFT_RFFT) {
+    // mags = 2*|rfft(y)|/n, freqs = rfftfreq(n, 1/fs)   (signal_processor.py:254-258)
+    N = n; F = n / 2 + 1;
+    for (int i = tid; i < N; i += blockDim.x) sincospi(2.0 * (double)i / (double)N, &tws[i], &twc[i]);
+    __syncthreads();
+    for (int k = tid; k < F; k += blockDim.x) {
+      double re = 0.0, im = 0.0;
+      int idx = 0;
+      for (int j = 0; j < N; ++j) {
+        const double v = ys[j];
+        re = fma(v, twc[idx], re);
+        im = fma(-v, tws[idx], im);
+        idx += k; if (idx >= N) idx -= N;
+      }
+      mags[k] = 2.0 * hypot(re, im) / (double)N;
+    }
+  } else {
+    // scipy.signal.welch(y, fs) defaults (signal_processor.py:260): periodic Hann, nperseg=min(256,n),
+    // 50 % overlap, per-segment mean removal, one-sided density, mean over segments.
+    N = n < 256 ? n : 256; F = N / 2 + 1;
+    const int nov = N / 2, hop = N - nov, nseg = (n - nov) / hop;
+    for (int i = tid; i < N; i += blockDim.x) sincospi(2.0 * (double)i / (double)N, &tws[i], &twc[i]);
+    for (int k = tid; k < F; k += blockDim.x) mags[k] = 0.0;
+    __syncthreads();
+    // sum of squared window: w_j = 0.5 - 0.5*cos(2*pi*j/N) = 0.5 - 0.5*twc[j]
+    double sw = 0.0;
+    for (int i = tid; i < N; i += blockDim.x) { const double wj = 0.5 - 0.5 * twc[i]; sw += wj * wj; }
+    const double sumw2 = block_sum(sw, s_val);
+    const double scale = 1.0 / (fs * sumw2);
+    for (int s = 0; s < nseg; ++s) {
+      const double* seg = ys + s * hop;
+      double a = 0.0;
+      for (int i = tid; i < N; i += blockDim.x) a += seg[i];
+      const double mean = block_sum(a, s_val) / (double)N;
+      for (int i = tid; i < N; i += blockDim.x) z[i] = (seg[i] - mean) * (0.5 - 0.5 * twc[i]);
+      __syncthreads();
+      for (int k = tid; k < F; k += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        int idx = 0;
+        for (int j = 0; j < N; ++j) {
+          const double v = z[j];
+          re = fma(v, twc[idx], re);
+          im = fma(-v, tws[idx], im);
+          idx += k; if (idx >= N) idx -= N;
+        }
+        double pw = (re * re + im * im) * scale;
+        const bool dbl = (N % 2 == 0) ? (k >= 1 && k < F - 1) : (k >= 1);
+        if (dbl) pw *= 2.0;
+        mags[k] += pw;
+      }
+      __syncthreads();
+    }
+    for (int k = tid; k < F; k += blockDim.x) mags[k] /= (double)nseg;
+  }
+  __syncthreads();
+  // rfftfreq(N, d=1/fs)[k] = k * (1/(N*d))
+  const double fval = 1.0 / ((double)N * (1.0 / fs));
+  if (spec_mag) {
+    for (int k = tid; k < F && k < max_bins; k += blockDim.x) {
+      spec_f[sig * max_bins + k] = (float)((double)k * fval);
+      spec_mag[sig * max_bins + k] = (float)mags[k];
+    }
+  }
+  const Peak pk = block_argmax(mags, F, s_val, s_idx);
+  if (tid == 0) {
+    num_bins[sig] = F;
+    if (pk.nfinite >= 2) { peak_idx[sig] = pk.idx; peak_freq[sig] = (double)pk.idx * fval; peak_mag[sig] = pk.val; }
+    else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lomb-Scargle
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ls_freq(int k, int F, double fmin, double fmax) {  // np.linspace(fmin, fmax, F)[k]
+  if (F == 1) return fmin;
+  if (k == F - 1) return fmax;
+  const double step = (fmax - fmin) / (double)(F - 1);
+  return __dadd_rn(__dmul_rn((double)k, step), fmin);
+}
+
+// Generalised LS (floating mean, normalised) at one frequency, float64, scipy's two passes.
+// t: times relative to the first sample (the estimator is shift invariant), y: samples, n of them.
+// Executed by one warp; returns the value on every lane.
+__device__ double ls_eval_f64(const double* __restrict__ t, const double* __restrict__ y, int n, double f,
+                              double Y, double YY /* already minus Y*Y */) {
+  const int lane = threadIdx.x & 31;
+  const double w = 1.0 / (double)n;
+  double C = 0, S = 0, CC = 0, CS = 0;
+  for (int j = lane; j < n; j += 32) {
+    double ph = f * t[j];
+    ph -= rint(ph);
+    double s, c;
+    sincospi(2.0 * ph, &s, &c);
+    C += c; S += s; CC = fma(c, c, CC); CS = fma(c, s, CS);
+  }
+  C = warp_sum(C) * w; S = warp_sum(S) * w; CC = warp_sum(CC) * w; CS = warp_sum(CS) * w;
+  double SS = 1.0 - CC;
+  CC -= C * C; SS -= S * S; CS -= C * S;
+  const double tau = 0.5 * atan2(2.0 * CS, CC - SS);
+  const double tau_turns = tau / (2.0 * 3.141592653589793);
+  double YC = 0, YS = 0, C2 = 0, S2 = 0, CC2 = 0;
+  for (int j = lane; j < n; j += 32) {
+    double ph = f * t[j];
+    ph -= rint(ph);
+    ph -= tau_turns;
+    double s, c;
+    sincospi(2.0 * ph, &s, &c);
+    YC = fma(y[j], c, YC); YS = fma(y[j], s, YS);
+    C2 += c; S2 += s; CC2 = fma(c, c, CC2);
+  }
+  YC = warp_sum(YC) * w; YS = warp_sum(YS) * w; C2 = warp_sum(C2) * w; S2 = warp_sum(S2) * w; CC2 = warp_sum(CC2) * w;
+  double SS2 = 1.0 - CC2;
+  YC -= Y * C2; YS -= Y * S2; CC2 -= C2 * C2; SS2 -= S2 * S2;
+  if (CC2 < EPSNEG) CC2 = EPSNEG;
+  if (SS2 < EPSNEG) SS2 = EPSNEG;
+  const double a = YC / CC2, b = YS / SS2;
+  return 2.0 * (a * YC + b * YS) * (0.5 / YY);
+}
+
+// Coarse fp32 pass.  grid = (nsig, ceil(Fmax / 128)), block = 128 threads = 128 frequencies.
+// smem floats: th[W] | tl[W] | yc[W]; doubles for the gather scratch come first.
+__global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+                                                        const bpv_window_params p, int max_bins,
+                                                        float* __restrict__ spec_f, float* __restrict__ psd) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_cnt[4];
+  __shared__ double s_d[2];
+  __shared__ double s_red[33];
+  const int W = p.window, tid = threadIdx.x;
+  const long long sig = blockIdx.x;
+  double* xs = sm;            // [W]
+  double* ys = xs + W;        // [W]
+  float* th = reinterpret_cast<float*>(ys + W);
+  float* tl = th + W;
+  float* yc = tl + W;
+  const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, xs, ys, s_cnt, s_d);
+  const int n = si.n;
+  if (!(n >= 2 && isfinite(si.fs))) return;              // peak kernel reports the empty spectrum
+  const int F = p.ls_num_freqs > 0 ? p.ls_num_freqs : n;
+  if ((int)blockIdx.y * 128 >= F) return;
+  // centre y (floating mean makes this a no-op mathematically; it is what keeps fp32 usable)
+  double a = 0.0;
+  for (int j = tid; j < n; j += blockDim.x) a += ys[j];
+  const double mean = block_sum(a, s_red) / (double)n;
+  double q = 0.0;
+  const double t0 = xs[0];
+  for (int j = tid; j < n; j += blockDim.x) {
+    const double d = ys[j] - mean, t = xs[j] - t0;
+    q = fma(d, d, q);
+    const float hi = (float)t;
+    th[j] = hi; tl[j] = (float)(t - (double)hi); yc[j] = (float)d;
+  }
+  const double YY = block_sum(q, s_red) / (double)n;     // variance (Y = 0 after centring)
+  const int k = blockIdx.y * 128 + tid;
+  if (k >= F) return;
+  const double f = ls_freq(k, F, p.min_freq, p.max_freq);
+  const float fh = (float)f, fl = (float)(f - (double)fh);
+  float C = 0.f, S = 0.f, CC = 0.f, CS = 0.f, YC = 0.f, YS = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const float t_hi = th[j], t_lo = tl[j], yv = yc[j];
+    const float ph = fh * t_hi;
+    const float e1 = fmaf(fh, t_hi, -ph);                 // exact low part of the product
+    const float e2 = fmaf(fh, t_lo, fl * t_hi);
+    const float r = (ph - rintf(ph)) + (e1 + e2);          // phase in turns, [-0.5, 0.5]
+    float s, c;
+    __sincosf(6.283185307179586f * r, &s, &c);
+    C += c; S += s;
+    CC = fmaf(c, c, CC); CS = fmaf(c, s, CS);
+    YC = fmaf(yv, c, YC); YS = fmaf(yv, s, YS);
+  }
+  // closed-form tau rotation + floating-mean corrections, once per frequency, in float64
+  const double w = 1.0 / (double)n;
+  const double dC = C * w, dS = S * w, dCC = CC * w, dCS = CS * w, dYC = YC * w, dYS = YS * w;
+  const double cc0 = dCC - dC * dC, ss0 = (1.0 - dCC) - dS * dS, cs0 = dCS - dC * dS;
+  const double tau = 0.5 * atan2(2.0 * cs0, cc0 - ss0);
+  double st, ct;
+  sincos(tau, &st, &ct);
+  const double YCt = ct * dYC + st * dYS, YSt = ct * dYS - st * dYC;
+  const double Ct = ct * dC + st * dS, St = ct * dS - st * dC;
+  const double CCraw = ct * ct * dCC + 2.0 * ct * st * dCS + st * st * (1.0 - dCC);
+  double CCt = CCraw - Ct * Ct, SSt = (1.0 - CCraw) - St * St;
+  if (CCt < EPSNEG) CCt = EPSNEG;
+  if (SSt < EPSNEG) SSt = EPSNEG;
+  const double pw = 2.0 * (YCt * YCt / CCt + YSt * YSt / SSt) * (0.5 / YY);
+  psd[sig * max_bins + k] = (float)pw;
+  if (spec_f) spec_f[sig * max_bins + k] = (float)f;
+}
+
+// Peak pass: one CTA (128 threads) per signal.  smem doubles: ts[W] | ys[W] | cand_val[max_bins];
+// ints: cand_idx[max_bins].
+__global__ void __launch_bounds__(128) ls_peak_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+                                                      const bpv_window_params p, int max_bins,
+                                                      float* __restrict__ spec_f, float* __restrict__ psd,
+                                                      int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
+                                                      double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_cnt[4];
+  __shared__ double s_d[2];
+  __shared__ double s_val[33];
+  __shared__ int s_idx[64];
+  __shared__ int s_nc;
+  const int W = p.window, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const long long sig = blockIdx.x;
+  double* xs = sm;
+  double* ys = xs + W;
+  double* cval = ys + W;
+  int* cidx = reinterpret_cast<int*>(cval + max_bins);
+  const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, xs, ys, s_cnt, s_d);
+  const int n = si.n;
+  if (!(n >= 2 && isfinite(si.fs))) {
+    if (tid == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    return;
+  }
+  const int F = p.ls_num_freqs > 0 ? p.ls_num_freqs : n;
+  float* row = psd + sig * max_bins;
+  // fp32 maximum over finite bins
+  float bv = -INFINITY; int cnt = 0;
+  for (int k = tid; k < F; k += blockDim.x) { const float v = row[k]; if (isfinite(v)) { ++cnt; bv = fmaxf(bv, v); } }
+  for (int o = 16; o > 0; o >>= 1) { bv = fmaxf(bv, __shfl_xor_sync(0xffffffffu, bv, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if (lane == 0) { s_val[wid] = bv; s_idx[wid] = cnt; }
+  if (tid == 0) s_nc = 0;
+  __syncthreads();
+  bv = s_val[0]; cnt = s_idx[0];
+  for (int w2 = 1; w2 < nw; ++w2) { bv = fmaxf(bv, s_val[w2]); cnt += s_idx[w2]; }
+  __syncthreads();
+  // moments for the float64 evaluation (relative time; Y, YY as scipy Eq. 7 / 10)
+  const double t0 = xs[0];
+  double a = 0.0;
+  for (int j = tid; j < n; j += blockDim.x) a += ys[j];
+  const double Y = block_sum(a, s_val) / (double)n;
+  double q = 0.0;
+  for (int j = tid; j < n; j += blockDim.x) { q = fma(ys[j], ys[j], q); }
+  double YY = block_sum(q, s_val) / (double)n - Y * Y;
+  {  // the centred second moment is better conditioned than YY - Y*Y when DC >> AC
+    double q2 = 0.0;
+    for (int j = tid; j < n; j += blockDim.x) { const double d = ys[j] - Y; q2 = fma(d, d, q2); }
+    YY = block_sum(q2, s_val) / (double)n;
+  }
+  for (int j = tid; j < n; j += blockDim.x) xs[j] -= t0;
+  __syncthreads();
+  // candidate list: every bin for small problems, else bins within LS_DELTA of the fp32 maximum
+  const bool all = n < LS_SMALL_N || cnt < 2;
+  for (int k = tid; k < F; k += blockDim.x) {
+    const float v = row[k];
+    if (all || (isfinite(v) && v >= bv - LS_DELTA)) cidx[atomicAdd(&s_nc, 1)] = k;
+  }
+  __syncthreads();
+  const int nc = s_nc;
+  for (int c = wid; c < nc; c += nw) {
+    const int k = cidx[c];
+    const double v = ls_eval_f64(xs, ys, n, ls_freq(k, F, p.min_freq, p.max_freq), Y, YY);
+    if (lane == 0) { cval[c] = v; row[k] = (float)v; }
+  }
+  __syncthreads();
+  if (all && tid == 0) {   // recount finite bins from the float64 values
+    int c2 = 0;
+    for (int c = 0; c < nc; ++c) c2 += isfinite(cval[c]);
+    s_idx[0] = c2;
+  }
+  __syncthreads();
+  const int nfinite = all ? s_idx[0] : cnt;
+  __syncthreads();
+  // first-max rule in float64 over the candidates (ties -> smallest bin index)
+  double best = -INFINITY; int bi = 0x7fffffff;
+  if (tid == 0) {
+    for (int c = 0; c < nc; ++c) {
+      const double v = cval[c];
+      if (isfinite(v) && (v > best || (v == best && cidx[c] < bi))) { best = v; bi = cidx[c]; }
+    }
+    num_bins[sig] = F;
+    if (nfinite >= 2 && bi != 0x7fffffff) {
+      peak_idx[sig] = bi; peak_freq[sig] = ls_freq(bi, F, p.min_freq, p.max_freq); peak_mag[sig] = best;
+    } else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+  }
+  if (all && spec_f)
+    for (int k = tid; k < F; k += blockDim.x) spec_f[sig * max_bins + k] = (float)ls_freq(k, F, p.min_freq, p.max_freq);
+}
+
+}  // namespace bpv
+
+extern "C" int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins) {
+  if (!p) return -1;
+  if (p->transform != BPV_PGRAM_LS) return 0;
+  return (int64_t)p->S * p->jobs_per_stream * p->R * max_bins * 4;
+}
+
+extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,
+                                   int32_t max_bins, void* workspace, int64_t workspace_bytes,
+                                   float* spec_f, float* spec_mag, int32_t* num_bins,
+                                   int32_t* peak_idx, double* peak_freq, double* peak_mag, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(p && proc_x && proc_y && num_bins && peak_idx && peak_freq && peak_mag, BPV_E_INVALID,
+              "bpv_window_spectrum: NULL pointer");
+  BPV_REQUIRE((spec_f == nullptr) == (spec_mag == nullptr), BPV_E_INVALID, "bpv_window_spectrum: spec_f/spec_mag must both be set or both NULL");
+  BPV_REQUIRE(p->transform == BPV_DFT_RFFT || p->transform == BPV_PGRAM_WELCH || p->transform == BPV_PGRAM_LS, BPV_E_UNSUPPORTED,
+              "bpv_window_spectrum: unknown spectrum transform %d (NotImplementedError, signal_processor.py:268)", p->transform);
+  const int W = p->window;
+  const long long nsig = (long long)p->S * p->jobs_per_stream * p->R;
+  BPV_REQUIRE(W > 0 && nsig > 0 && max_bins > 0, BPV_E_INVALID, "bpv_window_spectrum: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->transform != BPV_PGRAM_LS) {
+    const int need = p->transform == BPV_DFT_RFFT ? W / 2 + 1 : (W < 256 ? W : 256) / 2 + 1;
+    BPV_REQUIRE(!spec_mag || max_bins >= need, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, need);
+    const size_t smem = (size_t)(4 * W + W / 2 + 2) * sizeof(double);
+    BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window %d too large for the dense spectrum kernel", W);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    spectrum_dense_kernel<<<(unsigned)nsig, 128, smem, st>>>(proc_x, proc_y, *p, max_bins, spec_f, spec_mag, num_bins,
+                                                            peak_idx, peak_freq, peak_mag);
+    return check_launch("spectrum_dense_kernel");
+  }
+  const int Fmax = p->ls_num_freqs > 0 ? p->ls_num_freqs : W;
+  BPV_REQUIRE(max_bins >= Fmax, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, Fmax);
+  float* psd = spec_mag;
+  if (!psd) {
+    BPV_REQUIRE(workspace && workspace_bytes >= bpv_spectrum_workspace_bytes(p, max_bins), BPV_E_INVALID,
+                "bpv_window_spectrum: workspace too small (see bpv_spectrum_workspace_bytes)");
+    psd = (float*)workspace;
+  }
+  const size_t smem_c = (size_t)W * (2 * sizeof(double) + 3 * sizeof(float));
+  const size_t smem_p = (size_t)W * 2 * sizeof(double) + (size_t)max_bins * (sizeof(double) + sizeof(int));
+  BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
+  if (smem_c > 48 * 1024) cudaFuncSetAttribute(ls_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  dim3 grid((unsigned)nsig, (Fmax + 127) / 128);
+  ls_coarse_kernel<<<grid, 128, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
+  if (int rc = check_launch("ls_coarse_kernel")) return rc;
+  ls_peak_kernel<<<(unsigned)nsig, 128, smem_p, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd, num_bins, peak_idx, peak_freq, peak_mag);
+  return check_launch("ls_peak_kernel");
+}

@@ -1,0 +1,545 @@
+// F2 — window preprocessing (SignalProcessor.process_signal, signal_processor.py:196-241), batched
+// over window jobs.  One warp per signal (job x ROI); the window lives in that warp's slice of shared
+// memory; everything is float64 (the reference's dtype; fp32 IIR state loses up to 15 % of the
+// peak at 120 fps).  Filters come from the per-job design kernels (filters.cu).
+//
+// Work layout inside a warp
+//   gather      lanes stride the window, ballot/popc-compact valid samples (NaN-aware masks v, w)
+//   diff/detrend lane-strided elementwise + warp-shuffle reductions
+//   interp      lane-strided evaluation with per-lane binary search; the not-a-knot spline's
+//               tridiagonal solve is a serial Thomas sweep on lane 0 (latency hidden by other warps)
+//   sosfiltfilt 16 biquads = 16 lanes of a systolic cascade: lane s owns section s, samples flow
+//               lane to lane by __shfl_up (one sample enters per step), forward then backward
+//   FIR filtfilt lane-strided direct convolution; only the part of the padded signal that reaches the
+//               cropped output is computed
+#include "filters.cuh"
+
+namespace bpv {
+
+int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* sos_out, cudaStream_t st);
+int launch_job_firls(const double* ring_t, const bpv_window_params& p, double* taps_out, cudaStream_t st);
+int check_filter_params(const bpv_window_params* p, const char* who);
+
+struct PreLayout {        // per-warp shared-memory plan, in bytes
+  int yv, xv, posv, posb, buf0, buf1, coef, total;
+  int buf_len;            // doubles in buf0 / buf1
+};
+
+__host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
+  bool interp = false, cubic = false, butter = false, fir = false;
+  for (int i = 0; i < p.num_methods; ++i) {
+    const int m = p.methods[i];
+    interp |= (m == BPV_INTERP_LINEAR || m == BPV_INTERP_CUBIC);
+    cubic |= m == BPV_INTERP_CUBIC;
+    butter |= m == BPV_FILTER_BUTTER;
+    fir |= m == BPV_FILTER_FIR;
+  }
+  const int W = p.window;
+  int pad = 0;
+  if (butter) pad = 3 * (2 * p.butter_order + 1);
+  if (fir && 3 * p.fir_taps > pad) pad = 3 * p.fir_taps;
+  if (pad > W - 1) pad = W - 1 > 0 ? W - 1 : 0;
+  PreLayout L;
+  L.buf_len = W + 2 * pad;
+  int o = 0;
+  L.yv = o; o += W * 8;
+  L.xv = o; o += interp ? W * 8 : 0;
+  L.buf0 = o; o += (butter || fir || interp) ? L.buf_len * 8 : 0;
+  L.buf1 = o; o += (fir || cubic) ? L.buf_len * 8 : 0;
+  L.coef = o; o += (butter || fir) ? 256 * 8 : 0;
+  L.posv = o; o += ((W * 2 + 7) / 8) * 8;
+  L.posb = o; o += interp ? ((W * 2 + 7) / 8) * 8 : 0;
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+// ---------------------------------------------------------------------------------------------
+struct Warp {
+  int lane;
+  double *yv, *xv, *buf0, *buf1, *coef;
+  unsigned short *posv, *posb;
+  int n, m;            // valid (finite y) / block (finite x) counts
+  double xfirst, xlast;
+  bool grid;           // x[block] has been replaced by the uniform grid (after an INTERP_*)
+};
+
+__device__ void diff1(Warp& w) {  // np.diff(y, n=1, prepend=y[0])  (signal_processor.py:203)
+  for (int c = (w.n - 1) / 32; c >= 0; --c) {
+    const int i = c * 32 + w.lane;
+    double v = 0.0;
+    if (i < w.n && i > 0) v = w.yv[i] - w.yv[i - 1];
+    __syncwarp();
+    if (i < w.n) w.yv[i] = v;
+    __syncwarp();
+  }
+}
+
+__device__ void diff2(Warp& w) {  // np.diff(y, n=2, prepend=y[:2])  (signal_processor.py:205)
+  const double y0 = w.yv[0], y1 = w.yv[1];
+  __syncwarp();
+  for (int c = (w.n - 1) / 32; c >= 0; --c) {
+    const int i = c * 32 + w.lane;
+    double v = 0.0;
+    if (i < w.n) {
+      // z = [y0, y1, y0, y1, y2, ...];  out[i] = (z[i+2]-z[i+1]) - (z[i+1]-z[i])
+      const double z2 = w.yv[i];
+      const double z1 = i >= 1 ? w.yv[i - 1] : y1;
+      const double z0 = i >= 2 ? w.yv[i - 2] : (i == 1 ? y1 : y0);
+      v = (z2 - z1) - (z1 - z0);
+    }
+    __syncwarp();
+    if (i < w.n) w.yv[i] = v;
+    __syncwarp();
+  }
+}
+
+__device__ void detrend_const(Warp& w) {  // scipy.signal.detrend(type='constant')
+  double s = 0.0;
+  for (int i = w.lane; i < w.n; i += 32) s += w.yv[i];
+  const double mean = warp_sum(s) / (double)w.n;
+  for (int i = w.lane; i < w.n; i += 32) w.yv[i] -= mean;
+  __syncwarp();
+}
+
+__device__ void detrend_linear(Warp& w) {
+  // scipy.signal.detrend(type='linear'): least squares of y on [i/N, 1], i = 1..N (sample index, not
+  // time; scipy/signal/_signaltools.py:4307-4314), solved in centred closed form.
+  const double N = (double)w.n;
+  double s = 0.0;
+  for (int i = w.lane; i < w.n; i += 32) s += w.yv[i];
+  const double ybar = warp_sum(s) / N;
+  const double ubar = (N + 1.0) / (2.0 * N);
+  double sxy = 0.0, sxx = 0.0;
+  for (int i = w.lane; i < w.n; i += 32) {
+    const double du = (double)(i + 1) / N - ubar;
+    sxy += du * (w.yv[i] - ybar);
+    sxx += du * du;
+  }
+  sxy = warp_sum(sxy); sxx = warp_sum(sxx);
+  const double slope = sxx > 0.0 ? sxy / sxx : 0.0;
+  for (int i = w.lane; i < w.n; i += 32) {
+    const double du = (double)(i + 1) / N - ubar;
+    w.yv[i] = (w.yv[i] - ybar) - slope * du;
+  }
+  __syncwarp();
+}
+
+// np.linspace(xfirst, xlast, m)[i] (numpy/_core/function_base.py): i*step + start, last = stop
+__device__ __forceinline__ double grid_x(const Warp& w, int i, double step) {
+  if (i == w.m - 1 && w.m > 1) return w.xlast;
+  return __dadd_rn(__dmul_rn((double)i, step), w.xfirst);
+}
+
+// largest j in [0, n-1] with xs[j] <= x (caller guarantees xs[0] <= x)
+__device__ __forceinline__ int bsearch_le(const double* xs, int n, double x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xs[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ void finish_interp(Warp& w, double step) {
+  // x[block], y[block] = grid, interpolated; valid = block  (signal_processor.py:209-210, 216-217)
+  __syncwarp();
+  for (int i = w.lane; i < w.m; i += 32) {
+    w.yv[i] = w.buf0[i];
+    w.xv[i] = grid_x(w, i, step);
+    w.posv[i] = w.posb[i];
+  }
+  w.n = w.m;
+  w.grid = true;
+  __syncwarp();
+}
+
+__device__ void interp_linear(Warp& w) {  // np.interp(linspace(...), x[valid], y[valid])
+  const double step = (w.xlast - w.xfirst) / (double)(w.m - 1);
+  const int n = w.n;
+  for (int i = w.lane; i < w.m; i += 32) {
+    const double xi = grid_x(w, i, step);
+    double r;
+    if (xi > w.xv[n - 1]) r = w.yv[n - 1];
+    else if (xi < w.xv[0]) r = w.yv[0];
+    else {
+      const int j = bsearch_le(w.xv, n, xi);
+      if (j == n - 1 || w.xv[j] == xi) r = w.yv[j];
+      else {
+        const double slope = (w.yv[j + 1] - w.yv[j]) / (w.xv[j + 1] - w.xv[j]);
+        r = __dadd_rn(__dmul_rn(slope, xi - w.xv[j]), w.yv[j]);
+      }
+    }
+    w.buf0[i] = r;
+  }
+  finish_interp(w, step);
+}
+
+// scipy.interpolate.CubicSpline(x, y) (not-a-knot, extrapolate) evaluated on the grid
+// (scipy/interpolate/_cubic.py:795-963; PPoly evaluation order of _ppoly.evaluate).
+// Returns false if x is not strictly increasing (the reference raises ValueError).
+__device__ bool interp_cubic(Warp& w) {
+  const int n = w.n;
+  const double* x = w.xv;
+  const double* y = w.yv;
+  int bad = 0;
+  for (int i = w.lane; i + 1 < n; i += 32) bad |= !(x[i + 1] - x[i] > 0.0);
+  if (__any_sync(0xffffffffu, bad)) return false;
+  double* cp = w.buf0;   // Thomas scratch, later the evaluation output
+  double* s = w.buf1;    // knot slopes
+  if (w.lane == 0) {
+    if (n == 2) {
+      s[0] = s[1] = (y[1] - y[0]) / (x[1] - x[0]);
+    } else if (n == 3) {
+      const double dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+      const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
+      const double s1 = (dx0 * sl1 + dx1 * sl0) / (dx0 + dx1);   // parabola through the 3 points
+      s[1] = s1; s[0] = 2.0 * sl0 - s1; s[2] = 2.0 * sl1 - s1;
+    } else {
+      double dxp = x[1] - x[0], slp = (y[1] - y[0]) / dxp;      // dx[i-1], slope[i-1]
+      double dxc = x[2] - x[1], slc = (y[2] - y[1]) / dxc;      // dx[i],   slope[i]
+      {  // row 0: dx1*s0 + (x2-x0)*s1 = ((dx0+2d)*dx1*sl0 + dx0^2*sl1)/d
+        const double d = x[2] - x[0];
+        const double diag = dxc, up = d;
+        const double rhs = ((dxp + 2.0 * d) * dxc * slp + dxp * dxp * slc) / d;
+        cp[0] = up / diag;
+        s[0] = rhs / diag;
+      }
+      for (int i = 1; i <= n - 2; ++i) {
+        // dx[i]*s[i-1] + 2(dx[i-1]+dx[i])*s[i] + dx[i-1]*s[i+1] = 3(dx[i]*sl[i-1] + dx[i-1]*sl[i])
+        const double lo = dxc, diag = 2.0 * (dxp + dxc), up = dxp;
+        const double rhs = 3.0 * (dxc * slp + dxp * slc);
+        const double den = diag - lo * cp[i - 1];
+        cp[i] = up / den;
+        s[i] = (rhs - lo * s[i - 1]) / den;
+        if (i < n - 2) {
+          dxp = dxc; slp = slc;
+          dxc = x[i + 2] - x[i + 1];
+          slc = (y[i + 2] - y[i + 1]) / dxc;
+        }
+      }
+      {  // last row: (x[n-1]-x[n-3])*s[n-2] + dx[n-3]*s[n-1] = (dx[n-2]^2*sl[n-3] + (2d+dx[n-2])*dx[n-3]*sl[n-2])/d
+        const double d = x[n - 1] - x[n - 3];
+        const double lo = d, diag = dxp;   // dxp = dx[n-3], dxc = dx[n-2], slp = sl[n-3], slc = sl[n-2]
+        const double rhs = (dxc * dxc * slp + (2.0 * d + dxc) * dxp * slc) / d;
+        const double den = diag - lo * cp[n - 2];
+        s[n - 1] = (rhs - lo * s[n - 2]) / den;
+      }
+      for (int i = n - 2; i >= 0; --i) s[i] -= cp[i] * s[i + 1];
+    }
+  }
+  __syncwarp();
+  const double step = (w.xlast - w.xfirst) / (double)(w.m - 1);
+  for (int i = w.lane; i < w.m; i += 32) {
+    const double xi = grid_x(w, i, step);
+    int j;
+    if (xi < x[0]) j = 0;
+    else if (xi >= x[n - 1]) j = n - 2;
+    else j = bsearch_le(x, n, xi);
+    const double dxj = x[j + 1] - x[j];
+    const double slj = (y[j + 1] - y[j]) / dxj;
+    const double t = (s[j] + s[j + 1] - 2.0 * slj) / dxj;
+    const double c0 = t / dxj, c1 = (slj - s[j]) / dxj - t, c2 = s[j], c3 = y[j];
+    const double u = xi - x[j];
+    double res = c3, z = u;            // sum of c[k]*u^k in increasing powers, as _ppoly.evaluate_poly1
+    res = __dadd_rn(res, __dmul_rn(c2, z)); z = __dmul_rn(z, u);
+    res = __dadd_rn(res, __dmul_rn(c1, z)); z = __dmul_rn(z, u);
+    res = __dadd_rn(res, __dmul_rn(c0, z));
+    cp[i] = res;
+  }
+  finish_interp(w, step);
+  return true;
+}
+
+// odd extension (scipy.signal._arraytools.odd_ext) of yv[0..n) by p into ext[0..n+2p)
+__device__ void odd_ext(const Warp& w, double* ext, int p) {
+  const int n = w.n, L = n + 2 * p;
+  const double y0 = w.yv[0], yl = w.yv[n - 1];
+  for (int i = w.lane; i < L; i += 32) {
+    double v;
+    if (i < p) v = 2.0 * y0 - w.yv[p - i];
+    else if (i < p + n) v = w.yv[i - p];
+    else v = 2.0 * yl - w.yv[n - 2 - (i - p - n)];
+    ext[i] = v;
+  }
+  __syncwarp();
+}
+
+// scipy.signal.sosfiltfilt(sos, y, padlen) (scipy/signal/_signaltools.py:5091-5203): odd extension,
+// sosfilt_zi steady state, forward + backward DF2T cascade (Cython _sosfilt), crop.
+__device__ void sos_filtfilt(Warp& w, const double* __restrict__ sos_g, int N) {
+  double* sos = w.coef;            // [N*6]
+  double* zi = w.coef + 6 * MAX_SOS;  // [N*2]
+  for (int i = w.lane; i < N * 6; i += 32) sos[i] = sos_g[i];
+  __syncwarp();
+  int nb0 = 0, na0 = 0;
+  if (w.lane == 0) {
+    // sosfilt_zi: zi[s] = scale * lfilter_zi(b, a); scale *= sum(b)/sum(a)   (:4520-4541)
+    double scale = 1.0;
+    for (int s = 0; s < N; ++s) {
+      const double* c = sos + 6 * s;
+      const double B0 = c[1] - c[4] * c[0], B1 = c[2] - c[5] * c[0];
+      const double z0 = (B0 + B1) / (1.0 + c[4] + c[5]);
+      zi[2 * s] = scale * z0;
+      zi[2 * s + 1] = scale * (B1 - c[5] * z0);
+      scale *= (c[0] + c[1] + c[2]) / (1.0 + c[4] + c[5]);
+    }
+  }
+  for (int s = 0; s < N; ++s) { nb0 += sos[6 * s + 2] == 0.0; na0 += sos[6 * s + 5] == 0.0; }
+  __syncwarp();
+  // padlen as signal_processor.py:227-228
+  const int dpl = 3 * (2 * N + 1 - (nb0 < na0 ? nb0 : na0));
+  const int n = w.n, p = n <= dpl ? n - 1 : dpl;
+  const int L = n + 2 * p;
+  double* ext = w.buf0;
+  odd_ext(w, ext, p);
+
+  const int s = w.lane;
+  const bool sec = s < N;
+  const double b0 = sec ? sos[6 * s] : 0, b1 = sec ? sos[6 * s + 1] : 0, b2 = sec ? sos[6 * s + 2] : 0;
+  const double a1 = sec ? sos[6 * s + 4] : 0, a2 = sec ? sos[6 * s + 5] : 0;
+  const double zi0 = sec ? zi[2 * s] : 0, zi1 = sec ? zi[2 * s + 1] : 0;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0 runs over ext[0..L), pass 1 over the reversed forward output, both in place
+    const double x0 = pass == 0 ? ext[0] : ext[L - 1];
+    double z0 = zi0 * x0, z1 = zi1 * x0;
+    double prev_out = 0.0;
+    double nxt = pass == 0 ? ext[0] : ext[L - 1];  // software-prefetched input of lane 0
+    __syncwarp();
+    for (int t = 0; t < L + N - 1; ++t) {
+      const double from_prev = shfl_up_d(prev_out, 1);
+      double xc = s == 0 ? nxt : from_prev;
+      if (s == 0 && t + 1 < L) nxt = pass == 0 ? ext[t + 1] : ext[L - 2 - t];
+      const int i = t - s;
+      if (sec && i >= 0 && i < L) {
+        const double xn = b0 * xc + z0;
+        z0 = b1 * xc - a1 * xn + z1;
+        z1 = b2 * xc - a2 * xn;
+        prev_out = xn;
+        if (s == N - 1) ext[pass == 0 ? i : L - 1 - i] = xn;
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = w.lane; i < n; i += 32) w.yv[i] = ext[p + i];
+  __syncwarp();
+}
+
+// scipy.signal.filtfilt(b, 1.0, y, padlen) for an FIR b (scipy/signal/_signaltools.py:4893-4924):
+// odd extension, zi = lfilter_zi(b, [1]) (suffix sums of b[1:]), forward, backward, crop.
+// Only forward outputs that can reach the cropped result are evaluated.
+__device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) {
+  double* b = w.coef;          // [T]
+  double* zi = w.coef + 128;   // [T-1]
+  for (int i = w.lane; i < T; i += 32) b[i] = taps_g[i];
+  __syncwarp();
+  if (w.lane == 0) {
+    double acc = 0.0;
+    for (int i = T - 2; i >= 0; --i) { acc += b[i + 1]; zi[i] = acc; }
+  }
+  __syncwarp();
+  const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
+  const int L = n + 2 * p;
+  double* ext = w.buf0;
+  double* F = w.buf1;
+  odd_ext(w, ext, p);
+  const double x0 = ext[0];
+  // forward outputs needed: F[p .. fb], plus F[L-1] when the backward zi term survives the crop
+  const int fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);
+  const bool need_y0 = p < T - 1;
+  for (int i0 = p; i0 <= fb; i0 += 32) {
+    const int i = i0 + w.lane;
+    if (i <= fb) {
+      const int kmax = i < T - 1 ? i : T - 1;
+      double acc = i < T - 1 ? zi[i] * x0 : 0.0;
+      for (int k = 0; k <= kmax; ++k) acc = fma(b[k], ext[i - k], acc);
+      F[i] = acc;
+    }
+  }
+  if (need_y0 && fb < L - 1 && w.lane == 0) {
+    const int i = L - 1;
+    const int kmax = i < T - 1 ? i : T - 1;
+    double acc = i < T - 1 ? zi[i] * x0 : 0.0;
+    for (int k = 0; k <= kmax; ++k) acc = fma(b[k], ext[i - k], acc);
+    F[i] = acc;
+  }
+  __syncwarp();
+  const double y0 = F[L - 1 < fb || need_y0 ? L - 1 : fb];  // only used when need_y0
+  // backward: out[m] = sum_k b[k] * F[p+m+k] (+ zi[i]*y0 for i = L-1-p-m < T-1)
+  for (int m0 = 0; m0 < n; m0 += 32) {
+    const int m = m0 + w.lane;
+    if (m < n) {
+      const int i = L - 1 - p - m;
+      const int kmax = i < T - 1 ? i : T - 1;
+      double acc = i < T - 1 ? zi[i] * y0 : 0.0;
+      for (int k = 0; k <= kmax; ++k) acc = fma(b[k], F[p + m + k], acc);
+      w.yv[m] = acc;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __restrict__ ring_t,
+                                                                const double* __restrict__ ring_y,
+                                                                const bpv_window_params p, const PreLayout L,
+                                                                const double* __restrict__ sos_ws,
+                                                                const double* __restrict__ taps_ws,
+                                                                double* __restrict__ proc_x, double* __restrict__ proc_y,
+                                                                int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long sig = (long long)blockIdx.x * wpb + wib;       // job * R + r
+  const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
+  if (sig >= nsig) return;
+  unsigned char* sm = smem_raw + (size_t)wib * L.total;
+  Warp w;
+  w.lane = threadIdx.x & 31;
+  w.yv = reinterpret_cast<double*>(sm + L.yv);
+  w.xv = reinterpret_cast<double*>(sm + L.xv);
+  w.buf0 = reinterpret_cast<double*>(sm + L.buf0);
+  w.buf1 = reinterpret_cast<double*>(sm + L.buf1);
+  w.coef = reinterpret_cast<double*>(sm + L.coef);
+  w.posv = reinterpret_cast<unsigned short*>(sm + L.posv);
+  w.posb = reinterpret_cast<unsigned short*>(sm + L.posb);
+  w.grid = false;
+
+  const long long job = sig / p.R;
+  const int r = (int)(sig % p.R);
+  const int s = (int)(job / p.jobs_per_stream), j = (int)(job % p.jobs_per_stream);
+  const long long head = p.head0 + (long long)j * p.head_step;
+  const double* rt = ring_t + (long long)s * p.cap;
+  const double* ry = ring_y + ((long long)s * p.R + r) * p.cap;
+  double* ox = proc_x + sig * p.window;
+  double* oy = proc_y + sig * p.window;
+  const int W = p.window;
+  bool has_interp = false;
+  for (int i = 0; i < p.num_methods; ++i) has_interp |= (p.methods[i] == BPV_INTERP_LINEAR || p.methods[i] == BPV_INTERP_CUBIC);
+
+  // ---- gather + compaction (Signal.reset_mask: v = isfinite(x), w = isfinite(y); signal_data.py:43-45)
+  int n = 0, m = 0;
+  double xfirst = 0.0, xlast = 0.0;
+  const unsigned lt = (1u << w.lane) - 1u;
+  for (int k0 = 0; k0 < W; k0 += 32) {
+    const int k = k0 + w.lane;
+    double x = nan_f64(), y = nan_f64();
+    if (k < W) {
+      const long long g = head - W + 1 + k;
+      if (g >= 0) { const int slot = (int)(g % p.cap); x = rt[slot]; y = ry[slot]; }
+      ox[k] = x; oy[k] = y;
+    }
+    const bool fx = isfinite(x), fy = isfinite(y);
+    const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+    if (fy) {
+      const int idx = n + __popc(by & lt);
+      w.yv[idx] = y; w.posv[idx] = (unsigned short)k;
+      if (has_interp) w.xv[idx] = x;
+    }
+    if (fx && has_interp) w.posb[m + __popc(bx & lt)] = (unsigned short)k;
+    if (bx) {
+      if (m == 0) xfirst = shfl_d(x, __ffs(bx) - 1);
+      xlast = shfl_d(x, 31 - __clz(bx));
+    }
+    n += __popc(by); m += __popc(bx);
+  }
+  __syncwarp();
+  w.n = n; w.m = m; w.xfirst = xfirst; w.xlast = xlast;
+  const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
+  int st = ST_OK;
+  if (!(n >= 2 && isfinite(fs))) {            // guard, signal_processor.py:200
+    if (w.lane == 0) status[sig] = ST_GUARD;
+    return;
+  }
+  const int jobi = (int)job;
+  for (int mi = 0; mi < p.num_methods && st == ST_OK; ++mi) {
+    switch (p.methods[mi]) {
+      case BPV_DIFF_1: diff1(w); break;
+      case BPV_DIFF_2: diff2(w); break;
+      case BPV_INTERP_LINEAR: interp_linear(w); break;
+      case BPV_INTERP_CUBIC: if (!interp_cubic(w)) st = ST_CUBIC_X; break;
+      case BPV_DETREND_CONST: detrend_const(w); break;
+      case BPV_DETREND_LINEAR: detrend_linear(w); break;
+      case BPV_FILTER_BUTTER: {
+        const double* sg = sos_ws + (long long)jobi * p.butter_order * 6;
+        if (!isfinite(sg[0])) { st = ST_BAD_BANDS; break; }
+        sos_filtfilt(w, sg, p.butter_order);
+        break;
+      }
+      case BPV_FILTER_FIR: {
+        const double* tg = taps_ws + (long long)jobi * p.fir_taps;
+        if (!isfinite(tg[0])) { st = ST_BAD_BANDS; break; }
+        fir_filtfilt(w, tg, p.fir_taps);
+        break;
+      }
+      default: break;
+    }
+  }
+  // ---- scatter back into the position-preserving window (y[valid] = ..., signal_processor.py)
+  if (st == ST_OK) {
+    for (int i = w.lane; i < w.n; i += 32) {
+      const int k = w.posv[i];
+      oy[k] = w.yv[i];
+      if (w.grid) ox[k] = w.xv[i];
+    }
+  } else {
+    for (int k = w.lane; k < W; k += 32) oy[k] = nan_f64();
+  }
+  if (w.lane == 0) status[sig] = st;
+}
+
+}  // namespace bpv
+
+extern "C" int64_t bpv_window_workspace_bytes(const bpv_window_params* p) {
+  if (!p) return -1;
+  const int64_t J = (int64_t)p->S * p->jobs_per_stream;
+  return J * (int64_t)(bpv::MAX_SOS * 6 + 128) * 8;
+}
+
+extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
+                                     void* workspace, int64_t workspace_bytes,
+                                     double* proc_x, double* proc_y, int32_t* status, void* stream) {
+  using namespace bpv;
+  if (int rc = check_filter_params(p, "bpv_window_preprocess")) return rc;
+  BPV_REQUIRE(ring_t && ring_y && proc_x && proc_y && status, BPV_E_INVALID, "bpv_window_preprocess: NULL pointer");
+  BPV_REQUIRE(p->S > 0 && p->R > 0 && p->window > 0 && p->window <= p->cap && p->jobs_per_stream > 0 &&
+              p->num_methods >= 0 && p->num_methods <= BPV_MAX_METHODS, BPV_E_INVALID, "bpv_window_preprocess: bad sizes");
+  BPV_REQUIRE(p->window <= 65535, BPV_E_TOO_LARGE, "bpv_window_preprocess: window > 65535");
+  bool butter = false, fir = false;
+  for (int i = 0; i < p->num_methods; ++i) {
+    const int m = p->methods[i];
+    BPV_REQUIRE(m >= BPV_DIFF_1 && m <= BPV_FILTER_FIR, BPV_E_UNSUPPORTED,
+                "bpv_window_preprocess: unknown processing method %d (NotImplementedError, signal_processor.py:238)", m);
+    butter |= m == BPV_FILTER_BUTTER;
+    fir |= m == BPV_FILTER_FIR;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long J = (long long)p->S * p->jobs_per_stream;
+  double* sos_ws = (double*)workspace;
+  double* taps_ws = sos_ws ? sos_ws + J * MAX_SOS * 6 : nullptr;
+  if (butter || fir) {
+    BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
+                "bpv_window_preprocess: workspace too small (see bpv_window_workspace_bytes)");
+    if (butter) if (int rc = launch_job_butter(ring_t, *p, sos_ws, st)) return rc;
+    if (fir) if (int rc = launch_job_firls(ring_t, *p, taps_ws, st)) return rc;
+  }
+  const PreLayout L = pre_layout(*p);
+  const int max_smem = 200 * 1024;
+  BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
+              p->window, L.total);
+  int wpb = max_smem / L.total;
+  if (wpb > 4) wpb = 4;
+  const size_t smem = (size_t)wpb * L.total;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = 227 * 1024;
+  }
+  const long long nsig = J * p->R;
+  window_preprocess_kernel<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, *p, L, sos_ws, taps_ws,
+                                                                                     proc_x, proc_y, status);
+  return check_launch("bpv_window_preprocess");
+}

@@ -58,6 +58,11 @@ extern "C" {
 int bpv_version(void);
 const char* bpv_last_error(void);
 
+/* L2->DRAM fetch granularity hint of the device (32 / 64 / 128 bytes).  ROI rows are short unaligned
+ * spans, so a smaller granularity trims the DRAM over-fetch around each row.  get returns bytes or -1. */
+int bpv_set_l2_fetch_granularity(int bytes);
+int bpv_get_l2_fetch_granularity(void);
+
 /* ---------------------------------------------------------------------------------------------
  * F1  ROI sampling — replaces SignalProcessor.sample_signal / sample_signals
  *     (signal_processor.py:176-193).
@@ -117,9 +122,13 @@ typedef struct bpv_window_params {
  * proc_x, proc_y float64 [J, R, window]: the processed window, position-preserving (NaN where the
  * reference's arrays hold NaN).  status int32 [J, R]: 0 ok, 1 = guard failed (copied through
  * unprocessed, signal_processor.py:200), 2 = INTERP_CUBIC saw non-increasing x (the reference
- * raises ValueError there).
+ * raises ValueError there), 3 = filter band edges invalid for this fs (scipy raises ValueError).
+ * workspace: caller-owned device scratch of bpv_window_workspace_bytes(p) bytes holding the per-job
+ * filters (needed only when a FILTER_* method is listed).
  */
+int64_t bpv_window_workspace_bytes(const bpv_window_params* p);
 int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
+                          void* workspace, int64_t workspace_bytes,
                           double* proc_x, double* proc_y, int32_t* status, void* stream);
 
 /* F3 + F4(a) spectrum and HR peak — replaces transform_signal(s) + SignalGroup.get_peaks on
@@ -128,9 +137,13 @@ int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_
  * spec_f, spec_mag float32 [J, R, max_bins] (first num_bins[j,r] entries valid; may be NULL to skip
  * storing the spectrum); num_bins int32 [J, R]; peak_idx int32 [J, R] (-1 = none);
  * peak_freq, peak_mag float64 [J, R] (NaN = none).  The peak is decided in float64.
+ * workspace: device scratch of bpv_spectrum_workspace_bytes() bytes, needed only for PGRAM_LS when the
+ * spectrum is not stored (spec_mag == NULL).
  */
+int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins);
 int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,
-                        int32_t max_bins, float* spec_f, float* spec_mag, int32_t* num_bins,
+                        int32_t max_bins, void* workspace, int64_t workspace_bytes,
+                        float* spec_f, float* spec_mag, int32_t* num_bins,
                         int32_t* peak_idx, double* peak_freq, double* peak_mag, void* stream);
 
 /* F4(b) pairwise cross-correlation lag search — replaces correlate_signal_pair / correlate_signals

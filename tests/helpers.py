@@ -66,8 +66,10 @@ def same(a, b):
     return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
 
 
-def close(a, b, rtol=1e-4, atol_frac=1e-5):
-    """|a-b| <= rtol*|b| + atol_frac*max|b|  with NaN == NaN (north_star: rtol 1e-4)."""
+def close(a, b, rtol=1e-4, atol_frac=1e-5, atol=0.0):
+    """|a-b| <= rtol*|b| + atol_frac*max|b| + atol  with NaN == NaN (north_star: rtol 1e-4).
+    `atol` covers outputs that are pure rounding residue of a much larger input (e.g. a detrended
+    2-sample window): pass eps-level * input scale."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     if a.shape != b.shape:
         return False
@@ -77,4 +79,4 @@ def close(a, b, rtol=1e-4, atol_frac=1e-5):
     if b.size == 0 or nb.all():
         return True
     scale = np.nanmax(np.abs(b))
-    return bool(np.all(np.abs(a - b)[~nb] <= rtol * np.abs(b)[~nb] + atol_frac * scale))
+    return bool(np.all(np.abs(a - b)[~nb] <= rtol * np.abs(b)[~nb] + atol_frac * scale + atol))

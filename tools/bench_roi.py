@@ -17,8 +17,14 @@ ap.add_argument('--W', type=int, default=1920)
 ap.add_argument('--iters', type=int, default=20)
 ap.add_argument('--hint', type=int, default=0)
 ap.add_argument('--mode', type=int, default=1)
+ap.add_argument('--l2gran', type=int, default=0)
 a = ap.parse_args()
 N, H, W = a.frames, a.H, a.W
+from bpv import _cabi  # noqa: E402
+torch.cuda.init(); torch.zeros(1, device='cuda')
+if a.l2gran:
+    _cabi.check(_cabi.lib().bpv_set_l2_fetch_granularity(a.l2gran), 'l2gran')
+print('l2 fetch granularity', _cabi.lib().bpv_get_l2_fetch_granularity())
 frames = torch.empty((N, H, W, 3), dtype=torch.uint8, device='cuda')
 for i in range(0, N, 64):
     frames[i:i + 64].random_(0, 256)
