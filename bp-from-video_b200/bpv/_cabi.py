@@ -33,6 +33,7 @@ _P = C.c_void_p
 _SIGS = {
     'bpv_version': (C.c_int, []),
     'bpv_last_error': (C.c_char_p, []),
+    'bpv_sizeof_window_params': (C.c_int, []),
     'bpv_set_l2_fetch_granularity': (C.c_int, [C.c_int]),
     'bpv_get_l2_fetch_granularity': (C.c_int, []),
     'bpv_roi_sample_u8': (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, C.c_int32,
@@ -62,6 +63,8 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        if l.bpv_sizeof_window_params() != C.sizeof(WindowParams):
+            raise BpvError('bpv_window_params layout mismatch between libbpv.so and the ctypes binding')
         _lib = l
     return _lib
 

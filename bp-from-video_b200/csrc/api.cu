@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int bpv_version(void) { return BPV_VERSION; }
 extern "C" const char* bpv_last_error(void) { return bpv::g_err; }
+extern "C" int bpv_sizeof_window_params(void) { return (int)sizeof(bpv_window_params); }
 
 // L2 -> DRAM fetch granularity hint (32/64/128 B).  ROI rows are short, unaligned spans: a smaller
 // granularity cuts the DRAM over-fetch around every row.  Device-wide limit of the primary context.

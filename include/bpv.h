@@ -116,6 +116,7 @@ typedef struct bpv_window_params {
   int32_t ls_num_freqs;             /* 0 = reference behaviour (F = n valid); >0 fixed grid       */
   double butter_min_bw, fir_df, min_freq, max_freq;   /* signal_processor.py:58,60,64,65          */
 } bpv_window_params;
+int bpv_sizeof_window_params(void);   /* lets a binding verify its struct layout */
 
 /* F2 preprocessing — replaces SignalProcessor.process_signal(s) + make_filter
  *     (signal_processor.py:158-173, 196-245).
