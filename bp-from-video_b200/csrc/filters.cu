@@ -10,14 +10,37 @@ namespace bpv {
 __device__ inline double job_fs(const double* __restrict__ ring_t, int cap, int window, long long head, int* m_out) {
   double first = 0, last = 0;
   int m = 0;
-  for (int k = 0; k < window; ++k) {
-    const long long g = head - window + 1 + k;
-    if (g < 0) continue;
-    const double x = ring_t[g % cap];
+  long long g = head - window + 1;
+  int k = 0;
+  if (g < 0) { k = (int)(-g < window ? -g : window); g = 0; }     // samples before the stream started read as NaN
+  int slot = (int)(g % cap);
+  for (; k < window; ++k) {
+    const double x = ring_t[slot];
+    if (++slot == cap) slot = 0;
     if (isfinite(x)) { if (m == 0) first = x; last = x; ++m; }
   }
   if (m_out) *m_out = m;
   return m >= 2 ? 1.0 / ((last - first) / (double)(m - 1)) : nan_f64();
+}
+
+// Block-cooperative version (one window per CTA): threads stride the window, shared atomics pick the first /
+// last finite timestamp and count them.  s_i = 3 ints of shared memory.
+__device__ inline double job_fs_block(const double* __restrict__ ring_t, int cap, int window, long long head, int* s_i) {
+  if (threadIdx.x == 0) { s_i[0] = 0x7fffffff; s_i[1] = -1; s_i[2] = 0; }
+  __syncthreads();
+  const long long g0 = head - window + 1;
+  int lo = 0x7fffffff, hi = -1, cnt = 0;
+  for (int k = threadIdx.x; k < window; k += blockDim.x) {
+    const long long g = g0 + k;
+    if (g < 0) continue;
+    if (isfinite(ring_t[g % cap])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+  }
+  if (cnt) { atomicMin(&s_i[0], lo); atomicMax(&s_i[1], hi); atomicAdd(&s_i[2], cnt); }
+  __syncthreads();
+  const int m = s_i[2];
+  if (m < 2) return nan_f64();
+  const double first = ring_t[(g0 + s_i[0]) % cap], last = ring_t[(g0 + s_i[1]) % cap];
+  return 1.0 / ((last - first) / (double)(m - 1));
 }
 
 __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int order, double min_freq, double max_freq,
@@ -29,16 +52,28 @@ __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int 
   for (int k = 0; k < order * 6; ++k) sos_out[(long long)i * order * 6 + k] = sos[k];
 }
 
-// One CTA (64 threads) per filter: q/b vectors, Q = toeplitz + hankel (64x64, lda 65), Cholesky,
-// two triangular solves, symmetric tap assembly — scipy.signal.firls (_fir_filter_design.py:1130-1171)
-// with desired = [0,0,1,1,0,0], weight = 1.
+// One CTA (FIRLS_THREADS) per filter — scipy.signal.firls (_fir_filter_design.py:1130-1171) with
+// desired = [0,0,1,1,0,0], weight = 1: q/b vectors, Q = toeplitz(q) + hankel(q) (n x n, n <= 64),
+// Cholesky solve, symmetric tap assembly.
+//
+// The Cholesky is register tiled: the 64x64 matrix is cut into 16x16 blocks of 4x4 and the 136 lower-
+// triangular blocks are dealt row-major to threads, each keeping its block in registers (rows finish top
+// down, so whole warps retire as the sweep advances).  Step k: the owners of column k publish the raw
+// column to a double-buffered shared vector, the pivot's owner adds 1/sqrt(p) and 1/p, ONE barrier, then
+// every live thread applies the rank-1 update to its registers.  No masking is needed: entries of finished
+// rows/columns are dead, so updating them with stale values is harmless.  The right-hand side rides along
+// as a 65th matrix row (16 extra threads), which folds the forward substitution into the same sweep; the
+// scaled columns are kept (transposed) in shared memory for the backward substitution, done by warp 0 with
+// shuffles.
 constexpr int FIR_LDA = 65;
+constexpr int FIRLS_THREADS = 160;   // 136 block owners + 16 rhs-row owners + 8 idle
 __device__ void firls_design_block(double fs, int taps, double min_freq, double max_freq, double df,
                                    double* __restrict__ out, double* smem) {
   const int M = (taps - 1) / 2, n = M + 1;  // n unknowns (<= 64)
   double* q = smem;                 // [128]
-  double* rhs = q + 128;            // [64]
-  double* A = rhs + 64;             // [64 * FIR_LDA]
+  double* rhs = q + 128;            // [64]   b, later z, later the solution a
+  double* colb = rhs + 64;          // [2][72] raw column k, [64] rhs-row entry, [65] 1/sqrt(p), [66] 1/p
+  double* Lt = colb + 144;          // [64 * FIR_LDA]  Lt[k][i] = L[i][k]
   const int t = threadIdx.x;
   double fb[6];
   const bool ok = firls_bands(fs, min_freq, max_freq, df, fb);
@@ -51,40 +86,78 @@ __device__ void firls_design_block(double fs, int taps, double min_freq, double 
     for (int b = 0; b < 3; ++b) acc += fb[2 * b + 1] * np_sinc(fb[2 * b + 1] * i) - fb[2 * b] * np_sinc(fb[2 * b] * i);
     q[i] = acc;
   }
-  for (int i = t; i < n; i += blockDim.x) rhs[i] = fb[3] * np_sinc(fb[3] * i) - fb[2] * np_sinc(fb[2] * i);
+  for (int i = t; i < 64; i += blockDim.x) rhs[i] = i < n ? fb[3] * np_sinc(fb[3] * i) - fb[2] * np_sinc(fb[2] * i) : 0.0;
+  for (int i = t; i < 144; i += blockDim.x) colb[i] = 0.0;
   __syncthreads();
-  for (int idx = t; idx < n * n; idx += blockDim.x) {
-    const int i = idx / n, j = idx % n;
-    A[i * FIR_LDA + j] = q[i > j ? i - j : j - i] + q[i + j];
+  // thread -> block: t < 136: lower-triangular block (bi, bj) in row-major order; 136 <= t < 152: rhs row
+  const bool owner = t < 136, rrow = t >= 136 && t < 152;
+  int bi = 16, bj = rrow ? t - 136 : 0;
+  if (owner) {
+    bi = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while (bi * (bi + 1) / 2 > t) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    bj = t - bi * (bi + 1) / 2;
   }
-  __syncthreads();
-  // right-looking Cholesky, thread i owns row i (lower triangle)
-  for (int k = 0; k < n; ++k) {
-    const double dkk = sqrt(A[k * FIR_LDA + k]);
-    __syncthreads();
-    if (t == k) A[k * FIR_LDA + k] = dkk;
-    if (t > k && t < n) A[t * FIR_LDA + k] /= dkk;
-    __syncthreads();
-    if (t > k && t < n) {
-      const double lik = A[t * FIR_LDA + k];
-      for (int j = k + 1; j <= t; ++j) A[t * FIR_LDA + j] -= lik * A[j * FIR_LDA + k];
+  double a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * bi + r, j = 4 * bj + c;
+      if (owner) a[r][c] = (i < n && j < n) ? q[i > j ? i - j : j - i] + q[i + j] : (i == j ? 1.0 : 0.0);
+      else if (rrow && r == 0) a[r][c] = rhs[j];
+      else a[r][c] = 0.0;
     }
-    __syncthreads();
+  const int nkb = (n + 3) >> 2;
+  for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      const int k = 4 * kb + kc;
+      double* col = colb + (k & 1) * 72;
+      if (bj == kb && (owner || rrow)) {
+        if (owner) {
+          col[4 * bi + 0] = a[0][kc]; col[4 * bi + 1] = a[1][kc]; col[4 * bi + 2] = a[2][kc]; col[4 * bi + 3] = a[3][kc];
+          if (bi == kb) { const double ri = rsqrt(a[kc][kc]); col[65] = ri; col[66] = ri * ri; }
+        } else {
+          col[64] = a[0][kc];
+        }
+      }
+      __syncthreads();
+      const double inv = col[65], invp = col[66];
+      if (t < 64) Lt[k * FIR_LDA + t] = t >= k ? col[t] * inv : 0.0;     // L[t][k]
+      if (t == 64) rhs[k] = col[64] * inv;                                // z[k]
+      if (bi >= kb && (owner || rrow)) {       // finished block rows skip the update (whole warps retire)
+        const double lj0 = col[4 * bj + 0], lj1 = col[4 * bj + 1], lj2 = col[4 * bj + 2], lj3 = col[4 * bj + 3];
+        if (owner) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double li = -col[4 * bi + r] * invp;
+            a[r][0] = fma(li, lj0, a[r][0]); a[r][1] = fma(li, lj1, a[r][1]);
+            a[r][2] = fma(li, lj2, a[r][2]); a[r][3] = fma(li, lj3, a[r][3]);
+          }
+        } else {
+          const double li = -col[64] * invp;
+          a[0][0] = fma(li, lj0, a[0][0]); a[0][1] = fma(li, lj1, a[0][1]);
+          a[0][2] = fma(li, lj2, a[0][2]); a[0][3] = fma(li, lj3, a[0][3]);
+        }
+      }
+    }
   }
-  // L z = rhs (column-oriented forward substitution)
-  for (int k = 0; k < n; ++k) {
-    if (t == k) rhs[k] /= A[k * FIR_LDA + k];
-    __syncthreads();
-    if (t > k && t < n) rhs[t] -= A[t * FIR_LDA + k] * rhs[k];
-    __syncthreads();
+  __syncthreads();
+  // L^T x = z by warp 0: lane owns x[lane], x[lane + 32]
+  if (t < 32) {
+    double z0 = rhs[t], z1 = rhs[t + 32];
+    for (int k = n - 1; k >= 0; --k) {
+      const double zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
+      const double xk = zk / Lt[k * FIR_LDA + k];
+      if (t == (k & 31)) { if (k < 32) z0 = xk; else z1 = xk; }
+      // z[i] -= L[k][i] * x[k] for i < k ;  L[k][i] = Lt[i][k]
+      if (t < k) z0 = fma(-Lt[t * FIR_LDA + k], xk, z0);
+      if (t + 32 < k) z1 = fma(-Lt[(t + 32) * FIR_LDA + k], xk, z1);
+    }
+    rhs[t] = z0; rhs[t + 32] = z1;
   }
-  // L^T a = z (backward)
-  for (int k = n - 1; k >= 0; --k) {
-    if (t == k) rhs[k] /= A[k * FIR_LDA + k];
-    __syncthreads();
-    if (t < k) rhs[t] -= A[k * FIR_LDA + t] * rhs[k];
-    __syncthreads();
-  }
+  __syncthreads();
   // coeffs = [a[M..1], 2 a0, a[1..M]]
   for (int i = t; i < taps; i += blockDim.x) {
     const int d = i < M ? M - i : i - M;
@@ -92,7 +165,7 @@ __device__ void firls_design_block(double fs, int taps, double min_freq, double 
   }
 }
 
-__global__ void __launch_bounds__(64) firls_from_fs_kernel(const double* __restrict__ fs, int taps, double min_freq,
+__global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const double* __restrict__ fs, int taps, double min_freq,
                                                            double max_freq, double df, double* __restrict__ out) {
   extern __shared__ double smem[];
   firls_design_block(fs[blockIdx.x], taps, min_freq, max_freq, df, out + (long long)blockIdx.x * taps, smem);
@@ -111,19 +184,17 @@ __global__ void job_butter_kernel(const double* __restrict__ ring_t, bpv_window_
   for (int k = 0; k < p.butter_order * 6; ++k) sos_out[(long long)job * p.butter_order * 6 + k] = sos[k];
 }
 
-__global__ void __launch_bounds__(64) job_firls_kernel(const double* __restrict__ ring_t, bpv_window_params p,
+__global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* __restrict__ ring_t, bpv_window_params p,
                                                        double* __restrict__ out) {
   extern __shared__ double smem[];
-  __shared__ double fs_s;
+  __shared__ int s_i[3];
   const int job = blockIdx.x;
   const int s = job / p.jobs_per_stream, j = job % p.jobs_per_stream;
-  if (threadIdx.x == 0)
-    fs_s = job_fs(ring_t + (long long)s * p.cap, p.cap, p.window, p.head0 + (long long)j * p.head_step, nullptr);
-  __syncthreads();
+  const double fs_s = job_fs_block(ring_t + (long long)s * p.cap, p.cap, p.window, p.head0 + (long long)j * p.head_step, s_i);
   firls_design_block(fs_s, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, out + (long long)job * p.fir_taps, smem);
 }
 
-constexpr size_t FIRLS_SMEM = (128 + 64 + 64 * FIR_LDA) * sizeof(double);
+constexpr size_t FIRLS_SMEM = (128 + 64 + 144 + 64 * FIR_LDA) * sizeof(double);
 
 int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* sos_out, cudaStream_t st) {
   const int J = p.S * p.jobs_per_stream;
@@ -133,7 +204,7 @@ int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* 
 
 int launch_job_firls(const double* ring_t, const bpv_window_params& p, double* taps_out, cudaStream_t st) {
   const int J = p.S * p.jobs_per_stream;
-  job_firls_kernel<<<J, 64, FIRLS_SMEM, st>>>(ring_t, p, taps_out);
+  job_firls_kernel<<<J, FIRLS_THREADS, FIRLS_SMEM, st>>>(ring_t, p, taps_out);
   return check_launch("job_firls_kernel");
 }
 
@@ -162,6 +233,6 @@ extern "C" int bpv_firls_design(const double* fs, int32_t n, const bpv_window_pa
   if (int rc = check_filter_params(p, "bpv_firls_design")) return rc;
   BPV_REQUIRE(fs && taps_out && n >= 0, BPV_E_INVALID, "bpv_firls_design: bad arguments");
   if (n == 0) return 0;
-  firls_from_fs_kernel<<<n, 64, FIRLS_SMEM, (cudaStream_t)stream>>>(fs, p->fir_taps, p->min_freq, p->max_freq, p->fir_df, taps_out);
+  firls_from_fs_kernel<<<n, FIRLS_THREADS, FIRLS_SMEM, (cudaStream_t)stream>>>(fs, p->fir_taps, p->min_freq, p->max_freq, p->fir_df, taps_out);
   return check_launch("bpv_firls_design");
 }
