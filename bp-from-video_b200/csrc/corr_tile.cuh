@@ -1,0 +1,37 @@
+// Register-tiled sliding dot product shared by the FIR filtfilt (F2) and the cross-correlation (F4):
+//
+//     acc[r] += sum_{k=0}^{K-1} c[k] * X[j0 + r - k],      r = 0 .. RT-1,   K % RT == 0
+//
+// A thread owns RT consecutive outputs, so consecutive taps reuse RT-1 of its RT operands: one new
+// sample + one coefficient are loaded per RT FMAs (a plain "one output per thread" loop needs two
+// shared-memory loads per FMA and is bound by shared-memory bandwidth, not by the FP64 pipe).
+// X is stored "de-interleaved" — XT[(j % RT) * LD + j / RT] — so that the lanes of a warp, whose j0 are
+// RT apart, read consecutive words (no bank conflicts).  j0 must be a multiple of RT and j0 - K >= 0.
+#pragma once
+
+namespace bpv {
+
+template <int RT>
+__device__ __forceinline__ int xt_index(int j, int LD) { return (j % RT) * LD + j / RT; }
+
+template <int RT>
+__device__ __forceinline__ void corr_tile(double (&acc)[RT], const double* __restrict__ c, int K,
+                                          const double* __restrict__ XT, int LD, int j0) {
+  const int col0 = j0 / RT;
+  double w[RT];                       // w[s] = X[j] with j % RT == s, the RT samples under the current tap
+#pragma unroll
+  for (int s = 0; s < RT; ++s) w[s] = XT[s * LD + col0];
+  for (int kb = 0; kb * RT < K; ++kb) {
+    const double* cc = c + kb * RT;
+    const double* xn = XT + (col0 - kb - 1);
+#pragma unroll
+    for (int kk = 0; kk < RT; ++kk) {
+      const double ck = cc[kk];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r] = fma(ck, w[(r - kk + RT) % RT], acc[r]);
+      w[RT - 1 - kk] = xn[(RT - 1 - kk) * LD];      // X[j0 - k - 1] replaces X[j0 - k + RT - 1]
+    }
+  }
+}
+
+}  // namespace bpv

@@ -13,6 +13,7 @@
 //   FIR filtfilt lane-strided direct convolution; only the part of the padded signal that reaches the
 //               cropped output is computed
 #include "filters.cuh"
+#include "corr_tile.cuh"
 
 namespace bpv {
 
@@ -40,7 +41,7 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   if (fir && 3 * p.fir_taps > pad) pad = 3 * p.fir_taps;
   if (pad > W - 1) pad = W - 1 > 0 ? W - 1 : 0;
   PreLayout L;
-  L.buf_len = W + 2 * pad;
+  L.buf_len = W + 2 * pad + (fir ? 128 + 16 + 8 + 8 : 0);   // FIR: front zero padding + tile slack, see fir_filtfilt
   int o = 0;
   L.yv = o; o += W * 8;
   L.xv = o; o += interp ? W * 8 : 0;
@@ -330,53 +331,76 @@ __device__ void sos_filtfilt(Warp& w, const double* __restrict__ sos_g, int N) {
 
 // scipy.signal.filtfilt(b, 1.0, y, padlen) for an FIR b (scipy/signal/_signaltools.py:4893-4924):
 // odd extension, zi = lfilter_zi(b, [1]) (suffix sums of b[1:]), forward, backward, crop.
-// Only forward outputs that can reach the cropped result are evaluated.
+//   F[i] = sum_k b[k] ext[i-k] + (i < T-1 ? zi[i]*ext[0] : 0)          forward over the padded signal
+//   B[i] = sum_k b[k] G[i-k]   + (i < T-1 ? zi[i]*F[L-1] : 0),  G[g] = F[L-1-g]   backward
+//   out[m] = B[L-1-p-m]
+// Only forward outputs that can reach the cropped result are evaluated (F[p .. p+n-1+T-1]).  Both passes
+// are the register-tiled sliding dot product of corr_tile.cuh: each lane owns 8 consecutive outputs, the
+// operand buffers are de-interleaved by 8 and zero padded in front so no tap needs a bounds check.
+constexpr int FIR_RT = 8;
 __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) {
-  double* b = w.coef;          // [T]
+  const int Kp = (T + FIR_RT - 1) / FIR_RT * FIR_RT;
+  double* b = w.coef;          // [Kp] zero padded
   double* zi = w.coef + 128;   // [T-1]
-  for (int i = w.lane; i < T; i += 32) b[i] = taps_g[i];
+  for (int i = w.lane; i < Kp; i += 32) b[i] = i < T ? taps_g[i] : 0.0;
   __syncwarp();
   if (w.lane == 0) {
     double acc = 0.0;
     for (int i = T - 2; i >= 0; --i) { acc += b[i + 1]; zi[i] = acc; }
   }
-  __syncwarp();
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
-  double* ext = w.buf0;
-  double* F = w.buf1;
-  odd_ext(w, ext, p);
-  const double x0 = ext[0];
-  // forward outputs needed: F[p .. fb], plus F[L-1] when the backward zi term survives the crop
-  const int fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);
-  const bool need_y0 = p < T - 1;
-  for (int i0 = p; i0 <= fb; i0 += 32) {
-    const int i = i0 + w.lane;
-    if (i <= fb) {
-      const int kmax = i < T - 1 ? i : T - 1;
-      double acc = i < T - 1 ? zi[i] * x0 : 0.0;
-      for (int k = 0; k <= kmax; ++k) acc = fma(b[k], ext[i - k], acc);
-      F[i] = acc;
+  const int LD = (Kp + L + 15) / FIR_RT + 1;
+  double* XT = w.buf0;   // ext, storage index = logical index + Kp, de-interleaved
+  double* GT = w.buf1;   // reversed forward output, same layout
+  const double y_first = w.yv[0], y_last = w.yv[n - 1];
+  for (int jj = w.lane; jj < FIR_RT * LD; jj += 32) {
+    const int i = jj - Kp;
+    double v = 0.0;
+    if (i >= 0 && i < L) {                       // odd extension (scipy.signal._arraytools.odd_ext)
+      if (i < p) v = 2.0 * y_first - w.yv[p - i];
+      else if (i < p + n) v = w.yv[i - p];
+      else v = 2.0 * y_last - w.yv[n - 2 - (i - p - n)];
     }
-  }
-  if (need_y0 && fb < L - 1 && w.lane == 0) {
-    const int i = L - 1;
-    const int kmax = i < T - 1 ? i : T - 1;
-    double acc = i < T - 1 ? zi[i] * x0 : 0.0;
-    for (int k = 0; k <= kmax; ++k) acc = fma(b[k], ext[i - k], acc);
-    F[i] = acc;
+    const int a = xt_index<FIR_RT>(jj, LD);
+    XT[a] = v;
+    GT[a] = 0.0;
   }
   __syncwarp();
-  const double y0 = F[L - 1 < fb || need_y0 ? L - 1 : fb];  // only used when need_y0
-  // backward: out[m] = sum_k b[k] * F[p+m+k] (+ zi[i]*y0 for i = L-1-p-m < T-1)
-  for (int m0 = 0; m0 < n; m0 += 32) {
-    const int m = m0 + w.lane;
-    if (m < n) {
-      const int i = L - 1 - p - m;
-      const int kmax = i < T - 1 ? i : T - 1;
-      double acc = i < T - 1 ? zi[i] * y0 : 0.0;
-      for (int k = 0; k <= kmax; ++k) acc = fma(b[k], F[p + m + k], acc);
-      w.yv[m] = acc;
+  const double x0 = p >= 1 ? 2.0 * y_first - w.yv[p] : y_first;       // ext[0]
+  const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);
+  for (int I = (fa + Kp) / FIR_RT * FIR_RT; I <= fb + Kp; I += 32 * FIR_RT) {
+    const int j0 = I + FIR_RT * w.lane, i0 = j0 - Kp;
+    if (i0 <= fb) {
+      double acc[FIR_RT];
+#pragma unroll
+      for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
+      corr_tile<FIR_RT>(acc, b, Kp, XT, LD, j0);
+#pragma unroll
+      for (int r = 0; r < FIR_RT; ++r) {
+        const int i = i0 + r;
+        if (i >= fa && i <= fb) {
+          const double v = acc[r] + (i < T - 1 ? zi[i] * x0 : 0.0);
+          GT[xt_index<FIR_RT>(L - 1 - i + Kp, LD)] = v;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  const double yend = GT[xt_index<FIR_RT>(Kp, LD)];       // F[L-1]; only used when p < T-1 (then fb == L-1)
+  const int ba = p, bb = p + n - 1;
+  for (int I = (ba + Kp) / FIR_RT * FIR_RT; I <= bb + Kp; I += 32 * FIR_RT) {
+    const int j0 = I + FIR_RT * w.lane, i0 = j0 - Kp;
+    if (i0 <= bb) {
+      double acc[FIR_RT];
+#pragma unroll
+      for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
+      corr_tile<FIR_RT>(acc, b, Kp, GT, LD, j0);
+#pragma unroll
+      for (int r = 0; r < FIR_RT; ++r) {
+        const int i = i0 + r;
+        if (i >= ba && i <= bb) w.yv[L - 1 - p - i] = acc[r] + (i < T - 1 ? zi[i] * yend : 0.0);
+      }
     }
   }
   __syncwarp();
