@@ -14,14 +14,17 @@ namespace bpv {
 template <int RT>
 __device__ __forceinline__ int xt_index(int j, int LD) { return (j % RT) * LD + j / RT; }
 
+// Optional [kb_begin, kb_end): only taps k in [kb_begin*RT, kb_end*RT) are applied (skips known-zero operands).
 template <int RT>
 __device__ __forceinline__ void corr_tile(double (&acc)[RT], const double* __restrict__ c, int K,
-                                          const double* __restrict__ XT, int LD, int j0) {
+                                          const double* __restrict__ XT, int LD, int j0,
+                                          int kb_begin = 0, int kb_end = 0x7fffffff) {
   const int col0 = j0 / RT;
+  if (kb_end > K / RT) kb_end = K / RT;
   double w[RT];                       // w[s] = X[j] with j % RT == s, the RT samples under the current tap
 #pragma unroll
-  for (int s = 0; s < RT; ++s) w[s] = XT[s * LD + col0];
-  for (int kb = 0; kb * RT < K; ++kb) {
+  for (int s = 0; s < RT; ++s) w[s] = XT[s * LD + col0 - kb_begin];
+  for (int kb = kb_begin; kb < kb_end; ++kb) {
     const double* cc = c + kb * RT;
     const double* xn = XT + (col0 - kb - 1);
 #pragma unroll

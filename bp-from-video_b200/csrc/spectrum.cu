@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
   double* tws = twc + W;
   double* z = tws + W;
   double* mags = z + W;
+  double* fim = mags + (W / 2 + 2);   // [256] FFT imaginary parts (Welch fast path)
   const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, nullptr, ys, s_cnt, s_d);
   const int n = si.n;
   if (!(n >= 2 && isfinite(si.fs))) {        // guard signal_processor.py:252 -> empty spectrum
@@ -165,6 +166,39 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
       const double mean = block_sum(a, s_val) / (double)N;
       for (int i = tid; i < N; i += blockDim.x) z[i] = (seg[i] - mean) * (0.5 - 0.5 * twc[i]);
       __syncthreads();
+      if (N == 256) {
+        // steady state (n >= 256): radix-2 FFT of the 256 real samples in shared memory — 8 stages of 128
+        // butterflies, one per thread — instead of a 129 x 256 direct DFT.  fr/fi reuse z[] and ys-free space.
+        double* fr = z;            // [256] real parts (bit-reversed load done below)
+        double* fi = fim;          // [256] imaginary parts
+        const double v0 = z[tid], v1 = z[tid + 128];
+        __syncthreads();
+        fr[__brev((unsigned)tid) >> 24] = v0;
+        fr[__brev((unsigned)(tid + 128)) >> 24] = v1;
+        fi[tid] = 0.0; fi[tid + 128] = 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int half = 1 << st;
+          const int pos = tid & (half - 1);
+          const int i0 = ((tid >> st) << (st + 1)) + pos, i1 = i0 + half;
+          const int tw = pos << (7 - st);                       // twiddle exp(-2*pi*i*tw/256)
+          const double wr = twc[tw], wi = -tws[tw];
+          const double xr = fr[i1], xi = fi[i1];
+          const double tr = wr * xr - wi * xi, ti = wr * xi + wi * xr;
+          const double ur = fr[i0], ui = fi[i0];
+          fr[i0] = ur + tr; fi[i0] = ui + ti;
+          fr[i1] = ur - tr; fi[i1] = ui - ti;
+          __syncthreads();
+        }
+        for (int k = tid; k < F; k += blockDim.x) {
+          double pw = (fr[k] * fr[k] + fi[k] * fi[k]) * scale;
+          if (k >= 1 && k < F - 1) pw *= 2.0;
+          mags[k] += pw;
+        }
+        __syncthreads();
+        continue;
+      }
       for (int k = tid; k < F; k += blockDim.x) {
         double re = 0.0, im = 0.0;
         int idx = 0;
@@ -434,7 +468,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   if (p->transform != BPV_PGRAM_LS) {
     const int need = p->transform == BPV_DFT_RFFT ? W / 2 + 1 : (W < 256 ? W : 256) / 2 + 1;
     BPV_REQUIRE(!spec_mag || max_bins >= need, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, need);
-    const size_t smem = (size_t)(4 * W + W / 2 + 2) * sizeof(double);
+    const size_t smem = (size_t)(4 * W + W / 2 + 2 + 256) * sizeof(double);
     BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window %d too large for the dense spectrum kernel", W);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

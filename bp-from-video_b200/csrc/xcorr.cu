@@ -5,6 +5,7 @@
 // "direct" method scipy.signal.correlate picks for these sizes); normalisation by max(a.a, b.b, a.b);
 // first-max argmax over every finite lag fused in.
 #include "filters.cuh"
+#include "corr_tile.cuh"
 
 namespace bpv {
 
@@ -29,13 +30,29 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
   const double* xa_g = proc_x + (job * R + ra) * W;
   const double* ya_g = proc_y + (job * R + ra) * W;
   const double* yb_g = proc_y + (job * R + rb) * W;
-  double* a = sm;            // [W]
-  double* b = a + W;         // [W]
-  double* xa = b + W;        // [W]
-  double* cv = xa + W;       // [2W-1] correlation values (for the argmax)
-  // valid = a.w & b.w  (finite in both)
+  // shared memory (doubles): xa[W] | cv[2W] | c[Kw] reversed b, zero padded | XT[8*LD] a, de-interleaved
+  constexpr int RT = 8;
+  const int Kw = (W + RT - 1) / RT * RT;
+  double* xa = sm;             // [W]
+  double* cv = xa + W;         // [2W] correlation values (for the argmax)
+  double* c = cv + 2 * W;      // [Kw]
+  double* XT = c + Kw;         // [RT * LDw], LDw = (Kw + 3W + 16) / RT + 1
+  const int LDw = (Kw + 3 * W + 16) / RT + 1;
+  for (int i = tid; i < Kw; i += blockDim.x) c[i] = 0.0;
+  for (int i = tid; i < RT * LDw; i += blockDim.x) XT[i] = 0.0;
+  __syncthreads();
+  // valid = a.w & b.w  (finite in both); compacted sample i of a goes to X[u = i + n - 1], of b to c[n-1-i].
+  // n is only known after the walk, so warp 0 first counts, then places.
   if (tid < 32) {
     int n = 0;
+    for (int k0 = 0; k0 < W; k0 += 32) {
+      const int k = k0 + lane;
+      const bool ok = k < W && isfinite(ya_g[k]) && isfinite(yb_g[k]);
+      n += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) s_n = n;
+    const int K = (n + RT - 1) / RT * RT;
+    int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
     for (int k0 = 0; k0 < W; k0 += 32) {
       const int k = k0 + lane;
@@ -43,10 +60,14 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
       if (k < W) { va = ya_g[k]; vb = yb_g[k]; vx = xa_g[k]; }
       const bool ok = isfinite(va) && isfinite(vb);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) { const int i = n + __popc(bal & lt); a[i] = va; b[i] = vb; xa[i] = vx; }
-      n += __popc(bal);
+      if (ok) {
+        const int i = cnt + __popc(bal & lt);
+        XT[xt_index<RT>(i + n - 1 + K, LDw)] = va;     // storage index = u + K
+        c[n - 1 - i] = vb;
+        xa[i] = vx;
+      }
+      cnt += __popc(bal);
     }
-    if (lane == 0) s_n = n;
   }
   __syncthreads();
   const int n = s_n;
@@ -54,24 +75,40 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
     if (tid == 0) { num_lags[jp] = 0; lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
     return;
   }
+  const int K = (n + RT - 1) / RT * RT;
   double daa = 0, dbb = 0, dab = 0;
-  for (int i = tid; i < n; i += blockDim.x) { daa = fma(a[i], a[i], daa); dbb = fma(b[i], b[i], dbb); dab = fma(a[i], b[i], dab); }
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double va = XT[xt_index<RT>(i + n - 1 + K, LDw)], vb = c[n - 1 - i];
+    daa = fma(va, va, daa); dbb = fma(vb, vb, dbb); dab = fma(va, vb, dab);
+  }
   daa = block_sum(daa, s_val); dbb = block_sum(dbb, s_val); dab = block_sum(dab, s_val);
   const double den = fmax(fmax(daa, dbb), dab);
   const int L = 2 * n - 1;
   const long long ob = jp * (2LL * W - 1);
-  for (int li = tid; li < L; li += blockDim.x) {
-    const int k = li - (n - 1);                // corr[k + n - 1] = sum_l a[l + k] * b[l]
-    const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
-    double acc = 0.0;
-    for (int l = l0; l < l1; ++l) acc = fma(a[l + k], b[l], acc);
-    const double c = acc / den;
-    cv[li] = c;
-    if (corr_val) {
-      const int ak = k < 0 ? -k : k;
-      const double lag = (xa[n - 1] - xa[n - 1 - ak]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
-      corr_lag[ob + li] = (float)lag;
-      corr_val[ob + li] = (float)c;
+  // corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1 (corr_tile.cuh);
+  // X is non-zero only on u in [n-1, 2n-2], so each tile applies just the taps that can touch it.
+  const int jbase = (n - 1 + K) / RT * RT;      // storage index of the tile that holds li = 0
+  for (int J0 = jbase + RT * tid; J0 <= (L - 1) + (n - 1) + K; J0 += RT * blockDim.x) {
+    double acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    const int u0 = J0 - K;                       // logical index of the tile's first output operand
+    int kb_lo = (u0 - (2 * n - 2)) / RT; if (kb_lo < 0) kb_lo = 0;
+    int kb_hi = (u0 + RT - 1 - (n - 1)) / RT + 1; if (kb_hi < 0) kb_hi = 0;
+    corr_tile<RT>(acc, c, K, XT, LDw, J0, kb_lo, kb_hi);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int li = u0 + r - (n - 1);
+      if (li >= 0 && li < L) {
+        const double cc = acc[r] / den;
+        cv[li] = cc;
+        if (corr_val) {
+          const int k = li - (n - 1), ak = k < 0 ? -k : k;
+          const double lag = (xa[n - 1] - xa[n - 1 - ak]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
+          corr_lag[ob + li] = (float)lag;
+          corr_val[ob + li] = (float)cc;
+        }
+      }
     }
   }
   __syncthreads();
@@ -117,7 +154,8 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   if (P == 0) return 0;
   const long long n = (long long)p->S * p->jobs_per_stream * P;
   BPV_REQUIRE(W > 0 && n > 0, BPV_E_INVALID, "bpv_window_xcorr: bad sizes");
-  const size_t smem = (size_t)(5 * W) * sizeof(double);
+  const int Kw = (W + 7) / 8 * 8;
+  const size_t smem = (size_t)(3 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(double);
   BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_xcorr: window %d too large for shared memory", W);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
