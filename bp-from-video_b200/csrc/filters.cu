@@ -57,8 +57,8 @@ __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int 
 // Cholesky solve, symmetric tap assembly.
 //
 // The Cholesky is register tiled: the 64x64 matrix is cut into 16x16 blocks of 4x4 and the 136 lower-
-// triangular blocks are dealt row-major to threads, each keeping its block in registers (rows finish top
-// down, so whole warps retire as the sweep advances).  Step k: the owners of column k publish the raw
+// triangular blocks are dealt column-major to threads, each keeping its block in registers (block columns
+// die left to right, so whole warps retire as the sweep advances).  Step k: the owners of column k publish the raw
 // column to a double-buffered shared vector, the pivot's owner adds 1/sqrt(p) and 1/p, ONE barrier, then
 // every live thread applies the rank-1 update to its registers.  No masking is needed: entries of finished
 // rows/columns are dead, so updating them with stale values is harmless.  The right-hand side rides along
@@ -89,14 +89,15 @@ __device__ void firls_design_block(double fs, int taps, double min_freq, double 
   for (int i = t; i < 64; i += blockDim.x) rhs[i] = i < n ? fb[3] * np_sinc(fb[3] * i) - fb[2] * np_sinc(fb[2] * i) : 0.0;
   for (int i = t; i < 144; i += blockDim.x) colb[i] = 0.0;
   __syncthreads();
-  // thread -> block: t < 136: lower-triangular block (bi, bj) in row-major order; 136 <= t < 152: rhs row
+  // thread -> block: t < 136: lower-triangular block (bi, bj) in COLUMN-major order (block column bj is dead
+  // once the sweep passes it, so the warps holding the early columns retire first); 136 <= t < 152: rhs row
   const bool owner = t < 136, rrow = t >= 136 && t < 152;
   int bi = 16, bj = rrow ? t - 136 : 0;
   if (owner) {
-    bi = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while (bi * (bi + 1) / 2 > t) --bi;
-    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-    bj = t - bi * (bi + 1) / 2;
+    int rem = t;
+    bj = 0;
+    while (rem >= 16 - bj) { rem -= 16 - bj; ++bj; }
+    bi = bj + rem;
   }
   double a[4][4];
 #pragma unroll
@@ -109,36 +110,66 @@ __device__ void firls_design_block(double fs, int taps, double min_freq, double 
       else a[r][c] = 0.0;
     }
   const int nkb = (n + 3) >> 2;
+  double* dinv = q;                 // q[] is dead once the blocks are loaded: reuse it for 1/L[k][k]
+  __syncthreads();
+  // publish column 0
+  if (bj == 0) {
+    double* col = colb;
+    if (owner) {
+      col[4 * bi + 0] = a[0][0]; col[4 * bi + 1] = a[1][0]; col[4 * bi + 2] = a[2][0]; col[4 * bi + 3] = a[3][0];
+      if (bi == 0) { const double ri = rsqrt(a[0][0]); col[65] = ri; col[66] = ri * ri; }
+    } else if (rrow) {
+      col[64] = a[0][0];
+    }
+  }
   for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
       const int k = 4 * kb + kc;
-      double* col = colb + (k & 1) * 72;
-      if (bj == kb && (owner || rrow)) {
-        if (owner) {
-          col[4 * bi + 0] = a[0][kc]; col[4 * bi + 1] = a[1][kc]; col[4 * bi + 2] = a[2][kc]; col[4 * bi + 3] = a[3][kc];
-          if (bi == kb) { const double ri = rsqrt(a[kc][kc]); col[65] = ri; col[66] = ri * ri; }
-        } else {
-          col[64] = a[0][kc];
-        }
-      }
-      __syncthreads();
+      const double* col = colb + (k & 1) * 72;
+      double* ncol = colb + ((k + 1) & 1) * 72;
+      __syncthreads();                       // column k (published during step k-1) is visible
       const double inv = col[65], invp = col[66];
       if (t < 64) Lt[k * FIR_LDA + t] = t >= k ? col[t] * inv : 0.0;     // L[t][k]
-      if (t == 64) rhs[k] = col[64] * inv;                                // z[k]
-      if (bi >= kb && (owner || rrow)) {       // finished block rows skip the update (whole warps retire)
-        const double lj0 = col[4 * bj + 0], lj1 = col[4 * bj + 1], lj2 = col[4 * bj + 2], lj3 = col[4 * bj + 3];
+      if (t == 64) { rhs[k] = col[64] * inv; dinv[k] = inv; }             // z[k], 1/L[k][k]
+      if (bj >= kb && (owner || rrow)) {       // finished block columns skip the update (whole warps retire)
+        const double2 ja = *reinterpret_cast<const double2*>(col + 4 * bj), jb = *reinterpret_cast<const double2*>(col + 4 * bj + 2);
+        const double lj[4] = {ja.x, ja.y, jb.x, jb.y};
+        double li[4];
         if (owner) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const double li = -col[4 * bi + r] * invp;
-            a[r][0] = fma(li, lj0, a[r][0]); a[r][1] = fma(li, lj1, a[r][1]);
-            a[r][2] = fma(li, lj2, a[r][2]); a[r][3] = fma(li, lj3, a[r][3]);
-          }
+          const double2 ia = *reinterpret_cast<const double2*>(col + 4 * bi), ib = *reinterpret_cast<const double2*>(col + 4 * bi + 2);
+          li[0] = -ia.x * invp; li[1] = -ia.y * invp; li[2] = -ib.x * invp; li[3] = -ib.y * invp;
         } else {
-          const double li = -col[64] * invp;
-          a[0][0] = fma(li, lj0, a[0][0]); a[0][1] = fma(li, lj1, a[0][1]);
-          a[0][2] = fma(li, lj2, a[0][2]); a[0][3] = fma(li, lj3, a[0][3]);
+          li[0] = -col[64] * invp; li[1] = li[2] = li[3] = 0.0;
+        }
+        // look-ahead: bring column k+1 up to date first and publish it, so that the barrier of step k+1
+        // overlaps the remaining 12 FMAs of step k
+        const int nc = (kc + 1) & 3;           // column of k+1 inside its block (constant after unrolling)
+        const int nkb2 = kc == 3 ? kb + 1 : kb;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r][nc] = fma(li[r], lj[nc], a[r][nc]);
+        if (kc != 3 && bj == nkb2 && k + 1 < 4 * nkb) {
+          if (owner) {
+            ncol[4 * bi + 0] = a[0][nc]; ncol[4 * bi + 1] = a[1][nc]; ncol[4 * bi + 2] = a[2][nc]; ncol[4 * bi + 3] = a[3][nc];
+            if (bi == nkb2) { const double ri = rsqrt(a[nc][nc]); ncol[65] = ri; ncol[66] = ri * ri; }
+          } else {
+            ncol[64] = a[0][nc];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c != nc) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r][c] = fma(li[r], lj[c], a[r][c]);
+          }
+      }
+      // kc == 3: column k+1 lives in the NEXT block column, whose blocks are complete only after the full update
+      if (kc == 3 && bj == kb + 1 && kb + 1 < nkb && (owner || rrow)) {
+        if (owner) {
+          ncol[4 * bi + 0] = a[0][0]; ncol[4 * bi + 1] = a[1][0]; ncol[4 * bi + 2] = a[2][0]; ncol[4 * bi + 3] = a[3][0];
+          if (bi == kb + 1) { const double ri = rsqrt(a[0][0]); ncol[65] = ri; ncol[66] = ri * ri; }
+        } else {
+          ncol[64] = a[0][0];
         }
       }
     }
@@ -149,7 +180,7 @@ __device__ void firls_design_block(double fs, int taps, double min_freq, double 
     double z0 = rhs[t], z1 = rhs[t + 32];
     for (int k = n - 1; k >= 0; --k) {
       const double zk = __shfl_sync(0xffffffffu, k < 32 ? z0 : z1, k & 31);
-      const double xk = zk / Lt[k * FIR_LDA + k];
+      const double xk = zk * dinv[k];
       if (t == (k & 31)) { if (k < 32) z0 = xk; else z1 = xk; }
       // z[i] -= L[k][i] * x[k] for i < k ;  L[k][i] = Lt[i][k]
       if (t < k) z0 = fma(-Lt[t * FIR_LDA + k], xk, z0);

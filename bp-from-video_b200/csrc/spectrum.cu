@@ -471,7 +471,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
     const size_t smem = (size_t)(4 * W + W / 2 + 2 + 256) * sizeof(double);
     BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window %d too large for the dense spectrum kernel", W);
     if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     spectrum_dense_kernel<<<(unsigned)nsig, 128, smem, st>>>(proc_x, proc_y, *p, max_bins, spec_f, spec_mag, num_bins,
@@ -489,8 +489,8 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   const size_t smem_c = (size_t)W * (2 * sizeof(double) + 3 * sizeof(float));
   const size_t smem_p = (size_t)W * 2 * sizeof(double) + (size_t)max_bins * (sizeof(double) + sizeof(int));
   BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
-  if (smem_c > 48 * 1024) cudaFuncSetAttribute(ls_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (smem_c > 48 * 1024) cudaFuncSetAttribute(ls_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+  if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
   dim3 grid((unsigned)nsig, (Fmax + 127) / 128);
   ls_coarse_kernel<<<grid, 128, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
   if (int rc = check_launch("ls_coarse_kernel")) return rc;

@@ -10,8 +10,8 @@
 //               tridiagonal solve is a serial Thomas sweep on lane 0 (latency hidden by other warps)
 //   sosfiltfilt 16 biquads = 16 lanes of a systolic cascade: lane s owns section s, samples flow
 //               lane to lane by __shfl_up (one sample enters per step), forward then backward
-//   FIR filtfilt lane-strided direct convolution; only the part of the padded signal that reaches the
-//               cropped output is computed
+//   FIR filtfilt register-tiled sliding dot product (corr_tile.cuh), 8 consecutive outputs per lane; only
+//               the part of the padded signal that reaches the cropped output is staged and computed
 #include "filters.cuh"
 #include "corr_tile.cuh"
 
@@ -37,11 +37,14 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   }
   const int W = p.window;
   int pad = 0;
-  if (butter) pad = 3 * (2 * p.butter_order + 1);
-  if (fir && 3 * p.fir_taps > pad) pad = 3 * p.fir_taps;
+  if (butter) pad = 3 * (2 * p.butter_order + 1);      // sosfiltfilt works on the whole odd-extended signal
   if (pad > W - 1) pad = W - 1 > 0 ? W - 1 : 0;
   PreLayout L;
-  L.buf_len = W + 2 * pad + (fir ? 128 + 16 + 8 + 8 : 0);   // FIR: front zero padding + tile slack, see fir_filtfilt
+  L.buf_len = butter ? W + 2 * pad : (interp ? W : 0);
+  if (fir) {   // FIR stages only the operands that reach the cropped output: Kp + n + T + tile slack (fir_filtfilt)
+    const int need = W + 2 * 128 + 32;
+    if (need > L.buf_len) L.buf_len = need;
+  }
   int o = 0;
   L.yv = o; o += W * 8;
   L.xv = o; o += interp ? W * 8 : 0;
@@ -350,12 +353,17 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   }
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
-  const int LD = (Kp + L + 15) / FIR_RT + 1;
-  double* XT = w.buf0;   // ext, storage index = logical index + Kp, de-interleaved
-  double* GT = w.buf1;   // reversed forward output, same layout
+  const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);   // forward outputs needed
+  const int ba = p, bb = p + n - 1;                                                      // backward outputs needed
+  // Only the operands those outputs can touch are staged: ext[fa-Kp .. fb+7] and G[ba-Kp .. bb+7]
+  // (negative logical indices are the zero history of lfilter).  storage index = logical index - base.
+  const int xbase = fa - Kp, gbase = ba - Kp;
+  const int LD = (Kp + n + T + 15) / FIR_RT + 1;
+  double* XT = w.buf0;   // ext, de-interleaved by FIR_RT
+  double* GT = w.buf1;   // reversed forward output G[g] = F[L-1-g], same layout
   const double y_first = w.yv[0], y_last = w.yv[n - 1];
   for (int jj = w.lane; jj < FIR_RT * LD; jj += 32) {
-    const int i = jj - Kp;
+    const int i = jj + xbase;
     double v = 0.0;
     if (i >= 0 && i < L) {                       // odd extension (scipy.signal._arraytools.odd_ext)
       if (i < p) v = 2.0 * y_first - w.yv[p - i];
@@ -368,9 +376,8 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   }
   __syncwarp();
   const double x0 = p >= 1 ? 2.0 * y_first - w.yv[p] : y_first;       // ext[0]
-  const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);
-  for (int I = (fa + Kp) / FIR_RT * FIR_RT; I <= fb + Kp; I += 32 * FIR_RT) {
-    const int j0 = I + FIR_RT * w.lane, i0 = j0 - Kp;
+  for (int I = Kp; I <= fb - xbase; I += 32 * FIR_RT) {               // storage Kp <-> logical fa
+    const int j0 = I + FIR_RT * w.lane, i0 = j0 + xbase;
     if (i0 <= fb) {
       double acc[FIR_RT];
 #pragma unroll
@@ -379,18 +386,19 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) {
         const int i = i0 + r;
-        if (i >= fa && i <= fb) {
+        if (i <= fb) {
           const double v = acc[r] + (i < T - 1 ? zi[i] * x0 : 0.0);
-          GT[xt_index<FIR_RT>(L - 1 - i + Kp, LD)] = v;
+          const int g = L - 1 - i;                                    // >= ba - (T-1) >= gbase
+          GT[xt_index<FIR_RT>(g - gbase, LD)] = v;
         }
       }
     }
   }
   __syncwarp();
-  const double yend = GT[xt_index<FIR_RT>(Kp, LD)];       // F[L-1]; only used when p < T-1 (then fb == L-1)
-  const int ba = p, bb = p + n - 1;
-  for (int I = (ba + Kp) / FIR_RT * FIR_RT; I <= bb + Kp; I += 32 * FIR_RT) {
-    const int j0 = I + FIR_RT * w.lane, i0 = j0 - Kp;
+  // F[L-1] = G[0]; only used when p < T-1 (then fb == L-1, so it has been computed)
+  const double yend = (0 - gbase >= 0) ? GT[xt_index<FIR_RT>(0 - gbase, LD)] : 0.0;
+  for (int I = Kp; I <= bb - gbase; I += 32 * FIR_RT) {
+    const int j0 = I + FIR_RT * w.lane, i0 = j0 + gbase;
     if (i0 <= bb) {
       double acc[FIR_RT];
 #pragma unroll
@@ -399,7 +407,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) {
         const int i = i0 + r;
-        if (i >= ba && i <= bb) w.yv[L - 1 - p - i] = acc[r] + (i < T - 1 ? zi[i] * yend : 0.0);
+        if (i <= bb) w.yv[L - 1 - p - i] = acc[r] + (i < T - 1 ? zi[i] * yend : 0.0);
       }
     }
   }
@@ -558,9 +566,9 @@ extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y,
   const size_t smem = (size_t)wpb * L.total;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(window_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = 227 * 1024;
+    configured = smem;
   }
   const long long nsig = J * p->R;
   window_preprocess_kernel<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, *p, L, sos_ws, taps_ws,

@@ -158,7 +158,7 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   const size_t smem = (size_t)(3 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(double);
   BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_xcorr: window %d too large for shared memory", W);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
   xcorr_kernel<<<(unsigned)n, 128, smem, (cudaStream_t)stream>>>(proc_x, proc_y, *p, corr_lag, corr_val, num_lags, lag_idx, lag_sec, lag_corr);

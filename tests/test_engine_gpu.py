@@ -151,3 +151,51 @@ def test_zero_copy_host_frames():
             if boxes_np[f, r, 0] == synth.NO_BOX:
                 continue
             assert tuple(int(v) for v in sums[f, r].cpu()) == orc.roi_sums(fn[f], boxes_np[f, r])
+
+
+@pytest.mark.parametrize('name,cfg', [
+    # BASELINE configs[3]: 720p-class 120 fps streams, W = n = 1200, spline resample + band-pass, LS HR, all 2399 xcorr lags
+    ('c4_full', dict(W=1200, fps=120.0, methods=[orc.INTERP_CUBIC, orc.FILTER_BUTTER], transform=orc.PGRAM_LS, kw={})),
+    # BASELINE configs[2]: irregular timestamps, LS on a 2048-frequency grid, no interpolation
+    ('c3_full', dict(W=300, fps=30.0, methods=[], transform=orc.PGRAM_LS, kw=dict(ls_num_freqs=2048))),
+    # BASELINE configs[4]/[0]: Butterworth + LS F = n = 300
+    ('c5_full', dict(W=300, fps=30.0, methods=[orc.FILTER_BUTTER], transform=orc.PGRAM_LS, kw=dict(min_freq=0.7))),
+    ('welch_long', dict(W=1200, fps=120.0, methods=[orc.DETREND_LINEAR, orc.FILTER_FIR], transform=orc.PGRAM_WELCH, kw={})),
+    ('dft_long', dict(W=1200, fps=120.0, methods=[orc.FILTER_BUTTER], transform=orc.DFT_RFFT, kw={})),
+])
+def test_full_size_windows_signals_only(name, cfg):
+    """Full BASELINE window sizes through step_signals (steady state: full windows, irregular timestamps, dropped
+    detections), every output against the oracle."""
+    from bpv import synth
+    from bpv.engine import BatchedSignalProcessor
+    S, R, W = 3, 2, cfg['W']
+    rng = np.random.default_rng(len(name))
+    n = W + 3
+    ts = np.stack([synth.timestamps(rng, n, cfg['fps'], irregular=True, drop=0.05) for _ in range(S)])
+    ys = np.stack([synth.raw_signals(rng, ts[s], R=R, p_nan=0.02) for s in range(S)])          # [S, R, n]
+    eng = BatchedSignalProcessor(S, R, signal_max_samples=W, max_frames_per_step=W, processing_methods=cfg['methods'],
+                                 spectrum_transform=cfg['transform'], windows='last', store_arrays=True, **cfg['kw'])
+    eng.step_signals(torch.from_numpy(np.ascontiguousarray(ys[:, :, :W].transpose(0, 2, 1))).cuda(), torch.from_numpy(ts[:, :W].copy()).cuda())
+    for g in range(W, n):
+        res = eng.step_signals(torch.from_numpy(np.ascontiguousarray(ys[:, :, g:g + 1].transpose(0, 2, 1))).cuda(),
+                               torch.from_numpy(ts[:, g:g + 1].copy()).cuda())
+        a = {k: v.cpu().numpy() for k, v in res.arrays.items()}
+        pidx, lidx = res.peak_idx.cpu().numpy(), res.lag_idx.cpu().numpy()
+        bpm, ptt = res.bpm.cpu().numpy(), res.ptt_ms.cpu().numpy()
+        for s in range(S):
+            tw = ts[s, g - W + 1:g + 1]
+            proc = [orc.preprocess(tw, ys[s, r, g - W + 1:g + 1], cfg['methods'], **cfg['kw']) for r in range(R)]
+            for r in range(R):
+                assert h.close(a['proc_y'][s, r], proc[r][1], rtol=1e-6, atol_frac=1e-7), (name, s, r)
+                ef, em = orc.spectrum(proc[r][0], proc[r][1], cfg['transform'], **cfg['kw'])
+                ex, ey, ei = orc.peak(ef, em)
+                F = a['num_bins'][s, r]
+                assert F == len(ef)
+                assert h.close(a['mags'][s, r, :F], em, rtol=1e-4, atol_frac=1e-5), (name, s, r, np.nanmax(np.abs(a['mags'][s, r, :F] - em)))
+                assert pidx[s, r] == ei, (name, s, r, pidx[s, r], ei)
+                assert h.close(bpm[s, r], ex * 60, rtol=1e-12, atol_frac=0)
+            el, ec = orc.xcorr(proc[0][0], proc[0][1], proc[1][1])
+            lx, ly, li = orc.peak(el, ec)
+            L = a['num_lags'][s, 0]
+            assert L == len(el) and h.close(a['corr'][s, 0, :L], ec, rtol=1e-4, atol_frac=1e-6)
+            assert lidx[s, 0] == li and h.close(ptt[s, 0], lx * 1000, rtol=1e-12, atol_frac=0)
