@@ -191,3 +191,19 @@ def test_signal_processor_surface_matches_reference_signature():
     st = sp.SignalStore(2, 1, 250, 50)
     assert [len(s.x) for s in st.sg_raw] == [250, 250] and st.sg_corr.num_signals == 1 and st.sg_roi.signals[0].y.shape == (1, 6)
     pickle.loads(pickle.dumps(st.snapshot()))
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason='reference not mounted (GPU box)')
+def test_reference_modules_import_on_top_of_the_drop_in():
+    """PYTHONPATH=<ours>:<reference>: the reference's own video_reader must import against OUR profiler/exceptions,
+    and `signal_processor` / `roi` / `signal_data` must resolve to the drop-in."""
+    import subprocess
+    code = ("import sys, video_reader, signal_processor, roi, signal_data, profiler, exceptions;"
+            "assert 'bp-from-video_b200' in signal_processor.__file__ and 'bp-from-video_b200' in roi.__file__;"
+            "assert 'bp-from-video_b200' in profiler.__file__ and video_reader.__file__.startswith('/root/reference');"
+            "assert issubclass(exceptions.CaptureError, RuntimeError);"
+            "p = signal_processor.SignalProcessor(); assert p.num_signals == 2 and p.store.sg_corr.num_signals == 1;"
+            "print('ok')")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'bp-from-video_b200') + ':' + REF)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
