@@ -123,7 +123,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -283,7 +283,7 @@ def run_gpu(args, wl):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    ke = max(3, min(args.steps, 10))
+    ke = max(3, min(args.steps, 20))
     for _ in range(ke):
         e2e_step()
     barrier()
@@ -344,13 +344,13 @@ def run_gpu(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='bpv', choices=['bpv', 'reference'])
     ap.add_argument('--workload', default='c2', choices=list(WORKLOADS))
     ap.add_argument('--windows', default='every_frame', choices=['every_frame', 'last'])
     ap.add_argument('--ref-frames', type=int, default=2048, help='CPU arm: steady-state frames per stream/core')
-    ap.add_argument('--e2e-frames', type=int, default=4, help='frames per stream per e2e step (pinned host memory)')
+    ap.add_argument('--e2e-frames', type=int, default=8, help='frames per stream per e2e step (pinned host memory)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
