@@ -53,7 +53,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 __device__ void firls_design_warp(double fs, int taps, double min_freq, double max_freq, double df,
-                                  double* __restrict__ out, double* smem) {
+                                  double* __restrict__ out, double* __restrict__ zi_out, double* smem) {
   const int M = (taps - 1) / 2, n = taps;
   double* r = smem;                 // [128] first column of T: q[0 .. taps-1]
   double* y = r + 128;              // [128] symmetric right-hand side
@@ -119,6 +119,24 @@ __device__ void firls_design_warp(double fs, int taps, double min_freq, double m
     const int i = lane + 32 * m;
     if (i < n) out[i] = x[m];
   }
+  if (zi_out) {
+    // lfilter_zi(b, [1]) = suffix sums of b[1:] (scipy/signal/_signaltools.py:4440-4463): zi[i] = sum_{k>i} b[k].
+    // Lane l holds taps l, l+32, l+64, l+96; suffix sums per 32-chunk by a shuffle scan, chunks chained.
+    double carry = 0.0;                                   // sum of all taps in higher chunks
+#pragma unroll
+    for (int m = 3; m >= 0; --m) {
+      const int i = lane + 32 * m;
+      const double v = i < n ? x[m] : 0.0;
+      double incl = v;                                    // inclusive suffix sum over lanes >= lane
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
+      }
+      if (i < n - 1) zi_out[i] = (incl - v) + carry;      // strictly-greater taps
+      carry += __shfl_sync(0xffffffffu, incl, 0);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const double* __restrict__ fs, int n, int taps, double min_freq,
@@ -126,7 +144,7 @@ __global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const doub
   extern __shared__ double smem[];
   const int w = threadIdx.x >> 5, job = blockIdx.x * FIRLS_WARPS + w;
   if (job >= n) return;
-  firls_design_warp(fs[job], taps, min_freq, max_freq, df, out + (long long)job * taps, smem + w * FIRLS_WS);
+  firls_design_warp(fs[job], taps, min_freq, max_freq, df, out + (long long)job * taps, nullptr, smem + w * FIRLS_WS);
 }
 
 // ---- per-job design from the ring timestamps (used by the window pipeline) ----------------------
@@ -153,17 +171,20 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
   const double* rt = ring_t + (long long)s * p.cap;
   const long long g0 = p.head0 + (long long)j * p.head_step - p.window + 1;
   int lo = 0x7fffffff, hi = -1, cnt = 0;
+  const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
+  const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
   for (int k = lane; k < p.window; k += 32) {
-    const long long g = g0 + k;
-    if (g >= 0 && isfinite(rt[g % p.cap])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+    int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
+    if (k >= kmin && isfinite(rt[slot])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
     lo = lo < l2 ? lo : l2; hi = hi > h2 ? hi : h2; cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
   double fs = nan_f64();
-  if (cnt >= 2) fs = 1.0 / ((rt[(g0 + hi) % p.cap] - rt[(g0 + lo) % p.cap]) / (double)(cnt - 1));
-  firls_design_warp(fs, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, out + (long long)job * p.fir_taps, smem + w * FIRLS_WS);
+  if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
+  firls_design_warp(fs, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, out + (long long)job * 256, out + (long long)job * 256 + 128,
+                    smem + w * FIRLS_WS);
 }
 
 constexpr size_t FIRLS_SMEM = (size_t)FIRLS_WARPS * FIRLS_WS * sizeof(double);

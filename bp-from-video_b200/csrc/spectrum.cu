@@ -283,8 +283,14 @@ __device__ double ls_eval_f64(const double* __restrict__ t, const double* __rest
   return 2.0 * (a * YC + b * YS) * (0.5 / YY);
 }
 
-// Coarse fp32 pass.  grid = (nsig, ceil(Fmax / 128)), block = 128 threads = 128 frequencies.
-// smem floats: th[W] | tl[W] | yc[W]; doubles for the gather scratch come first.
+// Coarse fp32 pass.  grid = (nsig, ceil(Fmax / (LS_NF * blockDim))), thread t of tile T owns the LS_NF
+// frequencies k = T*LS_NF*blockDim + t + m*blockDim, m = 0..LS_NF-1.  The grid is uniform, so consecutive
+// frequencies of a thread differ by D = blockDim*df and exp(i*2pi*(f+D)*t_j) = exp(i*2pi*f*t_j) * rot_j with
+// rot_j = exp(i*2pi*D*t_j) shared by the whole CTA: one sincos (2 MUFU + exact phase reduction) per sample
+// per thread, then LS_NF-1 complex rotations (4 FP32 ops each) — the kernel is issue-bound, and this cuts
+// the instructions per (sample, frequency) pair from ~26 to ~13.
+// smem: doubles xs[W] | ys[W] (gather scratch), then float4 {t_hi, t_lo, y - mean, 0}[W], float2 rot[W].
+constexpr int LS_NF = 4;
 __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                         const bpv_window_params p, int max_bins,
                                                         float* __restrict__ spec_f, float* __restrict__ psd) {
@@ -292,65 +298,86 @@ __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict
   __shared__ int s_cnt[4];
   __shared__ double s_d[2];
   __shared__ double s_red[33];
-  const int W = p.window, tid = threadIdx.x;
+  const int W = p.window, tid = threadIdx.x, BD = blockDim.x;
   const long long sig = blockIdx.x;
   double* xs = sm;            // [W]
   double* ys = xs + W;        // [W]
-  float* th = reinterpret_cast<float*>(ys + W);
-  float* tl = th + W;
-  float* yc = tl + W;
+  float4* smp = reinterpret_cast<float4*>(ys + W);    // [W]
+  float2* rot = reinterpret_cast<float2*>(smp + W);   // [W]
   const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, xs, ys, s_cnt, s_d);
   const int n = si.n;
   if (!(n >= 2 && isfinite(si.fs))) return;              // peak kernel reports the empty spectrum
   const int F = p.ls_num_freqs > 0 ? p.ls_num_freqs : n;
-  if ((int)blockIdx.y * 128 >= F) return;
+  const int kbase = blockIdx.y * LS_NF * BD;
+  if (kbase >= F) return;
   // centre y (floating mean makes this a no-op mathematically; it is what keeps fp32 usable)
   double a = 0.0;
-  for (int j = tid; j < n; j += blockDim.x) a += ys[j];
+  for (int j = tid; j < n; j += BD) a += ys[j];
   const double mean = block_sum(a, s_red) / (double)n;
   double q = 0.0;
   const double t0 = xs[0];
-  for (int j = tid; j < n; j += blockDim.x) {
+  const double dstep = F > 1 ? (p.max_freq - p.min_freq) / (double)(F - 1) : 0.0;
+  const double D = dstep * (double)BD;                    // frequency distance between a thread's bins
+  for (int j = tid; j < n; j += BD) {
     const double d = ys[j] - mean, t = xs[j] - t0;
     q = fma(d, d, q);
     const float hi = (float)t;
-    th[j] = hi; tl[j] = (float)(t - (double)hi); yc[j] = (float)d;
+    smp[j] = make_float4(hi, (float)(t - (double)hi), (float)d, 0.f);
+    double ph = D * t;
+    ph -= rint(ph);
+    double sr, cr;
+    sincospi(2.0 * ph, &sr, &cr);
+    rot[j] = make_float2((float)cr, (float)sr);
   }
-  const double YY = block_sum(q, s_red) / (double)n;     // variance (Y = 0 after centring)
-  const int k = blockIdx.y * 128 + tid;
-  if (k >= F) return;
-  const double f = ls_freq(k, F, p.min_freq, p.max_freq);
+  const double YY = block_sum(q, s_red) / (double)n;     // variance (Y = 0 after centring); barrier inside
+  const int k0 = kbase + tid;
+  const double f = ls_freq(k0 < F ? k0 : F - 1, F, p.min_freq, p.max_freq);
   const float fh = (float)f, fl = (float)(f - (double)fh);
-  float C = 0.f, S = 0.f, CC = 0.f, CS = 0.f, YC = 0.f, YS = 0.f;
-#pragma unroll 4
+  float C[LS_NF], S[LS_NF], CC[LS_NF], CS[LS_NF], YC[LS_NF], YS[LS_NF];
+#pragma unroll
+  for (int m = 0; m < LS_NF; ++m) { C[m] = S[m] = CC[m] = CS[m] = YC[m] = YS[m] = 0.f; }
+#pragma unroll 2
   for (int j = 0; j < n; ++j) {
-    const float t_hi = th[j], t_lo = tl[j], yv = yc[j];
-    const float ph = fh * t_hi;
-    const float e1 = fmaf(fh, t_hi, -ph);                 // exact low part of the product
-    const float e2 = fmaf(fh, t_lo, fl * t_hi);
+    const float4 sv = smp[j];
+    const float2 rv = rot[j];
+    const float ph = fh * sv.x;
+    const float e1 = fmaf(fh, sv.x, -ph);                 // exact low part of the product
+    const float e2 = fmaf(fh, sv.y, fl * sv.x);
     const float r = (ph - rintf(ph)) + (e1 + e2);          // phase in turns, [-0.5, 0.5]
     float s, c;
     __sincosf(6.283185307179586f * r, &s, &c);
-    C += c; S += s;
-    CC = fmaf(c, c, CC); CS = fmaf(c, s, CS);
-    YC = fmaf(yv, c, YC); YS = fmaf(yv, s, YS);
+#pragma unroll
+    for (int m = 0; m < LS_NF; ++m) {
+      C[m] += c; S[m] += s;
+      CC[m] = fmaf(c, c, CC[m]); CS[m] = fmaf(c, s, CS[m]);
+      YC[m] = fmaf(sv.z, c, YC[m]); YS[m] = fmaf(sv.z, s, YS[m]);
+      if (m + 1 < LS_NF) {                                 // advance to the next bin: (c, s) *= rot_j
+        const float c2 = fmaf(c, rv.x, -s * rv.y), s2 = fmaf(s, rv.x, c * rv.y);
+        c = c2; s = s2;
+      }
+    }
   }
   // closed-form tau rotation + floating-mean corrections, once per frequency, in float64
   const double w = 1.0 / (double)n;
-  const double dC = C * w, dS = S * w, dCC = CC * w, dCS = CS * w, dYC = YC * w, dYS = YS * w;
-  const double cc0 = dCC - dC * dC, ss0 = (1.0 - dCC) - dS * dS, cs0 = dCS - dC * dS;
-  const double tau = 0.5 * atan2(2.0 * cs0, cc0 - ss0);
-  double st, ct;
-  sincos(tau, &st, &ct);
-  const double YCt = ct * dYC + st * dYS, YSt = ct * dYS - st * dYC;
-  const double Ct = ct * dC + st * dS, St = ct * dS - st * dC;
-  const double CCraw = ct * ct * dCC + 2.0 * ct * st * dCS + st * st * (1.0 - dCC);
-  double CCt = CCraw - Ct * Ct, SSt = (1.0 - CCraw) - St * St;
-  if (CCt < EPSNEG) CCt = EPSNEG;
-  if (SSt < EPSNEG) SSt = EPSNEG;
-  const double pw = 2.0 * (YCt * YCt / CCt + YSt * YSt / SSt) * (0.5 / YY);
-  psd[sig * max_bins + k] = (float)pw;
-  if (spec_f) spec_f[sig * max_bins + k] = (float)f;
+#pragma unroll
+  for (int m = 0; m < LS_NF; ++m) {
+    const int k = k0 + m * BD;
+    if (k >= F) break;
+    const double dC = C[m] * w, dS = S[m] * w, dCC = CC[m] * w, dCS = CS[m] * w, dYC = YC[m] * w, dYS = YS[m] * w;
+    const double cc0 = dCC - dC * dC, ss0 = (1.0 - dCC) - dS * dS, cs0 = dCS - dC * dS;
+    const double tau = 0.5 * atan2(2.0 * cs0, cc0 - ss0);
+    double st, ct;
+    sincos(tau, &st, &ct);
+    const double YCt = ct * dYC + st * dYS, YSt = ct * dYS - st * dYC;
+    const double Ct = ct * dC + st * dS, St = ct * dS - st * dC;
+    const double CCraw = ct * ct * dCC + 2.0 * ct * st * dCS + st * st * (1.0 - dCC);
+    double CCt = CCraw - Ct * Ct, SSt = (1.0 - CCraw) - St * St;
+    if (CCt < EPSNEG) CCt = EPSNEG;
+    if (SSt < EPSNEG) SSt = EPSNEG;
+    const double pw = 2.0 * (YCt * YCt / CCt + YSt * YSt / SSt) * (0.5 / YY);
+    psd[sig * max_bins + k] = (float)pw;
+    if (spec_f) spec_f[sig * max_bins + k] = (float)ls_freq(k, F, p.min_freq, p.max_freq);
+  }
 }
 
 // Peak pass: one CTA (128 threads) per signal.  smem doubles: ts[W] | ys[W] | cand_val[max_bins];
@@ -486,13 +513,15 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
                 "bpv_window_spectrum: workspace too small (see bpv_spectrum_workspace_bytes)");
     psd = (float*)workspace;
   }
-  const size_t smem_c = (size_t)W * (2 * sizeof(double) + 3 * sizeof(float));
+  const size_t smem_c = (size_t)W * (2 * sizeof(double) + sizeof(float4) + sizeof(float2));
   const size_t smem_p = (size_t)W * 2 * sizeof(double) + (size_t)max_bins * (sizeof(double) + sizeof(int));
   BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
   if (smem_c > 48 * 1024) cudaFuncSetAttribute(ls_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
   if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-  dim3 grid((unsigned)nsig, (Fmax + 127) / 128);
-  ls_coarse_kernel<<<grid, 128, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
+  int bd = ((Fmax + LS_NF - 1) / LS_NF + 31) / 32 * 32;     // threads per CTA: enough for Fmax in one tile, up to 128
+  if (bd > 128) bd = 128;
+  dim3 grid((unsigned)nsig, (Fmax + LS_NF * bd - 1) / (LS_NF * bd));
+  ls_coarse_kernel<<<grid, bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
   if (int rc = check_launch("ls_coarse_kernel")) return rc;
   ls_peak_kernel<<<(unsigned)nsig, 128, smem_p, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd, num_bins, peak_idx, peak_freq, peak_mag);
   return check_launch("ls_peak_kernel");

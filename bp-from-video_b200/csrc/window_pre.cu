@@ -346,11 +346,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   double* b = w.coef;          // [Kp] zero padded
   double* zi = w.coef + 128;   // [T-1]
   for (int i = w.lane; i < Kp; i += 32) b[i] = i < T ? taps_g[i] : 0.0;
-  __syncwarp();
-  if (w.lane == 0) {
-    double acc = 0.0;
-    for (int i = T - 2; i >= 0; --i) { acc += b[i + 1]; zi[i] = acc; }
-  }
+  for (int i = w.lane; i < T - 1; i += 32) zi[i] = taps_g[128 + i];   // lfilter_zi, from the design kernel
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
   const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);   // forward outputs needed
@@ -455,12 +451,14 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   int n = 0, m = 0;
   double xfirst = 0.0, xlast = 0.0;
   const unsigned lt = (1u << w.lane) - 1u;
+  const long long gfirst = head - W + 1;                      // global index of window position 0
+  const int kmin = gfirst < 0 ? (int)(-gfirst < W ? -gfirst : W) : 0;   // positions before the stream started: NaN
+  const int slot0 = (int)(((gfirst % p.cap) + p.cap) % p.cap);       // ring slot of position 0 (one 64-bit modulo)
   for (int k0 = 0; k0 < W; k0 += 32) {
     const int k = k0 + w.lane;
     double x = nan_f64(), y = nan_f64();
     if (k < W) {
-      const long long g = head - W + 1 + k;
-      if (g >= 0) { const int slot = (int)(g % p.cap); x = rt[slot]; y = ry[slot]; }
+      if (k >= kmin) { int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap; x = rt[slot]; y = ry[slot]; }
       ox[k] = x; oy[k] = y;
     }
     const bool fx = isfinite(x), fy = isfinite(y);
@@ -501,7 +499,7 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
         break;
       }
       case BPV_FILTER_FIR: {
-        const double* tg = taps_ws + (long long)jobi * p.fir_taps;
+        const double* tg = taps_ws + (long long)jobi * 256;
         if (!isfinite(tg[0])) { st = ST_BAD_BANDS; break; }
         fir_filtfilt(w, tg, p.fir_taps);
         break;
@@ -527,7 +525,7 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
 extern "C" int64_t bpv_window_workspace_bytes(const bpv_window_params* p) {
   if (!p) return -1;
   const int64_t J = (int64_t)p->S * p->jobs_per_stream;
-  return J * (int64_t)(bpv::MAX_SOS * 6 + 128) * 8;
+  return J * (int64_t)(bpv::MAX_SOS * 6 + 256) * 8;   // per job: sos[16][6] | taps[128] | zi[128]
 }
 
 extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
@@ -561,8 +559,17 @@ extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y,
   const int max_smem = 200 * 1024;
   BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
               p->window, L.total);
-  int wpb = max_smem / L.total;
-  if (wpb > 4) wpb = 4;
+  // warps (signals) per CTA: the value in 1..8 that keeps the most warps resident per SM
+  int wpb = 1, best = 0;
+  for (int c = 1; c <= 8; ++c) {
+    const int per_block = c * L.total + 1024;                  // + per-CTA reservation
+    if (per_block > max_smem) break;
+    int blocks = (227 * 1024) / per_block;
+    if (blocks > 32) blocks = 32;
+    int warps = blocks * c;
+    if (warps > 16) warps = 16;                                // register file: ~126 regs/thread -> 16 warps
+    if (warps > best || (warps == best && c < wpb)) { best = warps; wpb = c; }
+  }
   const size_t smem = (size_t)wpb * L.total;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
