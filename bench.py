@@ -273,19 +273,45 @@ def run_gpu(args, wl):
     host_out = torch.empty((S * (Te if args.windows == 'every_frame' else 1), rec.shape[1]), dtype=torch.float64, pin_memory=True)
     e2e_roi_bytes = roi_bytes(boxes_np[:, :Te], H, W)
 
-    def e2e_step():
+    # Two-stage software pipeline over two CUDA streams: F1 of batch k+1 (PCIe bound: ROI rows read straight from
+    # pinned host memory) runs on a side stream while the window pipeline of batch k runs on the main stream and its
+    # records are copied back.  Every batch's inputs start in host memory and its results end in host memory inside
+    # the timed region; K batches are timed from the first F1 launch to the last result landing on the host.
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    sbuf = [torch.empty((S, Te, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+    bbuf = [torch.empty((S, Te, 2, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def launch_f1(k):
+        side.wait_event(done[k % 2])                        # buffer k%2 is free once batch k-2 has consumed it
+        with torch.cuda.stream(side):
+            bbuf[k % 2].copy_(host_boxes, non_blocking=True)
+            eng.roi_samples(host_frames, bbuf[k % 2], out=sbuf[k % 2])
+            evs[k % 2].record(side)
+
+    def finish(k):
         host_ts.copy_(torch.from_numpy((t_next[0] + (np.arange(Te) + 1) / fps)[None, :].repeat(S, 0)))
         t_next[0] += Te / fps
-        r = eng.step(host_frames, host_boxes.to(dev, non_blocking=True), host_ts.to(dev, non_blocking=True))
+        main.wait_event(evs[k % 2])
+        r = eng.step_signals(sbuf[k % 2], host_ts.to(dev, non_blocking=True))
+        done[k % 2].record(main)
         host_out.copy_(r.packed(), non_blocking=True)
-        torch.cuda.synchronize()
-    for _ in range(3):
-        e2e_step()
+        torch.cuda.synchronize(dev) if False else main.synchronize()
+
+    def run_e2e(K):
+        launch_f1(0)
+        for k in range(K):
+            if k + 1 < K:
+                launch_f1(k + 1)
+            finish(k)
+
+    run_e2e(4)
     barrier()
+    ke = max(4, min(args.steps, 40))
     t0 = time.perf_counter()
-    ke = max(3, min(args.steps, 20))
-    for _ in range(ke):
-        e2e_step()
+    run_e2e(ke)
     barrier()
     e2e_s = (time.perf_counter() - t0) / ke
     if world > 1:
@@ -330,8 +356,9 @@ def run_gpu(args, wl):
         'e2e': {'value': world * S * Te / e2e_s, 'unit': UNIT,
                 'h2d_bytes_per_step': int(e2e_roi_bytes + host_boxes.numel() * 4 + host_ts.numel() * 8),
                 'd2h_bytes_per_step': int(host_out.numel() * 8), 'frames_per_stream_per_step': Te,
-                'how': 'BatchedSignalProcessor.step on pinned HOST frames/boxes/timestamps; F1 reads the ROI rows zero-copy '
-                       'over PCIe (the other 99.5 % of each frame never crosses the bus); records copied back to host; wall clock'},
+                'how': 'BatchedSignalProcessor.roi_samples + step_signals on pinned HOST frames/boxes/timestamps; F1 reads the '
+                       'ROI rows zero-copy over PCIe (the other 99.5 % of each frame never crosses the bus) on a side stream, '
+                       'overlapped with the previous batch\'s window pipeline; records copied back to host every batch; wall clock'},
     }
     if cpu_rate is not None:
         line['cpu_baseline'] = {'value': cpu_rate, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
@@ -339,6 +366,15 @@ def run_gpu(args, wl):
                                           f'oracle port of SignalProcessor.process per frame, one process per core; '
                                           f'{cpu_t:.1f} s of CPU work per core'}
     print(json.dumps(line), flush=True)
+
+
+def _shutdown():
+    try:
+        import torch.distributed as tdist
+        if tdist.is_available() and tdist.is_initialized():
+            tdist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def main():
@@ -357,7 +393,10 @@ def main():
     if args.impl == 'reference':
         run_reference(args, wl)
     else:
-        run_gpu(args, wl)
+        try:
+            run_gpu(args, wl)
+        finally:
+            _shutdown()
 
 
 if __name__ == '__main__':

@@ -109,6 +109,18 @@ class BatchedSignalProcessor:
                        roi_pixels_hint=self.roi_pixels_hint, out_value=samples.view(S * T, self.R))
         return self.step_signals(samples, timestamps, _count_roi=True)
 
+    def roi_samples(self, frames: torch.Tensor, boxes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """F1 only, on the current stream: float64 [S, T, R] samples of frames uint8 [S, T, H, W, 3].  Lets a caller
+        overlap the ROI sampling of the next batch (e.g. zero-copy from pinned host memory, PCIe bound) with the
+        window pipeline of the current one: run this on a side stream, then `step_signals` on the main stream."""
+        S, T = frames.shape[:2]
+        assert S == self.S and boxes.shape == (S, T, self.R, 4)
+        if out is None:
+            out = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)
+        ops.roi_sample(frames.view(S * T, *frames.shape[2:]), boxes.view(S * T, self.R, 4), self.color_channel,
+                       roi_pixels_hint=self.roi_pixels_hint, out_value=out.view(S * T, self.R))
+        return out
+
     def step_signals(self, samples: torch.Tensor, timestamps: torch.Tensor, _count_roi: bool = False) -> StepResult:
         """Signals-only entry: samples float64 [S, T, R] (already ROI-sampled), timestamps float64 [S, T]."""
         S, T, R = samples.shape
