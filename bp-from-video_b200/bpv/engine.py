@@ -109,6 +109,27 @@ class BatchedSignalProcessor:
                        roi_pixels_hint=self.roi_pixels_hint, out_value=samples.view(S * T, self.R))
         return self.step_signals(samples, timestamps, _count_roi=True)
 
+    # ------------------------------------------------------------------------------------------
+    # calc_rois + ROI smoothing on the device for batched landmark tensors
+    def set_roi_configs(self, relative_bboxes, num_points, roi_max_samples: int = 1):
+        """relative_bboxes [R][4] (left, top, right, bottom) and the number of anchor landmarks per ROI, as in
+        roi.ROIConfig (roi.py:8-13); roi_max_samples = length of the smoothing history (signal_processor.py:47)."""
+        assert len(relative_bboxes) == self.R and len(num_points) == self.R
+        self._rel = torch.tensor(relative_bboxes, dtype=torch.float64, device=self.device).contiguous()
+        self._npts = torch.tensor(num_points, dtype=torch.int32, device=self.device)
+        self._roi_hist = torch.full((self.S, self.R, int(roi_max_samples), 6), float('nan'), dtype=torch.float64, device=self.device)
+        self._roi_count = 0
+
+    def step_detections(self, frames, present, bbox, points, timestamps, want_locations: bool = False):
+        """One step from detector outputs instead of boxes: present u8 [S,T,R], bbox i32 [S,T,R,4] (largest detection
+        of the ROI's model), points i32 [S,T,R,K,2] (the landmarks the ROI config selects).  Returns (StepResult, boxes
+        [, locations, smoothed])."""
+        out = ops.calc_rois(present, bbox, points, self._npts, self._rel, self._roi_hist, self._roi_count, want_locations)
+        self._roi_count += present.shape[1]
+        boxes = out[0] if want_locations else out
+        res = self.step(frames, boxes, timestamps)
+        return (res, *out) if want_locations else (res, boxes)
+
     def roi_samples(self, frames: torch.Tensor, boxes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """F1 only, on the current stream: float64 [S, T, R] samples of frames uint8 [S, T, H, W, 3].  Lets a caller
         overlap the ROI sampling of the next batch (e.g. zero-copy from pinned host memory, PCIe bound) with the

@@ -53,6 +53,21 @@ def roi_sample_ptrs(frame_ptrs: torch.Tensor, H: int, W: int, row_stride: int, b
     return out_value, sums
 
 
+def calc_rois(present, bbox, points, num_points, rel_bbox, hist, g0: int, want_locations: bool = False):
+    """Batched calc_rois + ROI smoothing (signal_processor.py:133-155, 304-305).  present u8 [S,T,R], bbox i32 [S,T,R,4],
+    points i32 [S,T,R,K,2], num_points i32 [R], rel_bbox f64 [R,4], hist f64 [S,R,H,6] (state, NaN-initialised).
+    Returns boxes i32 [S,T,R,4] (+ locations, smoothed f64 [S,T,R,6] when want_locations)."""
+    S, T, R = present.shape
+    K, H = points.shape[3], hist.shape[2]
+    dev = present.device
+    boxes = torch.empty((S, T, R, 4), dtype=torch.int32, device=dev)
+    loc = torch.empty((S, T, R, 6), dtype=torch.float64, device=dev) if want_locations else None
+    smo = torch.empty((S, T, R, 6), dtype=torch.float64, device=dev) if want_locations else None
+    check(lib().bpv_calc_rois(ptr(present), ptr(bbox), ptr(points), ptr(num_points), ptr(rel_bbox), S, T, R, K, H, int(g0),
+                              ptr(hist), ptr(loc), ptr(smo), ptr(boxes), stream_handle()), 'bpv_calc_rois')
+    return (boxes, loc, smo) if want_locations else boxes
+
+
 def ring_push(ring_t: torch.Tensor, ring_y: torch.Tensor, g0: int, ts: torch.Tensor, values: torch.Tensor):
     """Append T samples per stream (signal_data.py:31-35, 94-98).  ring_t f64 [S,cap], ring_y f64 [S,R,cap],
     ts f64 [S,T], values f64 [S,T,R]."""

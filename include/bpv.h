@@ -87,6 +87,22 @@ int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
                       int64_t roi_pixels_hint, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ROI geometry for batched landmark tensors — replaces SignalProcessor.calc_rois and the ROI smoothing
+ *     sg_roi.add_samples + get_means(as_int=True) (signal_processor.py:133-155, 304-305; signal_data.py:60-63).
+ *
+ * Per (stream, frame, ROI): present uint8 [S,T,R] (0 = no detection of the ROI's model), bbox int32 [S,T,R,4]
+ * of the largest detection, points int32 [S,T,R,K,2] = the landmark points the ROI config selects (first
+ * num_points[r] <= K used), rel_bbox float64 [R,4] = (left, top, right, bottom).
+ * hist float64 [S,R,H,6] is the smoothing state (H = roi_max_samples; fill with NaN before the first call), g0 =
+ * frames pushed so far.  Outputs: locations / smoothed float64 [S,T,R,6] (x, y, x0, y0, x1, y1; NaN rows; may be
+ * NULL) and boxes int32 [S,T,R,4] ready for bpv_roi_sample_u8 (x0 == BPV_NO_BOX when no box).
+ */
+int bpv_calc_rois(const uint8_t* present, const int32_t* bbox, const int32_t* points,
+                  const int32_t* num_points, const double* rel_bbox,
+                  int32_t S, int32_t T, int32_t R, int32_t K, int32_t H, int64_t g0,
+                  double* hist, double* locations, double* smoothed, int32_t* boxes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Ring buffers — replaces Signal.add_sample / SignalGroup.add_samples for sg_raw
  *     (signal_data.py:31-35, 94-98; deque(maxlen) prefilled with NaN, signal_data.py:18-19).
  *
