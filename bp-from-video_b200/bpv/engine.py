@@ -39,6 +39,7 @@ class StepResult:
     lag_corr: torch.Tensor                # f64 [J, P]
     status: torch.Tensor                  # i32 [J, R]
     arrays: dict = field(default_factory=dict)   # proc_x/proc_y/freqs/mags/lags/corr/num_bins/num_lags when stored
+    means: dict = field(default_factory=dict)    # mean_bpm, mean_bpm_int [J, R], mean_ptt, mean_ptt_int [J, P] when tracked
 
     @property
     def bpm(self):                        # signal_processor.py:310  f * 60
@@ -59,7 +60,7 @@ class BatchedSignalProcessor:
                  spectrum_transform: int = _cabi.PGRAM_LS, butter_order: int = 16, butter_min_bw: float = 0.1,
                  fir_taps: int = 127, fir_df: float = 0.3, min_freq: float = 0.8, max_freq: float = 4.0,
                  ls_num_freqs: int | None = None, windows: str = EVERY_FRAME, store_arrays: bool = False,
-                 device: str | torch.device = 'cuda', roi_pixels_hint: int = 0):
+                 device: str | torch.device = 'cuda', roi_pixels_hint: int = 0, peak_max_samples: int = 0):
         _cabi.lib()  # fail loudly if the CUDA library is missing: there is no CPU fallback
         if not torch.cuda.is_available():
             raise _cabi.BpvError('BatchedSignalProcessor needs a CUDA device (no CPU fallback)')
@@ -92,6 +93,12 @@ class BatchedSignalProcessor:
         self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self._spec = self._xc = None
         self.launches_per_step = 0
+        # sg_bpm / sg_ptt histories and their running means on the device (0 = off)
+        self.peak_max_samples = int(peak_max_samples)
+        if self.peak_max_samples:
+            self._bpm_ring = torch.full((self.S, self.R, self.peak_max_samples), float('nan'), dtype=f64, device=dev)
+            self._ptt_ring = torch.full((self.S, max(self.P, 1), self.peak_max_samples), float('nan'), dtype=f64, device=dev)
+            self._mean_count = 0
 
     # ------------------------------------------------------------------------------------------
     def _params(self, head0: int, head_step: int, jobs: int) -> _cabi.WindowParams:
@@ -167,8 +174,17 @@ class BatchedSignalProcessor:
         if self.store_arrays:
             arrays = dict(proc_x=px, proc_y=py, freqs=sp['freqs'], mags=sp['mags'], num_bins=sp['num_bins'],
                           lags=xc['lags'], corr=xc['corr'], num_lags=xc['num_lags'])
+        means = {}
+        if self.peak_max_samples:
+            mb, mbi = ops.running_mean(self._bpm_ring, self._mean_count, sp['peak_freq'].view(S, jobs, self.R), 60.0)
+            means = dict(mean_bpm=mb.view(J, self.R), mean_bpm_int=mbi.view(J, self.R))
+            if self.P:
+                mp, mpi = ops.running_mean(self._ptt_ring, self._mean_count, xc['lag_sec'].view(S, jobs, self.P), 1000.0)
+                means.update(mean_ptt=mp.view(J, self.P), mean_ptt_int=mpi.view(J, self.P))
+            self._mean_count += jobs
+            self.launches_per_step += 2 if self.P else 1
         return StepResult(jobs, samples, sp['peak_freq'], sp['peak_idx'], sp['peak_mag'], xc['lag_sec'], xc['lag_idx'],
-                          xc['lag_corr'], st, arrays)
+                          xc['lag_corr'], st, arrays, means)
 
     def reset(self):
         self.ring_t.fill_(float('nan'))

@@ -68,6 +68,19 @@ def calc_rois(present, bbox, points, num_points, rel_bbox, hist, g0: int, want_l
     return (boxes, loc, smo) if want_locations else boxes
 
 
+def running_mean(ring, g0: int, values, scale: float):
+    """Push values [S,T,C] * scale into ring [S,C,H] and return (mean, mean_int) f64 [S,T,C] after each push
+    (sg_bpm / sg_ptt + get_means, signal_processor.py:310, 312; signal_data.py:60-63)."""
+    S, C_, H = ring.shape
+    T = values.shape[1]
+    assert values.shape == (S, T, C_) and values.is_contiguous()
+    mean = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
+    mean_int = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
+    check(lib().bpv_running_mean(ptr(ring), S, C_, H, int(g0), T, ptr(values), float(scale), ptr(mean), ptr(mean_int),
+                                 stream_handle()), 'bpv_running_mean')
+    return mean, mean_int
+
+
 def ring_push(ring_t: torch.Tensor, ring_y: torch.Tensor, g0: int, ts: torch.Tensor, values: torch.Tensor):
     """Append T samples per stream (signal_data.py:31-35, 94-98).  ring_t f64 [S,cap], ring_y f64 [S,R,cap],
     ts f64 [S,T], values f64 [S,T,R]."""

@@ -29,3 +29,68 @@ extern "C" int bpv_ring_push(double* ring_t, double* ring_y, int32_t S, int32_t 
   ring_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ring_t, ring_y, S, R, cap, g0, T, ts, values);
   return check_launch("bpv_ring_push");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Running means of the per-frame results — SURVEY.md §8(f) row 3: sg_bpm / sg_ptt (deque(maxlen =
+// peak_max_samples), signal_processor.py:49, 83-84, 310, 312) and what the drawer shows,
+// sg_bpm.get_means(as_int=True) (drawer.py:134-135; Signal.get_mean, signal_data.py:60-63).
+// One thread per (stream, column) pushes the T new values of the step in order and emits, after each
+// push, nanmean over the history with numpy's summation order (pairwise_sum for a contiguous 1-D array:
+// 8 interleaved accumulators for n >= 8, numpy/_core/src/umath/loops_utils.h.src) and its half-to-even round.
+namespace bpv {
+__device__ inline double np_sum_small(const double* a, int n) {   // numpy pairwise sum, n <= 128
+  if (n < 8) {
+    double r = 0.0;          // numpy starts from -0.0; identical for every finite input except an all -0.0 array
+    for (int i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res += a[i];
+  return res;
+}
+
+constexpr int MAX_MEAN_HIST = 128;
+
+__global__ void running_mean_kernel(double* __restrict__ ring, int S, int C, int H, long long g0, int T,
+                                    const double* __restrict__ values, double scale,
+                                    double* __restrict__ mean, double* __restrict__ mean_int) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // s * C + c
+  if (idx >= S * C) return;
+  const int s = idx / C, c = idx % C;
+  double* rg = ring + (long long)idx * H;
+  double tmp[MAX_MEAN_HIST];
+  for (int t = 0; t < T; ++t) {
+    const long long e = ((long long)s * T + t) * C + c;
+    rg[(int)((g0 + t) % H)] = values[e] * scale;             // f * 60 / t * 1000 (signal_processor.py:310, 312)
+    // chronological order: oldest slot first (deque order), NaN -> 0 as np.nanmean does
+    const int newest = (int)((g0 + t) % H);
+    int cnt = 0;
+    for (int h = 0; h < H; ++h) {
+      int slot = newest + 1 + h; if (slot >= H) slot -= H;
+      const double v = rg[slot];
+      const bool ok = isfinite(v);
+      tmp[h] = ok ? v : 0.0;
+      cnt += ok;
+    }
+    double m = nan_f64();
+    if (cnt) m = np_sum_small(tmp, H) / (double)cnt;
+    if (mean) mean[e] = m;
+    if (mean_int) mean_int[e] = cnt ? rint(m) : nan_f64();
+  }
+}
+}  // namespace bpv
+
+extern "C" int bpv_running_mean(double* ring, int32_t S, int32_t C, int32_t H, int64_t g0, int32_t T,
+                                const double* values, double scale, double* mean, double* mean_int, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(ring && values && (mean || mean_int), BPV_E_INVALID, "bpv_running_mean: NULL pointer");
+  BPV_REQUIRE(S > 0 && C > 0 && H > 0 && H <= MAX_MEAN_HIST && T > 0 && g0 >= 0, BPV_E_INVALID, "bpv_running_mean: bad sizes (history <= 128)");
+  const int n = S * C;
+  running_mean_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ring, S, C, H, g0, T, values, scale, mean, mean_int);
+  return check_launch("bpv_running_mean");
+}

@@ -113,6 +113,16 @@ int bpv_calc_rois(const uint8_t* present, const int32_t* bbox, const int32_t* po
 int bpv_ring_push(double* ring_t, double* ring_y, int32_t S, int32_t R, int32_t cap,
                   int64_t g0, int32_t T, const double* ts, const double* values, void* stream);
 
+/* Running means of the per-frame results — replaces sg_bpm / sg_ptt (deque(maxlen=peak_max_samples)) and
+ * their get_means() (signal_processor.py:49, 83-84, 310, 312; signal_data.py:60-63; read by drawer.py:134-135).
+ * ring float64 [S, C, H] (NaN-initialised state, H = peak_max_samples <= 128), values float64 [S, T, C] (e.g.
+ * peak_freq of the step's S*T jobs), scale = 60 (bpm) or 1000 (ptt ms).  After each of the T pushes:
+ * mean float64 [S, T, C] = np.nanmean of the history (numpy's summation order), mean_int = its half-to-even
+ * round (NaN when the history holds no finite value).  Either output may be NULL.
+ */
+int bpv_running_mean(double* ring, int32_t S, int32_t C, int32_t H, int64_t g0, int32_t T,
+                     const double* values, double scale, double* mean, double* mean_int, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Window jobs.  A window job j of stream s looks at the `window` samples whose newest global
  * index is head(j) = head0 + j*head_step (samples with negative global index read as NaN,

@@ -76,3 +76,60 @@ def test_step_detections_equals_step_with_host_boxes():
         r2 = e2.step(torch.from_numpy(frames).cuda(), torch.from_numpy(hb).cuda(), torch.from_numpy(ts).cuda())
         assert torch.equal(torch.nan_to_num(r1.samples, nan=-1), torch.nan_to_num(r2.samples, nan=-1))
         assert torch.equal(r1.peak_idx, r2.peak_idx) and torch.equal(r1.lag_idx, r2.lag_idx)
+
+
+@pytest.mark.parametrize('H', [1, 5, 7, 8, 13, 50])
+def test_running_means_match_numpy_nanmean(H):
+    """sg_bpm / sg_ptt histories + get_means() on the device: bit-exact with np.nanmean over the
+    deque in chronological order, and its half-to-even integer round."""
+    from bpv import ops
+    rng = np.random.default_rng(H)
+    S, C = 7, 3
+    ring = torch.full((S, C, H), float('nan'), dtype=torch.float64, device='cuda')
+    hist = np.full((S, C, H), np.nan)
+    g0 = 0
+    for T in (1, 4, 9, 30, 2):
+        vals = rng.uniform(0.7, 4.0, (S, T, C))
+        vals[rng.uniform(size=vals.shape) < 0.2] = np.nan
+        vals[0, :, 0] = np.round(vals[0, :, 0] * 2) / 2 / 60          # exact .5 means now and then
+        mean, mean_int = ops.running_mean(ring, g0, torch.from_numpy(vals).cuda(), 60.0)
+        mean, mean_int = mean.cpu().numpy(), mean_int.cpu().numpy()
+        for t in range(T):
+            hist[:, :, :-1] = hist[:, :, 1:]
+            hist[:, :, -1] = vals[:, t] * 60
+            for s in range(S):
+                for c in range(C):
+                    y = hist[s, c]
+                    if np.isfinite(y).any():
+                        m = np.squeeze(np.nanmean(y, axis=0))
+                        assert mean[s, t, c] == m, (H, T, t, s, c, mean[s, t, c], m)
+                        assert mean_int[s, t, c] == m.round()
+                    else:
+                        assert np.isnan(mean[s, t, c]) and np.isnan(mean_int[s, t, c])
+        g0 += T
+
+
+def test_engine_tracks_running_means():
+    from bpv import synth
+    from bpv.engine import BatchedSignalProcessor
+    rng = np.random.default_rng(3)
+    S, W, T, R, Hm = 3, 40, 5, 2, 6
+    eng = BatchedSignalProcessor(S, R, signal_max_samples=W, max_frames_per_step=T, processing_methods=[orc.DETREND_CONST],
+                                 spectrum_transform=orc.PGRAM_LS, peak_max_samples=Hm)
+    n = 60
+    ts = np.stack([synth.timestamps(rng, n, 30.0) for _ in range(S)])
+    ys = np.stack([synth.raw_signals(rng, ts[s]).T for s in range(S)])
+    bpm_hist = np.full((S, R, Hm), np.nan)
+    for g0 in range(0, n, T):
+        res = eng.step_signals(torch.from_numpy(ys[:, g0:g0 + T].copy()).cuda(), torch.from_numpy(ts[:, g0:g0 + T].copy()).cuda())
+        bpm = res.bpm.cpu().numpy().reshape(S, T, R)
+        mb = res.means['mean_bpm_int'].cpu().numpy().reshape(S, T, R)
+        for t in range(T):
+            bpm_hist[:, :, :-1] = bpm_hist[:, :, 1:]
+            bpm_hist[:, :, -1] = bpm[:, t]
+            for s in range(S):
+                for r in range(R):
+                    y = bpm_hist[s, r]
+                    exp = np.nanmean(y).round() if np.isfinite(y).any() else np.nan
+                    assert (np.isnan(exp) and np.isnan(mb[s, t, r])) or mb[s, t, r] == exp
+        assert res.means['mean_ptt_int'].shape == (S * T, 1)
