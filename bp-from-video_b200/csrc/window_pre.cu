@@ -306,24 +306,56 @@ __device__ void sos_filtfilt(Warp& w, const double* __restrict__ sos_g, int N) {
   const double a1 = sec ? sos[6 * s + 4] : 0, a2 = sec ? sos[6 * s + 5] : 0;
   const double zi0 = sec ? zi[2 * s] : 0, zi1 = sec ? zi[2 * s + 1] : 0;
 
+  const double na1 = -a1, na2 = -a2;
   for (int pass = 0; pass < 2; ++pass) {
-    // pass 0 runs over ext[0..L), pass 1 over the reversed forward output, both in place
+    // pass 0 runs over ext[0..L), pass 1 over the reversed forward output, both in place.
+    // Sample i enters lane 0 at step i and leaves lane N-1 at step i + N - 1 (systolic cascade).
     const double x0 = pass == 0 ? ext[0] : ext[L - 1];
     double z0 = zi0 * x0, z1 = zi1 * x0;
     double prev_out = 0.0;
-    double nxt = pass == 0 ? ext[0] : ext[L - 1];  // software-prefetched input of lane 0
+    const int dir = pass == 0 ? 1 : -1, base = pass == 0 ? 0 : L - 1;   // position of sample i: base + dir*i
+    double nxt = ext[base];                                               // software-prefetched input of lane 0
     __syncwarp();
-    for (int t = 0; t < L + N - 1; ++t) {
+    const int t_steady = N - 1 < L ? N - 1 : L;
+    int t = 0;
+    // fill: lanes s <= t are live
+    for (; t < t_steady; ++t) {
       const double from_prev = shfl_up_d(prev_out, 1);
-      double xc = s == 0 ? nxt : from_prev;
-      if (s == 0 && t + 1 < L) nxt = pass == 0 ? ext[t + 1] : ext[L - 2 - t];
+      const double xc = s == 0 ? nxt : from_prev;
+      if (s == 0 && t + 1 < L) nxt = ext[base + dir * (t + 1)];
+      if (sec && t >= s) {
+        const double xn = fma(b0, xc, z0);
+        z0 = fma(b1, xc, fma(na1, xn, z1));
+        z1 = fma(b2, xc, na2 * xn);
+        prev_out = xn;
+      }
+    }
+    // steady state: every section is live, no per-step liveness tests; lane N-1 emits sample t - (N-1)
+    const double* in = ext + base + dir * (t + 1);
+    double* out = ext + base + dir * (t - (N - 1));
+    for (; t < L - 1; ++t) {
+      const double from_prev = shfl_up_d(prev_out, 1);
+      const double xc = s == 0 ? nxt : from_prev;
+      if (s == 0) nxt = *in;
+      in += dir;
+      const double xn = fma(b0, xc, z0);
+      z0 = fma(b1, xc, fma(na1, xn, z1));
+      z1 = fma(b2, xc, na2 * xn);
+      prev_out = xn;
+      if (s == N - 1) *out = xn;
+      out += dir;
+    }
+    // drain (and the last steady step, which has nothing left to prefetch): lanes with t - s < L are live
+    for (; t < L + N - 1; ++t) {
+      const double from_prev = shfl_up_d(prev_out, 1);
+      const double xc = s == 0 ? nxt : from_prev;
       const int i = t - s;
       if (sec && i >= 0 && i < L) {
-        const double xn = b0 * xc + z0;
-        z0 = b1 * xc - a1 * xn + z1;
-        z1 = b2 * xc - a2 * xn;
+        const double xn = fma(b0, xc, z0);
+        z0 = fma(b1, xc, fma(na1, xn, z1));
+        z1 = fma(b2, xc, na2 * xn);
         prev_out = xn;
-        if (s == N - 1) ext[pass == 0 ? i : L - 1 - i] = xn;
+        if (s == N - 1) ext[base + dir * i] = xn;
       }
     }
     __syncwarp();
