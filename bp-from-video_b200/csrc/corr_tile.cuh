@@ -7,6 +7,7 @@
 // shared-memory loads per FMA and is bound by shared-memory bandwidth, not by the FP64 pipe).
 // X is stored "de-interleaved" — XT[(j % RT) * LD + j / RT] — so that the lanes of a warp, whose j0 are
 // RT apart, read consecutive words (no bank conflicts).  j0 must be a multiple of RT and j0 - K >= 0.
+// T = double (FIR filtfilt: every later bit-exact decision depends on it) or float (xcorr coarse pass).
 #pragma once
 
 namespace bpv {
@@ -15,21 +16,21 @@ template <int RT>
 __device__ __forceinline__ int xt_index(int j, int LD) { return (j % RT) * LD + j / RT; }
 
 // Optional [kb_begin, kb_end): only taps k in [kb_begin*RT, kb_end*RT) are applied (skips known-zero operands).
-template <int RT>
-__device__ __forceinline__ void corr_tile(double (&acc)[RT], const double* __restrict__ c, int K,
-                                          const double* __restrict__ XT, int LD, int j0,
+template <int RT, typename T>
+__device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c, int K,
+                                          const T* __restrict__ XT, int LD, int j0,
                                           int kb_begin = 0, int kb_end = 0x7fffffff) {
   const int col0 = j0 / RT;
   if (kb_end > K / RT) kb_end = K / RT;
-  double w[RT];                       // w[s] = X[j] with j % RT == s, the RT samples under the current tap
+  T w[RT];                            // w[s] = X[j] with j % RT == s, the RT samples under the current tap
 #pragma unroll
   for (int s = 0; s < RT; ++s) w[s] = XT[s * LD + col0 - kb_begin];
   for (int kb = kb_begin; kb < kb_end; ++kb) {
-    const double* cc = c + kb * RT;
-    const double* xn = XT + (col0 - kb - 1);
+    const T* cc = c + kb * RT;
+    const T* xn = XT + (col0 - kb - 1);
 #pragma unroll
     for (int kk = 0; kk < RT; ++kk) {
-      const double ck = cc[kk];
+      const T ck = cc[kk];
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r] = fma(ck, w[(r - kk + RT) % RT], acc[r]);
       w[RT - 1 - kk] = xn[(RT - 1 - kk) * LD];      // X[j0 - k - 1] replaces X[j0 - k + RT - 1]

@@ -410,7 +410,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
       double acc[FIR_RT];
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
-      corr_tile<FIR_RT>(acc, b, Kp, XT, LD, j0);
+      corr_tile<FIR_RT, double>(acc, b, Kp, XT, LD, j0);
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) {
         const int i = i0 + r;
@@ -431,7 +431,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
       double acc[FIR_RT];
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
-      corr_tile<FIR_RT>(acc, b, Kp, GT, LD, j0);
+      corr_tile<FIR_RT, double>(acc, b, Kp, GT, LD, j0);
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) {
         const int i = i0 + r;

@@ -9,6 +9,8 @@
 
 namespace bpv {
 
+constexpr float XC_DELTA = 2.0e-4f;   // candidate band below the fp32 maximum (normalised correlation, |c| <~ 1)
+
 __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                     const bpv_window_params p, float* __restrict__ corr_lag,
                                                     float* __restrict__ corr_val, int32_t* __restrict__ num_lags,
@@ -30,16 +32,18 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
   const double* xa_g = proc_x + (job * R + ra) * W;
   const double* ya_g = proc_y + (job * R + ra) * W;
   const double* yb_g = proc_y + (job * R + rb) * W;
-  // shared memory (doubles): xa[W] | cv[2W] | c[Kw] reversed b, zero padded | XT[8*LD] a, de-interleaved
+  // shared memory: doubles xa[W] | a64[W] | b64[W] ; floats cv[2W] | c[Kw] reversed b, zero padded | XT[8*LD] a, de-interleaved
   constexpr int RT = 8;
   const int Kw = (W + RT - 1) / RT * RT;
-  double* xa = sm;             // [W]
-  double* cv = xa + W;         // [2W] correlation values (for the argmax)
-  double* c = cv + 2 * W;      // [Kw]
-  double* XT = c + Kw;         // [RT * LDw], LDw = (Kw + 3W + 16) / RT + 1
   const int LDw = (Kw + 3 * W + 16) / RT + 1;
-  for (int i = tid; i < Kw; i += blockDim.x) c[i] = 0.0;
-  for (int i = tid; i < RT * LDw; i += blockDim.x) XT[i] = 0.0;
+  double* xa = sm;             // [W] timestamps of signal a
+  double* a64 = xa + W;        // [W] jointly valid samples, float64 (normalisation + refinement)
+  double* b64 = a64 + W;       // [W]
+  float* cv = reinterpret_cast<float*>(b64 + W);   // [2W] coarse correlation values
+  float* c = cv + 2 * W;       // [Kw]
+  float* XT = c + Kw;          // [RT * LDw]
+  for (int i = tid; i < Kw; i += blockDim.x) c[i] = 0.f;
+  for (int i = tid; i < RT * LDw; i += blockDim.x) XT[i] = 0.f;
   __syncthreads();
   // valid = a.w & b.w  (finite in both); compacted sample i of a goes to X[u = i + n - 1], of b to c[n-1-i].
   // n is only known after the walk, so warp 0 first counts, then places.
@@ -62,12 +66,11 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         const int i = cnt + __popc(bal & lt);
-        XT[xt_index<RT>(i + n - 1 + K, LDw)] = va;     // storage index = u + K
-        c[n - 1 - i] = vb;
-        xa[i] = vx;
+        a64[i] = va; b64[i] = vb; xa[i] = vx;
       }
       cnt += __popc(bal);
     }
+    (void)K;
   }
   __syncthreads();
   const int n = s_n;
@@ -76,69 +79,104 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
     return;
   }
   const int K = (n + RT - 1) / RT * RT;
-  double daa = 0, dbb = 0, dab = 0;
+  double daa = 0, dbb = 0, dab = 0, amax = 0, bmax = 0;
   for (int i = tid; i < n; i += blockDim.x) {
-    const double va = XT[xt_index<RT>(i + n - 1 + K, LDw)], vb = c[n - 1 - i];
+    const double va = a64[i], vb = b64[i];
     daa = fma(va, va, daa); dbb = fma(vb, vb, dbb); dab = fma(va, vb, dab);
+    amax = fmax(amax, fabs(va)); bmax = fmax(bmax, fabs(vb));
   }
   daa = block_sum(daa, s_val); dbb = block_sum(dbb, s_val); dab = block_sum(dab, s_val);
   const double den = fmax(fmax(daa, dbb), dab);
+  // fp32 operands scaled to O(1) so tiny band-passed signals neither underflow nor lose bits
+  for (int o = 16; o > 0; o >>= 1) { amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o)); bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); }
+  __syncthreads();
+  if ((tid & 31) == 0) { s_val[tid >> 5] = amax; s_val[8 + (tid >> 5)] = bmax; }
+  __syncthreads();
+  for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) { amax = fmax(amax, s_val[w2]); bmax = fmax(bmax, s_val[8 + w2]); }
+  __syncthreads();
+  const double sa = amax > 0 ? 1.0 / amax : 1.0, sb = bmax > 0 ? 1.0 / bmax : 1.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    XT[xt_index<RT>(i + n - 1 + K, LDw)] = (float)(a64[i] * sa);     // storage index = u + K
+    c[n - 1 - i] = (float)(b64[i] * sb);
+  }
+  __syncthreads();
+  const float unscale = (float)(1.0 / (sa * sb * den));
   const int L = 2 * n - 1;
   const long long ob = jp * (2LL * W - 1);
-  // corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1 (corr_tile.cuh);
-  // X is non-zero only on u in [n-1, 2n-2], so each tile applies just the taps that can touch it.
+  // COARSE pass in fp32:  corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1
+  // (corr_tile.cuh); X is non-zero only on u in [n-1, 2n-2], so each tile applies just the taps that can touch it.
   const int jbase = (n - 1 + K) / RT * RT;      // storage index of the tile that holds li = 0
   for (int J0 = jbase + RT * tid; J0 <= (L - 1) + (n - 1) + K; J0 += RT * blockDim.x) {
-    double acc[RT];
+    float acc[RT];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    for (int r = 0; r < RT; ++r) acc[r] = 0.f;
     const int u0 = J0 - K;                       // logical index of the tile's first output operand
     int kb_lo = (u0 - (2 * n - 2)) / RT; if (kb_lo < 0) kb_lo = 0;
     int kb_hi = (u0 + RT - 1 - (n - 1)) / RT + 1; if (kb_hi < 0) kb_hi = 0;
-    corr_tile<RT>(acc, c, K, XT, LDw, J0, kb_lo, kb_hi);
+    corr_tile<RT, float>(acc, c, K, XT, LDw, J0, kb_lo, kb_hi);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int li = u0 + r - (n - 1);
       if (li >= 0 && li < L) {
-        const double cc = acc[r] / den;
+        const float cc = acc[r] * unscale;
         cv[li] = cc;
         if (corr_val) {
           const int k = li - (n - 1), ak = k < 0 ? -k : k;
           const double lag = (xa[n - 1] - xa[n - 1 - ak]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
           corr_lag[ob + li] = (float)lag;
-          corr_val[ob + li] = (float)cc;
+          corr_val[ob + li] = cc;
         }
       }
     }
   }
   __syncthreads();
-  // first-max over finite correlation values (Signal.get_peak after the range reset)
-  double bv = -INFINITY; int bi = 0x7fffffff, cnt = 0;
+  // PEAK in float64: every lag whose coarse value is within XC_DELTA of the coarse maximum is re-evaluated as a
+  // float64 dot product; the first maximum among those decides (Signal.get_peak after the range reset).
+  float cmax = -INFINITY; int cnt = 0;
+  for (int li = tid; li < L; li += blockDim.x) { const float v = cv[li]; if (isfinite(v)) { ++cnt; cmax = fmaxf(cmax, v); } }
+  for (int o = 16; o > 0; o >>= 1) { cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  {
+    const int wid = tid >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { s_val[wid] = cmax; s_idx[wid] = cnt; }
+    __syncthreads();
+    cmax = s_val[0]; cnt = s_idx[0];
+    for (int w2 = 1; w2 < nw; ++w2) { cmax = fmaxf(cmax, (float)s_val[w2]); cnt += s_idx[w2]; }
+    __syncthreads();
+  }
+  double bv = -INFINITY; int bi = 0x7fffffff;
   for (int li = tid; li < L; li += blockDim.x) {
-    const double v = cv[li];
-    if (isfinite(v)) { ++cnt; if (v > bv || (v == bv && li < bi)) { bv = v; bi = li; } }
+    const float v = cv[li];
+    if (cnt >= 2 ? (isfinite(v) && v >= cmax - XC_DELTA) : true) {
+      const int k = li - (n - 1);
+      const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
+      double acc = 0.0;
+      for (int l = l0; l < l1; ++l) acc = fma(a64[l + k], b64[l], acc);
+      const double cc = acc / den;
+      if (isfinite(cc) && (cc > bv || (cc == bv && li < bi))) { bv = cc; bi = li; }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
-  const int wid = tid >> 5, nw = blockDim.x >> 5;
-  if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; s_idx[32 + wid] = cnt; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < nw; ++w) {
-      if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
-      cnt += s_idx[32 + w];
+  {
+    const int wid = tid >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w2 = 1; w2 < nw; ++w2)
+        if (s_val[w2] > bv || (s_val[w2] == bv && s_idx[w2] < bi)) { bv = s_val[w2]; bi = s_idx[w2]; }
+      // finite-lag count in float64 terms: den == 0 or non-finite makes every lag non-finite (NaN / inf)
+      const bool any = isfinite(den) && den != 0.0 && bi != 0x7fffffff;
+      num_lags[jp] = L;
+      if (any && L >= 2) {
+        const int k = bi - (n - 1), ak = k < 0 ? -k : k;
+        lag_idx[jp] = bi;
+        lag_sec[jp] = (xa[n - 1] - xa[n - 1 - ak]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
+        lag_corr[jp] = bv;
+      } else { lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
     }
-    num_lags[jp] = L;
-    if (cnt >= 2) {
-      const int k = bi - (n - 1), ak = k < 0 ? -k : k;
-      lag_idx[jp] = bi;
-      lag_sec[jp] = (xa[n - 1] - xa[n - 1 - ak]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
-      lag_corr[jp] = bv;
-    } else { lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
   }
 }
 
@@ -155,7 +193,7 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   const long long n = (long long)p->S * p->jobs_per_stream * P;
   BPV_REQUIRE(W > 0 && n > 0, BPV_E_INVALID, "bpv_window_xcorr: bad sizes");
   const int Kw = (W + 7) / 8 * 8;
-  const size_t smem = (size_t)(3 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(double);
+  const size_t smem = (size_t)(3 * W) * sizeof(double) + (size_t)(2 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(float);
   BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_xcorr: window %d too large for shared memory", W);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -80,7 +80,7 @@ def test_golden_replay(name):
             assert L == len(g[f'f{i}_corr_x0'])
             assert h.close(a['lags'][0, 0, :L], g[f'f{i}_corr_x0'], rtol=1e-6, atol_frac=1e-7)
             if not any(residue):
-                assert h.close(a['corr'][0, 0, :L], g[f'f{i}_corr_y0'], rtol=1e-4, atol_frac=1e-6)
+                assert h.close(a['corr'][0, 0, :L], g[f'f{i}_corr_y0'], rtol=1e-4, atol_frac=1e-5)
 
 
 @pytest.mark.parametrize('windows', ['every_frame', 'last'])
@@ -197,5 +197,5 @@ def test_full_size_windows_signals_only(name, cfg):
             el, ec = orc.xcorr(proc[0][0], proc[0][1], proc[1][1])
             lx, ly, li = orc.peak(el, ec)
             L = a['num_lags'][s, 0]
-            assert L == len(el) and h.close(a['corr'][s, 0, :L], ec, rtol=1e-4, atol_frac=1e-6)
+            assert L == len(el) and h.close(a['corr'][s, 0, :L], ec, rtol=1e-4, atol_frac=1e-5)
             assert lidx[s, 0] == li and h.close(ptt[s, 0], lx * 1000, rtol=1e-12, atol_frac=0)

@@ -251,7 +251,7 @@ def test_xcorr_matches_oracle(methods, W, fps):
                 assert nl[s, k] == len(el)
                 if store:
                     assert h.close(o['lags'].cpu().numpy()[s, k, :len(el)], el, rtol=1e-6, atol_frac=1e-7)
-                    assert h.close(o['corr'].cpu().numpy()[s, k, :len(el)], ec, rtol=RTOL, atol_frac=1e-6)
+                    assert h.close(o['corr'].cpu().numpy()[s, k, :len(el)], ec, rtol=RTOL, atol_frac=1e-5)
                 assert li[s, k] == ei, (s, k, li[s, k], ei)
                 if ei >= 0:
                     assert ls[s, k] == ex
