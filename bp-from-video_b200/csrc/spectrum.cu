@@ -24,40 +24,36 @@ __device__ __forceinline__ double shfl_dd(double v, int src) { return __shfl_syn
 
 struct SigInfo { int n, m; double fs, xfirst; };
 
-// Block-cooperative gather of one processed signal: compacts samples with finite y into ys[] (and their
-// x into xs[] when xs != nullptr).  Returns n (finite y), m (finite x), fs = (m-1)/(x_last - x_first).
-// Signal.get_fs (signal_data.py:55-58) uses the finite-x mask v.
+// Block-cooperative gather of one processed signal.  All threads first stage the window into shared memory
+// (coalesced, one round trip to global memory); warp 0 then compacts the samples with finite y IN PLACE (a
+// compacted index never exceeds the position it came from) into ys[] and their x into xs[].
+// Returns n (finite y), m (finite x), fs = (m-1)/(x_last - x_first).  Signal.get_fs (signal_data.py:55-58) uses
+// the finite-x mask v.  xs and ys are shared-memory arrays of W doubles.
 __device__ SigInfo gather_signal(const double* __restrict__ px, const double* __restrict__ py, int W,
                                  double* xs, double* ys, int* s_cnt /* >= 4 ints smem */, double* s_d /* >= 2 doubles */) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0x7fffffff; s_cnt[3] = -1; }
+  for (int k = tid; k < W; k += blockDim.x) { xs[k] = px[k]; ys[k] = py[k]; }
   __syncthreads();
-  // ordered compaction: one warp walks the window (window <= a few thousand samples)
   if (tid < 32) {
     int n = 0, m = 0, kfirst = 0x7fffffff, klast = -1;
+    double xfirst = nan_f64(), xlast = nan_f64();
     const unsigned lt = (1u << lane) - 1u;
     for (int k0 = 0; k0 < W; k0 += 32) {
       const int k = k0 + lane;
       double x = nan_f64(), y = nan_f64();
-      if (k < W) { x = px[k]; y = py[k]; }
+      if (k < W) { x = xs[k]; y = ys[k]; }
       const bool fx = isfinite(x), fy = isfinite(y);
       const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
-      if (fy) {
-        const int idx = n + __popc(by & lt);
-        ys[idx] = y;
-        if (xs) xs[idx] = x;
-      }
       if (bx) {
-        if (kfirst == 0x7fffffff) kfirst = k0 + __ffs(bx) - 1;
-        klast = k0 + 31 - __clz(bx);
+        if (kfirst == 0x7fffffff) { kfirst = k0 + __ffs(bx) - 1; xfirst = __shfl_sync(0xffffffffu, x, __ffs(bx) - 1); }
+        klast = k0 + 31 - __clz(bx); xlast = __shfl_sync(0xffffffffu, x, 31 - __clz(bx));
       }
+      __syncwarp();
+      if (fy) { const int idx = n + __popc(by & lt); ys[idx] = y; xs[idx] = x; }
+      __syncwarp();
       n += __popc(by); m += __popc(bx);
     }
-    if (lane == 0) {
-      s_cnt[0] = n; s_cnt[1] = m;
-      s_d[0] = m >= 1 ? px[kfirst] : nan_f64();
-      s_d[1] = m >= 1 ? px[klast] : nan_f64();
-    }
+    if (lane == 0) { s_cnt[0] = n; s_cnt[1] = m; s_d[0] = xfirst; s_d[1] = xlast; }
   }
   __syncthreads();
   SigInfo si;
@@ -122,7 +118,7 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
   double* z = tws + W;
   double* mags = z + W;
   double* fim = mags + (W / 2 + 2);   // [256] FFT imaginary parts (Welch fast path)
-  const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, nullptr, ys, s_cnt, s_d);
+  const SigInfo si = gather_signal(proc_x + sig * W, proc_y + sig * W, W, twc /* x staging, overwritten below */, ys, s_cnt, s_d);
   const int n = si.n;
   if (!(n >= 2 && isfinite(si.fs))) {        // guard signal_processor.py:252 -> empty spectrum
     if (tid == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }

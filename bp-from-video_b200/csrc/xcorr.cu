@@ -45,32 +45,28 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
   for (int i = tid; i < Kw; i += blockDim.x) c[i] = 0.f;
   for (int i = tid; i < RT * LDw; i += blockDim.x) XT[i] = 0.f;
   __syncthreads();
-  // valid = a.w & b.w  (finite in both); compacted sample i of a goes to X[u = i + n - 1], of b to c[n-1-i].
-  // n is only known after the walk, so warp 0 first counts, then places.
+  // stage the three windows (coalesced), then warp 0 compacts the jointly valid samples in place:
+  // valid = a.w & b.w (finite in both)
+  for (int k = tid; k < W; k += blockDim.x) { xa[k] = xa_g[k]; a64[k] = ya_g[k]; b64[k] = yb_g[k]; }
+  __syncthreads();
   if (tid < 32) {
-    int n = 0;
-    for (int k0 = 0; k0 < W; k0 += 32) {
-      const int k = k0 + lane;
-      const bool ok = k < W && isfinite(ya_g[k]) && isfinite(yb_g[k]);
-      n += __popc(__ballot_sync(0xffffffffu, ok));
-    }
-    if (lane == 0) s_n = n;
-    const int K = (n + RT - 1) / RT * RT;
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
     for (int k0 = 0; k0 < W; k0 += 32) {
       const int k = k0 + lane;
       double va = nan_f64(), vb = nan_f64(), vx = nan_f64();
-      if (k < W) { va = ya_g[k]; vb = yb_g[k]; vx = xa_g[k]; }
+      if (k < W) { va = a64[k]; vb = b64[k]; vx = xa[k]; }
       const bool ok = isfinite(va) && isfinite(vb);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();
       if (ok) {
         const int i = cnt + __popc(bal & lt);
         a64[i] = va; b64[i] = vb; xa[i] = vx;
       }
+      __syncwarp();
       cnt += __popc(bal);
     }
-    (void)K;
+    if (lane == 0) s_n = cnt;
   }
   __syncthreads();
   const int n = s_n;
