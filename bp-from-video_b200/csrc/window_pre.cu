@@ -486,15 +486,28 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   const long long gfirst = head - W + 1;                      // global index of window position 0
   const int kmin = gfirst < 0 ? (int)(-gfirst < W ? -gfirst : W) : 0;   // positions before the stream started: NaN
   const int slot0 = (int)(((gfirst % p.cap) + p.cap) % p.cap);       // ring slot of position 0 (one 64-bit modulo)
+  // stage the window (independent, coalesced loads: no ballot in this loop, so they all overlap), writing the
+  // position-preserving pass-through copy on the way; y is staged in yv[] and compacted in place below
+  double* xstage = L.buf_len >= W ? w.buf0 : nullptr;
+  for (int k = w.lane; k < W; k += 32) {
+    double x = nan_f64(), y = nan_f64();
+    if (k >= kmin) { int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap; x = rt[slot]; y = ry[slot]; }
+    ox[k] = x; oy[k] = y;
+    w.yv[k] = y;
+    if (xstage) xstage[k] = x;
+  }
+  __syncwarp();
   for (int k0 = 0; k0 < W; k0 += 32) {
     const int k = k0 + w.lane;
     double x = nan_f64(), y = nan_f64();
     if (k < W) {
-      if (k >= kmin) { int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap; x = rt[slot]; y = ry[slot]; }
-      ox[k] = x; oy[k] = y;
+      y = w.yv[k];
+      if (xstage) x = xstage[k];
+      else if (k >= kmin) { int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap; x = rt[slot]; }
     }
     const bool fx = isfinite(x), fy = isfinite(y);
     const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+    __syncwarp();
     if (fy) {
       const int idx = n + __popc(by & lt);
       w.yv[idx] = y; w.posv[idx] = (unsigned short)k;
@@ -505,6 +518,7 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
       if (m == 0) xfirst = shfl_d(x, __ffs(bx) - 1);
       xlast = shfl_d(x, 31 - __clz(bx));
     }
+    __syncwarp();
     n += __popc(by); m += __popc(bx);
   }
   __syncwarp();
