@@ -32,8 +32,8 @@ __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int 
   for (int k = 0; k < order * 6; ++k) sos_out[(long long)i * order * 6 + k] = sos[k];
 }
 
-// One WARP per filter — scipy.signal.firls (_fir_filter_design.py:1130-1171) with desired = [0,0,1,1,0,0],
-// weight = 1.
+// scipy.signal.firls (_fir_filter_design.py:1130-1171) with desired = [0,0,1,1,0,0], weight = 1 — FIRLS_LPD lanes
+// per filter, 32 / FIRLS_LPD filters per warp.
 //
 // scipy solves Q a = b with Q = toeplitz(q[:M+1]) + hankel(q[:M+1], q[M:]) (Cholesky) and then mirrors a into
 // the taps h = [a[M..1], 2 a0, a[1..M]].  Written for h directly, that is the symmetric positive-definite
@@ -42,99 +42,164 @@ __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int 
 // than Q (cond 10 at 30 fps, 7e4 at 8.7 fps) and a Toeplitz solve is O(n^2): Levinson-Durbin, 126 steps of
 // two dot products + two AXPYs of growing length, instead of a 64^3/3 factorisation.  Agreement with scipy's
 // firls: <= 8e-13 relative over fs 8.7..240 Hz (checked against numpy in tests/test_window_gpu.py).
-// Lane l owns elements l, l+32, l+64, l+96 of the forward vector f and of the solution x (registers); f is
-// mirrored in shared memory (ping-pong) because every step needs it reversed.
-constexpr int FIRLS_WARPS = 4;                      // filters per CTA
+//
+// The recursion is a chain of 126 dependent steps whose cost is dominated by per-step overhead (shuffle
+// reductions, the reciprocal, warp syncs), not by the FMAs: with a whole warp per filter it issued 22 k warp
+// instructions per design.  Here a group of FIRLS_LPD = 8 lanes owns a filter (element i lives on lane i % 8,
+// register i / 8), so one warp instruction advances four designs, the reductions are 3 shuffle levels, and the
+// band-edge sinc tables are evaluated once with sinpi (5 per element instead of 8 sin).
+constexpr int FIRLS_LPD = 8;                        // lanes per design
+constexpr int FIRLS_EPL = 128 / FIRLS_LPD;          // elements per lane
+constexpr int FIRLS_DPW = 32 / FIRLS_LPD;           // designs per warp
+constexpr int FIRLS_WARPS = 2;                      // warps per CTA
 constexpr int FIRLS_THREADS = 32 * FIRLS_WARPS;
-constexpr int FIRLS_WS = 4 * 128;                   // doubles of shared memory per warp: r | y | f ping | f pong
-__device__ __forceinline__ double warp_sum_d(double v) {
+constexpr int FIRLS_DPB = FIRLS_DPW * FIRLS_WARPS;  // designs per CTA
+// doubles of shared memory per design: pad | r [128] | pad | f ping [128] | pad | f pong [128] | b [64].  The zero pads
+// (FIRLS_PAD >= 2 * LPD - 1 doubles) make r[k-i] and f_old[k-i] readable as 0 for the lanes whose element i lies
+// beyond k, so the element loops carry no per-lane predicate.  Odd designs are shifted by 8 doubles so that the four
+// groups of a warp read different bank halves.  Sized so that 7 CTAs (56 designs) fit an SM: 8192 designs = one wave.
+constexpr int FIRLS_PAD = 16;
+constexpr int FIRLS_WS = 3 * (FIRLS_PAD + 128) + 64;
+__host__ __device__ constexpr int firls_smem_offset(int d) { return d * FIRLS_WS + (d & 1) * 8; }   // design d of the CTA
+__device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ void firls_design_warp(double fs, int taps, double min_freq, double max_freq, double df,
-                                  double* __restrict__ out, double* __restrict__ zi_out, double* smem) {
+// f * numpy.sinc(f * i) = sin(pi f i) / (pi i)   (f for i == 0)
+__device__ __forceinline__ double band_term(double f, int i) {
+  return i == 0 ? f : sinpi(f * (double)i) / (3.141592653589793 * (double)i);
+}
+// Executed by whole warps: every lane group works on its own design (fs, out, zi_out, smem differ per group);
+// `live` = false for padding groups (they compute a shadow design and write nothing).
+//
+// Step k of Levinson-Durbin on T (f = forward vector of length k, zero extended; x = solution of the leading k x k system):
+//   ef = sum_i r[k-i] f[i],  ex = sum_i r[k-i] x[i]                     (two dot products, one shared r load)
+//   f'[i]      = (f[i] - ef * f[k-i]) / (1 - ef^2)
+//   rev(f')[i] = (f[k-i] - ef * f[i]) / (1 - ef^2)                      (the backward vector, from the same operands)
+//   x'[i]      = x[i] + (y[k] - ex) * rev(f')[i]
+// so one pass over the elements updates both vectors with a single reversed read of the old f from shared memory.
+__device__ void firls_design_group(double fs, bool live, int taps, double min_freq, double max_freq, double df,
+                                   double* __restrict__ out, double* __restrict__ zi_out, double* smem) {
   const int M = (taps - 1) / 2, n = taps;
-  double* r = smem;                 // [128] first column of T: q[0 .. taps-1]
-  double* y = r + 128;              // [128] symmetric right-hand side
-  double* fbuf = y + 128;           // [2][128] forward vector, ping-pong
-  const int lane = threadIdx.x & 31;
+  double* r = smem + FIRLS_PAD;                 // [128] first column of T: q[0 .. taps-1]; r[-PAD .. -1] = 0
+  double* fA = r + 128 + FIRLS_PAD;             // forward vector, ping (fA[-PAD .. -1] = 0)
+  double* fB = fA + 128 + FIRLS_PAD;            // forward vector, pong (fB[-PAD .. -1] = 0)
+  double* bt = fB + 128;                        // [64] b[d]; the symmetric right-hand side is y[i] = b[|i - M|]
+  const int sub = threadIdx.x & (FIRLS_LPD - 1);
   double fb[6];
   const bool ok = firls_bands(fs, min_freq, max_freq, df, fb);
-  if (!ok) {
-    for (int i = lane; i < taps; i += 32) out[i] = nan_f64();
-    return;
-  }
-  for (int i = lane; i < 128; i += 32) {
-    double acc = 0.0, bv = 0.0;
+  if (!ok) firls_bands(30.0, 0.8, 4.0, 0.3, fb);     // keep the group in step with the warp; NaN written at the end
+  // q[i] = sum_bands f2 sinc(f2 i) - f1 sinc(f1 i);  b[d] = f3 sinc(f3 d) - f2 sinc(f2 d)  (band edges fb[0..5])
+  // the b table is parked in fA / fB until y is in registers
+#pragma unroll 1
+  for (int i = sub; i < 128; i += FIRLS_LPD) {
+    double acc = 0.0, s2 = 0.0, s3 = 0.0;
     if (i < taps) {
-      for (int b = 0; b < 3; ++b) acc += fb[2 * b + 1] * np_sinc(fb[2 * b + 1] * i) - fb[2 * b] * np_sinc(fb[2 * b] * i);
-      const int d = i < M ? M - i : i - M;        // y[i] = b[|i - M|], b[d] = f3 sinc(f3 d) - f2 sinc(f2 d)
-      bv = fb[3] * np_sinc(fb[3] * d) - fb[2] * np_sinc(fb[2] * d);
+      const double s1 = band_term(fb[1], i), s4 = band_term(fb[4], i), s5 = band_term(fb[5], i);
+      s2 = band_term(fb[2], i); s3 = band_term(fb[3], i);
+      acc = s1 + (s3 - s2) + (s5 - s4);               // fb[0] = 0 contributes f sinc = 0
     }
     r[i] = acc;
-    y[i] = bv;
-    fbuf[i] = 0.0; fbuf[128 + i] = 0.0;
+    fA[i] = s2; fB[i] = s3;
   }
+  for (int i = sub; i < FIRLS_PAD; i += FIRLS_LPD) { r[i - FIRLS_PAD] = 0.0; fA[i - FIRLS_PAD] = 0.0; fB[i - FIRLS_PAD] = 0.0; }
   __syncwarp();
-  double f[4] = {0, 0, 0, 0}, x[4] = {0, 0, 0, 0};
+  for (int d = sub; d <= M; d += FIRLS_LPD) bt[d] = fB[d] - fA[d];
+  __syncwarp();
+  for (int i = sub; i < 128; i += FIRLS_LPD) { fA[i] = 0.0; fB[i] = 0.0; }
+  __syncwarp();
+  double f[FIRLS_EPL], x[FIRLS_EPL];
+#pragma unroll
+  for (int m = 0; m < FIRLS_EPL; ++m) { f[m] = 0.0; x[m] = 0.0; }
   const double r0inv = 1.0 / r[0];
-  if (lane == 0) { f[0] = r0inv; x[0] = y[0] * r0inv; fbuf[0] = r0inv; }
+  if (sub == 0) { f[0] = r0inv; x[0] = bt[M] * r0inv; fA[0] = r0inv; }
   __syncwarp();
+#pragma unroll 1
   for (int k = 1; k < n; ++k) {
-    const double* fo = fbuf + ((k - 1) & 1) * 128;   // f of step k-1 (length k)
-    double* fn = fbuf + (k & 1) * 128;               // f of step k (length k+1)
-    const int mmax = k >> 5;                         // element groups that can be non-empty (warp uniform)
-    double ef = 0.0, ex = 0.0;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m > mmax) break;
-      const int i = lane + 32 * m;
-      if (i < k) { const double rk = r[k - i]; ef = fma(rk, f[m], ef); ex = fma(rk, x[m], ex); }
+    const double* fo = ((k - 1) & 1) ? fB : fA;      // f of step k-1 (length k, zero beyond)
+    double* fn = (k & 1) ? fB : fA;                  // f of step k (length k+1)
+    const int mmax = k / FIRLS_LPD;                  // last element register that can be non-zero (warp uniform)
+    const double* rk = r + (k - sub);                // r[k - i] = rk[-LPD * m]
+    const double* fk = fo + (k - sub);               // f_old[k - i]
+    double ef0 = 0.0, ef1 = 0.0, ex0 = 0.0, ex1 = 0.0;
+    // Duff-style entry into the unrolled element blocks (highest live block first, fall through to block 0): one
+    // indexed branch per loop and no exit paths, so f[] / x[] stay pinned in their registers.
+#define FIRLS_DOT(m)                                                           \
+    { const double ra = rk[-FIRLS_LPD * (m)], rb = rk[-FIRLS_LPD * ((m) + 1)]; \
+      ef0 = fma(ra, f[m], ef0); ex0 = fma(ra, x[m], ex0);                      \
+      ef1 = fma(rb, f[(m) + 1], ef1); ex1 = fma(rb, x[(m) + 1], ex1); }
+    switch (mmax >> 1) {
+      case 7: FIRLS_DOT(14)
+      case 6: FIRLS_DOT(12)
+      case 5: FIRLS_DOT(10)
+      case 4: FIRLS_DOT(8)
+      case 3: FIRLS_DOT(6)
+      case 2: FIRLS_DOT(4)
+      case 1: FIRLS_DOT(2)
+      default: FIRLS_DOT(0)
     }
-    ef = warp_sum_d(ef); ex = warp_sum_d(ex);
+#undef FIRLS_DOT
+    const int dk = k < M ? M - k : k - M;
+    const double ykk = bt[dk];
+    const double ef = group_sum_d(ef0 + ef1), ex = group_sum_d(ex0 + ex1);
     const double dinv = 1.0 / (1.0 - ef * ef);
-    const double g = y[k] - ex;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m > mmax) break;
-      const int i = lane + 32 * m;
-      if (i <= k) {
-        const double frev = i >= 1 ? fo[k - i] : 0.0;          // bb[i] = f_old[k - i], bb[0] = 0
-        f[m] = (f[m] - ef * frev) * dinv;                       // fb[k] = 0 is already in the register
-        fn[i] = f[m];
-      }
+    const double gd = (ykk - ex) * dinv;
+    double* fw = fn + sub;
+#define FIRLS_UPD(m)                                                           \
+    { const double frev = fk[-FIRLS_LPD * (m)], fold = f[m];                   \
+      const double fnew = (fold - ef * frev) * dinv;                           \
+      x[m] = fma(gd, frev - ef * fold, x[m]);                                  \
+      f[m] = fnew; fw[FIRLS_LPD * (m)] = fnew; }
+    switch (mmax) {
+      case 15: FIRLS_UPD(15)
+      case 14: FIRLS_UPD(14)
+      case 13: FIRLS_UPD(13)
+      case 12: FIRLS_UPD(12)
+      case 11: FIRLS_UPD(11)
+      case 10: FIRLS_UPD(10)
+      case 9: FIRLS_UPD(9)
+      case 8: FIRLS_UPD(8)
+      case 7: FIRLS_UPD(7)
+      case 6: FIRLS_UPD(6)
+      case 5: FIRLS_UPD(5)
+      case 4: FIRLS_UPD(4)
+      case 3: FIRLS_UPD(3)
+      case 2: FIRLS_UPD(2)
+      case 1: FIRLS_UPD(1)
+      default: FIRLS_UPD(0)
     }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m > mmax) break;
-      const int i = lane + 32 * m;
-      if (i <= k) x[m] = fma(g, fn[k - i], x[m]);               // x += (y[k] - ex) * reversed(f_new)
-    }
+#undef FIRLS_UPD
     __syncwarp();
   }
+  // taps out (NaN when scipy would raise), staged through shared memory for lfilter_zi
+  double* hs = r;                                                 // [128] taps, zero padded
+  __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int i = lane + 32 * m;
-    if (i < n) out[i] = x[m];
+  for (int m = 0; m < FIRLS_EPL; ++m) {
+    const int i = sub + FIRLS_LPD * m;
+    hs[i] = i < n ? x[m] : 0.0;
+    if (live && i < n) out[i] = ok ? x[m] : nan_f64();
   }
-  if (zi_out) {
+  __syncwarp();
+  if (zi_out && live) {
     // lfilter_zi(b, [1]) = suffix sums of b[1:] (scipy/signal/_signaltools.py:4440-4463): zi[i] = sum_{k>i} b[k].
-    // Lane l holds taps l, l+32, l+64, l+96; suffix sums per 32-chunk by a shuffle scan, chunks chained.
-    double carry = 0.0;                                   // sum of all taps in higher chunks
+    // Lane `sub` owns the contiguous block [16 sub, 16 sub + 16): local suffix sums + the totals of higher blocks.
+    double tot = 0.0;
 #pragma unroll
-    for (int m = 3; m >= 0; --m) {
-      const int i = lane + 32 * m;
-      const double v = i < n ? x[m] : 0.0;
-      double incl = v;                                    // inclusive suffix sum over lanes >= lane
+    for (int e = 0; e < FIRLS_EPL; ++e) tot += hs[FIRLS_EPL * sub + e];
+    double above = 0.0;                                           // sum of the blocks of lanes > sub
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += t;
-      }
-      if (i < n - 1) zi_out[i] = (incl - v) + carry;      // strictly-greater taps
-      carry += __shfl_sync(0xffffffffu, incl, 0);
+    for (int o = 1; o < FIRLS_LPD; ++o) {
+      const double t = __shfl_down_sync(0xffffffffu, tot, o, FIRLS_LPD);
+      if (sub + o < FIRLS_LPD) above += t;
+    }
+    double run = above;
+#pragma unroll
+    for (int e = FIRLS_EPL - 1; e >= 0; --e) {
+      const int i = FIRLS_EPL * sub + e;
+      if (i < n - 1) zi_out[i] = ok ? run : nan_f64();
+      run += hs[i];
     }
   }
 }
@@ -142,9 +207,10 @@ __device__ void firls_design_warp(double fs, int taps, double min_freq, double m
 __global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const double* __restrict__ fs, int n, int taps, double min_freq,
                                                                       double max_freq, double df, double* __restrict__ out) {
   extern __shared__ double smem[];
-  const int w = threadIdx.x >> 5, job = blockIdx.x * FIRLS_WARPS + w;
-  if (job >= n) return;
-  firls_design_warp(fs[job], taps, min_freq, max_freq, df, out + (long long)job * taps, nullptr, smem + w * FIRLS_WS);
+  const int d = threadIdx.x / FIRLS_LPD, job = blockIdx.x * FIRLS_DPB + d;
+  const bool live = job < n;
+  firls_design_group(live ? fs[job] : 30.0, live, taps, min_freq, max_freq, df, out + (long long)(live ? job : 0) * taps, nullptr,
+                     smem + firls_smem_offset(d));
 }
 
 // ---- per-job design from the ring timestamps (used by the window pipeline) ----------------------
@@ -163,31 +229,35 @@ __global__ void job_butter_kernel(const double* __restrict__ ring_t, bpv_window_
 __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* __restrict__ ring_t, bpv_window_params p,
                                                                   double* __restrict__ out) {
   extern __shared__ double smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.x * FIRLS_WARPS + w;
-  if (job >= p.S * p.jobs_per_stream) return;
-  const int s = job / p.jobs_per_stream, j = job % p.jobs_per_stream;
-  // fs of the job's window, warp cooperative (first / last finite timestamp and their count)
-  const double* rt = ring_t + (long long)s * p.cap;
-  const long long g0 = p.head0 + (long long)j * p.head_step - p.window + 1;
-  int lo = 0x7fffffff, hi = -1, cnt = 0;
-  const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
-  const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
-  for (int k = lane; k < p.window; k += 32) {
-    int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
-    if (k >= kmin && isfinite(rt[slot])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+  const int d = threadIdx.x / FIRLS_LPD, sub = threadIdx.x & (FIRLS_LPD - 1);
+  const int job = blockIdx.x * FIRLS_DPB + d;
+  const bool live = job < p.S * p.jobs_per_stream;
+  double fs;
+  {
+    const int jc = live ? job : 0;                   // padding groups shadow job 0 (warp-uniform control flow), write nothing
+    const int s = jc / p.jobs_per_stream, j = jc % p.jobs_per_stream;
+    // fs of the job's window, group cooperative (first / last finite timestamp and their count)
+    const double* rt = ring_t + (long long)s * p.cap;
+    const long long g0 = p.head0 + (long long)j * p.head_step - p.window + 1;
+    int lo = 0x7fffffff, hi = -1, cnt = 0;
+    const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
+    const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
+    for (int k = sub; k < p.window; k += FIRLS_LPD) {
+      int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
+      if (k >= kmin && isfinite(rt[slot])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+    }
+    for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) {
+      const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = lo < l2 ? lo : l2; hi = hi > h2 ? hi : h2; cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    fs = nan_f64();
+    if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-    lo = lo < l2 ? lo : l2; hi = hi > h2 ? hi : h2; cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  double fs = nan_f64();
-  if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
-  firls_design_warp(fs, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, out + (long long)job * 256, out + (long long)job * 256 + 128,
-                    smem + w * FIRLS_WS);
+  double* o = out + (long long)(live ? job : 0) * 256;
+  firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, smem + firls_smem_offset(d));
 }
 
-constexpr size_t FIRLS_SMEM = (size_t)FIRLS_WARPS * FIRLS_WS * sizeof(double);
+constexpr size_t FIRLS_SMEM = (size_t)(FIRLS_DPB * FIRLS_WS + 8) * sizeof(double);
 
 int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* sos_out, cudaStream_t st) {
   const int J = p.S * p.jobs_per_stream;
@@ -197,7 +267,7 @@ int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* 
 
 int launch_job_firls(const double* ring_t, const bpv_window_params& p, double* taps_out, cudaStream_t st) {
   const int J = p.S * p.jobs_per_stream;
-  job_firls_kernel<<<(J + FIRLS_WARPS - 1) / FIRLS_WARPS, FIRLS_THREADS, FIRLS_SMEM, st>>>(ring_t, p, taps_out);
+  job_firls_kernel<<<(J + FIRLS_DPB - 1) / FIRLS_DPB, FIRLS_THREADS, FIRLS_SMEM, st>>>(ring_t, p, taps_out);
   return check_launch("job_firls_kernel");
 }
 
@@ -226,6 +296,6 @@ extern "C" int bpv_firls_design(const double* fs, int32_t n, const bpv_window_pa
   if (int rc = check_filter_params(p, "bpv_firls_design")) return rc;
   BPV_REQUIRE(fs && taps_out && n >= 0, BPV_E_INVALID, "bpv_firls_design: bad arguments");
   if (n == 0) return 0;
-  firls_from_fs_kernel<<<(n + FIRLS_WARPS - 1) / FIRLS_WARPS, FIRLS_THREADS, FIRLS_SMEM, (cudaStream_t)stream>>>(fs, n, p->fir_taps, p->min_freq, p->max_freq, p->fir_df, taps_out);
+  firls_from_fs_kernel<<<(n + FIRLS_DPB - 1) / FIRLS_DPB, FIRLS_THREADS, FIRLS_SMEM, (cudaStream_t)stream>>>(fs, n, p->fir_taps, p->min_freq, p->max_freq, p->fir_df, taps_out);
   return check_launch("bpv_firls_design");
 }

@@ -278,22 +278,246 @@ __global__ void __launch_bounds__(256, MINB) roi_rows_kernel(const RoiArgs a) {
   }
 }
 
-template <int GROUP>
+// ---------------------------------------------------------------------------------------------
+// Shared-memory staged fast path: one ROI per CTA.  The register path above can keep at most
+// UNROLL x 16 B per thread in flight (64 KB per SM at 4 CTAs); staging decouples the bytes in flight
+// from the register file, so a CTA has its whole ROI tile (or a K-row-step batch of it) outstanding.
+//   STAGE 1: every thread issues up to K 16-byte cp.async (LDGSTS, L2::64B fill) into its OWN slots
+//            and reads the same slots back -> no CTA barrier at all, only cp.async.wait_all.
+//   STAGE 2: warp 0 issues one cp.async.bulk (TMA 1-D) per ROI row (16-byte aligned span) against
+//            an mbarrier; the CTA then reduces the tile from shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16_64B(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int THREADS, int K, bool WANT_SUMS, int STAGE>
+__global__ void __launch_bounds__(THREADS) roi_staged_kernel(const RoiArgs a, const int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t stage[];
+  __shared__ __align__(8) unsigned long long bar;
+  constexpr int WARPS = THREADS / 32;
+  const int gt = threadIdx.x;
+  const long long roi = blockIdx.x;
+
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  bool has_box = false;
+  uintptr_t base = 0;
+  {
+    const int4 b = __ldg(reinterpret_cast<const int4*>(a.boxes) + roi);
+    has_box = b.x != BPV_NO_BOX;
+    if (has_box) {
+      py_slice(b.x, b.z, a.W, xs, xe);
+      py_slice(b.y, b.w, a.H, ys, ye);
+      const long long f = roi / a.R;
+      const uint8_t* fp = a.frame_ptrs ? a.frame_ptrs[f] : a.frames + f * a.frame_stride;
+      base = reinterpret_cast<uintptr_t>(fp) + (uintptr_t)((long long)ys * a.row_stride + (long long)xs * 3);
+    }
+  }
+  const int nrows = ye - ys, row_bytes = (xe - xs) * 3;
+  uint32_t sG = 0, sT = 0, sB = 0;
+  if (nrows > 0 && row_bytes > 0) {
+    const int off = (int)(base & 15);
+    const int vpr = (off + row_bytes + 15) >> 4;
+    int rps, r0, v0;
+    if (vpr >= THREADS) { rps = 1; r0 = 0; v0 = gt; }
+    else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
+    const uint32_t sbase = smem_u32(stage);
+    if (STAGE == 1) {
+      const long long step = (long long)rps * a.row_stride;
+      const uint32_t slot0 = sbase + 16u * (uint32_t)gt;
+      for (int v = v0; v < vpr; v += THREADS) {
+        const int rel = 16 * v - off;
+        const int lo = rel < 0 ? -rel : 0;
+        const int e = row_bytes - rel;
+        const int hi = e < 16 ? e : 16;
+        const int ph = (rel + 15) % 3;
+        uint32_t cT[4], cG[4], cB[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = byte_mask(lo - 4 * j, hi - 4 * j);
+          cT[j] = m & 0x01010101u;
+          cG[j] = m & sel_word((ph + 2) % 3, j);
+          cB[j] = m & sel_word(ph, j);
+        }
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(base - off) + (long long)r0 * a.row_stride + 16 * v;
+        for (int r = r0; r < nrows; r += rps * K) {
+#pragma unroll
+          for (int u = 0; u < K; ++u)
+            if (r + u * rps < nrows) cp_async16_64B(slot0 + (uint32_t)(u * THREADS * 16), p + u * step);
+          cp_async_wait_all();
+#pragma unroll
+          for (int u = 0; u < K; ++u) {
+            if (r + u * rps < nrows) {
+              const uint4 d = lds128(slot0 + (uint32_t)(u * THREADS * 16));
+              sT = __dp4a(d.x, cT[0], __dp4a(d.y, cT[1], __dp4a(d.z, cT[2], __dp4a(d.w, cT[3], sT))));
+              sG = __dp4a(d.x, cG[0], __dp4a(d.y, cG[1], __dp4a(d.z, cG[2], __dp4a(d.w, cG[3], sG))));
+              if (WANT_SUMS)
+                sB = __dp4a(d.x, cB[0], __dp4a(d.y, cB[1], __dp4a(d.z, cB[2], __dp4a(d.w, cB[3], sB))));
+            }
+          }
+          p += K * step;
+        }
+      }
+    } else {
+      const uint32_t bar_a = smem_u32(&bar);
+      if (gt == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      const uint32_t rowb = 16u * (uint32_t)vpr;
+      int chunk = stage_bytes / (int)rowb;
+      if (chunk < 1) chunk = 1;  // host sizes the stage for at least one full-width row
+      uint32_t phase = 0;
+      const uint8_t* g0 = reinterpret_cast<const uint8_t*>(base - off);
+      for (int c0 = 0; c0 < nrows; c0 += chunk) {
+        const int rows = nrows - c0 < chunk ? nrows - c0 : chunk;
+        if (gt < 32) {
+          if (gt == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(rowb * (uint32_t)rows) : "memory");
+          __syncwarp();
+          for (int r = gt; r < rows; r += 32)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(sbase + (uint32_t)r * rowb), "l"(g0 + (long long)(c0 + r) * a.row_stride), "r"(rowb), "r"(bar_a) : "memory");
+        }
+        {
+          uint32_t done = 0;
+          while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+          phase ^= 1;
+        }
+        for (int v = v0; v < vpr; v += THREADS) {
+          const int rel = 16 * v - off;
+          const int lo = rel < 0 ? -rel : 0;
+          const int e = row_bytes - rel;
+          const int hi = e < 16 ? e : 16;
+          const int ph = (rel + 15) % 3;
+          uint32_t cT[4], cG[4], cB[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = byte_mask(lo - 4 * j, hi - 4 * j);
+            cT[j] = m & 0x01010101u;
+            cG[j] = m & sel_word((ph + 2) % 3, j);
+            cB[j] = m & sel_word(ph, j);
+          }
+          uint32_t sp = sbase + (uint32_t)r0 * rowb + 16u * (uint32_t)v;
+          const uint32_t sstep = (uint32_t)rps * rowb;
+#pragma unroll 4
+          for (int r = r0; r < rows; r += rps) {
+            const uint4 d = lds128(sp);
+            sp += sstep;
+            sT = __dp4a(d.x, cT[0], __dp4a(d.y, cT[1], __dp4a(d.z, cT[2], __dp4a(d.w, cT[3], sT))));
+            sG = __dp4a(d.x, cG[0], __dp4a(d.y, cG[1], __dp4a(d.z, cG[2], __dp4a(d.w, cG[3], sG))));
+            if (WANT_SUMS)
+              sB = __dp4a(d.x, cB[0], __dp4a(d.y, cB[1], __dp4a(d.z, cB[2], __dp4a(d.w, cB[3], sB))));
+          }
+        }
+        if (c0 + chunk < nrows) __syncthreads();  // tile consumed before the next chunk overwrites it
+      }
+    }
+  }
+
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(xe - xs);
+  unsigned long long tG, tT, tB = 0;
+  if (N < 5600000ull) {
+    tG = warp_sum<uint32_t>(sG); tT = warp_sum<uint32_t>(sT);
+    if (WANT_SUMS) tB = warp_sum<uint32_t>(sB);
+  } else {
+    tG = warp_sum_u64(sG); tT = warp_sum_u64(sT);
+    if (WANT_SUMS) tB = warp_sum_u64(sB);
+  }
+  if (WARPS > 1) {
+    __shared__ unsigned long long part[WARPS][3];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { part[wid][0] = tG; part[wid][1] = tT; part[wid][2] = tB; }
+    __syncthreads();
+    if (gt == 0) {
+      tG = tT = tB = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) { tG += part[w][0]; tT += part[w][1]; tB += part[w][2]; }
+    }
+  }
+  if (gt == 0) {
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tT - tG - tB; o.w = N;
+      *reinterpret_cast<ulonglong4*>(a.out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (a.mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(3 * (long long)tG - (long long)tT + 2 * (long long)N) / (double)(4 * N);
+    a.out_value[roi] = val;
+  }
+}
+
+template <int THREADS, int K, int STAGE>
+static void launch_staged(const RoiArgs& a, int stage_bytes, cudaStream_t st) {
+  const int smem = STAGE == 1 ? THREADS * K * 16 : stage_bytes;
+  auto k1 = roi_staged_kernel<THREADS, K, true, STAGE>;
+  auto k0 = roi_staged_kernel<THREADS, K, false, STAGE>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr_done = true;
+  }
+  if (a.out_sums) k1<<<(unsigned)a.num_rois, THREADS, smem, st>>>(a, stage_bytes);
+  else k0<<<(unsigned)a.num_rois, THREADS, smem, st>>>(a, stage_bytes);
+}
+
+template <int GROUP, int LDMODE>
 static void launch_rows(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   // LDMODE 5 = ld.global.nc.L1::no_allocate.L2::64B: the default L2 fill granule on B200 is the whole
   // 128-byte line; asking for 64 B cuts the DRAM over-fetch around short unaligned ROI rows from 1.50x
-  // to 1.17x of the algorithmic bytes (ncu dram__bytes_read, profiles/roi_r1_notes.md).
-  if (a.out_sums) roi_rows_kernel<GROUP, 4, true, 5, 4><<<grid, 256, 0, st>>>(a);
-  else roi_rows_kernel<GROUP, 4, false, 5, 4><<<grid, 256, 0, st>>>(a);
+  // to 1.17x of the algorithmic bytes (ncu dram__bytes_read, profiles/r1a_roi_l2_fill_probe.txt).
+  // LDMODE 2 = plain ld.global, for frames in pinned HOST memory: over PCIe the 128-byte requests move
+  // 32.8 GB/s of ROI bytes (49 GB/s on the wire) against 19.9 GB/s with 64-byte requests
+  // (profiles/r1e_roi_host_variants.txt).
+  // Host frames are PCIe-bound (one 256-thread CTA per SM already keeps 2.4 MB of reads in flight): an unused dynamic
+  // shared-memory request caps the kernel at one CTA per SM, so the window pipeline of the previous batch can run
+  // beside it on another stream instead of queueing behind a machine-filling F1 grid.
+  size_t smem = 0;
+  if (LDMODE == 2) {
+    smem = 120 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(roi_rows_kernel<GROUP, 4, true, LDMODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(roi_rows_kernel<GROUP, 4, false, LDMODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_done = true;
+    }
+  }
+  if (a.out_sums) roi_rows_kernel<GROUP, 4, true, LDMODE, 4><<<grid, 256, smem, st>>>(a);
+  else roi_rows_kernel<GROUP, 4, false, LDMODE, 4><<<grid, 256, smem, st>>>(a);
 }
 
 // development-only tuning variants (BPV_ROI_VARIANT=<ldmode><unroll><minblocks>, e.g. "084"), GROUP=128
 static bool launch_variant(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   static const char* v = getenv("BPV_ROI_VARIANT");
-  if (!v || a.out_sums) return false;
-#define V(ld, un, mb) if (v[0] == '0' + ld && v[1] == '0' + un && v[2] == '0' + mb) { roi_rows_kernel<128, un, false, ld, mb><<<grid, 256, 0, st>>>(a); return true; }
+  if (!v) return false;
+  if (a.out_sums && v[0] < 'A') return false;
+  const unsigned grid128 = (unsigned)((a.num_rois + 1) / 2); (void)grid;
+#define V(ld, un, mb) if (v[0] == '0' + ld && v[1] == '0' + un && v[2] == '0' + mb) { roi_rows_kernel<128, un, false, ld, mb><<<grid128, 256, 0, st>>>(a); return true; }
   V(0, 4, 3) V(0, 4, 4) V(0, 8, 3) V(0, 8, 4) V(0, 2, 4) V(0, 2, 6)
   V(1, 4, 4) V(2, 4, 4) V(3, 4, 4) V(4, 4, 4) V(5, 4, 3) V(5, 8, 4) V(5, 2, 6) V(5, 2, 8) V(5, 4, 6)
+#define SA(tag, thr, k) if (v[0] == tag && atoi(v + 1) == k) { launch_staged<thr, k, 1>(a, 0, st); return true; }
+  SA('A', 128, 8) SA('A', 128, 10) SA('A', 128, 11) SA('A', 128, 12) SA('F', 96, 12) SA('F', 96, 14) SA('G', 64, 8) SA('H', 32, 12) SA('H', 32, 24) SA('A', 128, 16) SA('C', 256, 4) SA('C', 256, 6) SA('C', 256, 8) SA('G', 64, 12) SA('G', 64, 24)
+#undef SA
+  if (v[0] == 'B') { launch_staged<128, 1, 2>(a, atoi(v + 1) * 1024, st); return true; }
+  if (v[0] == 'D') { launch_staged<256, 1, 2>(a, atoi(v + 1) * 1024, st); return true; }
+  if (v[0] == 'E') { launch_staged<64, 1, 2>(a, atoi(v + 1) * 1024, st); return true; }
 #undef V
   return false;
 }
@@ -319,14 +543,28 @@ extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* fr
             num_frames * R, boxes, (unsigned long long*)out_sums, out_value};
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = a.num_rois;
+  bool host_frames = false;
+  if (frames) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, frames) == cudaSuccess) host_frames = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
   // threads per ROI: ~>= 4 vectors per thread before widening the group
   const long long px = roi_pixels_hint > 0 ? roi_pixels_hint : 4096;
   const int g = px * 3 <= 32 * 16 * 8 ? 32 : (px * 3 <= 128 * 16 * 16 ? 128 : 256);
   const unsigned grid = (unsigned)((n + 256 / g - 1) / (256 / g));
   if (row_stride_bytes % 16 == 0) {  // fast path: loop-invariant alignment per ROI
-    if (g == 32) launch_rows<32>(a, grid, st);
-    else if (g == 128) { if (!launch_variant(a, grid, st)) launch_rows<128>(a, grid, st); }
-    else launch_rows<256>(a, grid, st);
+    // small ROIs: a warp per ROI, loads held in registers; everything else: one ROI per CTA, tile staged in
+    // shared memory by cp.async (whole ROI in flight; measured 64.5 us vs 76.3 us for the register path on the
+    // config-2 boxes, 6.2 TB/s on 320x160 boxes; profiles/r1e_roi_variants.txt).  Frames in pinned host memory
+    // (zero-copy e2e path) are PCIe-bound and want full-line requests: register path with plain loads.
+    if (launch_variant(a, grid, st)) {}
+    else if (host_frames) {
+      if (g == 32) launch_rows<32, 2>(a, grid, st);
+      else launch_rows<128, 2>(a, (unsigned)((n + 1) / 2), st);
+    }
+    else if (g == 32) launch_rows<32, 5>(a, grid, st);
+    else launch_staged<128, 12, 1>(a, 0, st);
   } else {                           // generic path: alignment changes row by row
     if (g == 32) roi_sample_kernel<32, 4><<<grid, 256, 0, st>>>(a);
     else if (g == 128) roi_sample_kernel<128, 4><<<grid, 256, 0, st>>>(a);

@@ -231,6 +231,159 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// PGRAM_WELCH fast kernel: one WARP per signal, no CTA barrier after the shared twiddle table is built.
+// scipy.signal.welch(y, fs) with every default (signal_processor.py:260): periodic Hann, nperseg = min(256, n),
+// 50 % overlap, per-segment mean removal, one-sided density, mean over segments.  In steady state (n >= 256) a
+// segment is a 256-point radix-2 FFT held in the warp's shared-memory slice (4 butterflies per lane per stage,
+// __syncwarp between stages); shorter windows (warm-up) use a warp-level direct DFT with their own twiddles.
+// The CTA-per-signal version spent its time in ~25 __syncthreads with little work between them (197 us per
+// 16 384 signals); this one is ~1 k warp instructions per signal.
+// smem: CTA table tw[256] (cos, sin) | per warp: ys[W] | buf[512] | mags[130] | z[256]
+// ---------------------------------------------------------------------------------------------
+constexpr int WELCH_WPB = 4;
+__host__ __device__ inline int welch_warp_doubles(int W) { return W + 512 + 130 + 256; }
+
+__global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double* __restrict__ proc_x,
+                                                                    const double* __restrict__ proc_y,
+                                                                    const bpv_window_params p, int max_bins, long long nsig,
+                                                                    float* __restrict__ spec_f, float* __restrict__ spec_mag,
+                                                                    int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
+                                                                    double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
+  extern __shared__ __align__(16) double sm[];
+  const int W = p.window, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double2* tw = reinterpret_cast<double2*>(sm);                 // [256] exp(+2*pi*i*k/256) as (cos, sin)
+  for (int i = tid; i < 256; i += blockDim.x) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  __syncthreads();
+  const long long sig = (long long)blockIdx.x * WELCH_WPB + wid;
+  if (sig >= nsig) return;
+  double* ys = sm + 512 + (size_t)wid * welch_warp_doubles(W);
+  double* buf = ys + W;            // FFT: 256 complex (re, im interleaved); direct DFT: cos[256] | sin[256]
+  double* mags = buf + 512;
+  double* z = mags + 130;
+  const double* px = proc_x + sig * W;
+  const double* py = proc_y + sig * W;
+
+  // ---- gather: stage (independent loads), then ballot-compact finite y in place; fs from the finite-x mask
+  double* xst = buf;               // x staging (W <= 512 checked by the host)
+  for (int k = lane; k < W; k += 32) { xst[k] = px[k]; ys[k] = py[k]; }
+  __syncwarp();
+  int n = 0, m = 0;
+  double xfirst = 0.0, xlast = 0.0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int k0 = 0; k0 < W; k0 += 32) {
+    const int k = k0 + lane;
+    double x = nan_f64(), y = nan_f64();
+    if (k < W) { x = xst[k]; y = ys[k]; }
+    const bool fx = isfinite(x), fy = isfinite(y);
+    const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+    if (bx) {
+      if (m == 0) xfirst = shfl_dd(x, __ffs(bx) - 1);
+      xlast = shfl_dd(x, 31 - __clz(bx));
+    }
+    __syncwarp();
+    if (fy) ys[n + __popc(by & lt)] = y;
+    __syncwarp();
+    n += __popc(by); m += __popc(bx);
+  }
+  const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
+  if (!(n >= 2 && isfinite(fs))) {        // guard signal_processor.py:252 -> empty spectrum
+    if (lane == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    return;
+  }
+  const int N = n < 256 ? n : 256, F = N / 2 + 1;
+  const int nov = N / 2, hop = N - nov, nseg = (n - nov) / hop;
+  const bool fft = N == 256;
+  double* dc = buf;                // direct path: cos table
+  double* ds = buf + 256;          // direct path: sin table
+  if (!fft) {
+    for (int i = lane; i < N; i += 32) sincospi(2.0 * (double)i / (double)N, &ds[i], &dc[i]);
+  }
+  for (int k = lane; k < F; k += 32) mags[k] = 0.0;
+  __syncwarp();
+  double sw = 0.0;
+  for (int i = lane; i < N; i += 32) { const double wj = 0.5 - 0.5 * (fft ? tw[i].x : dc[i]); sw = fma(wj, wj, sw); }
+  const double scale = 1.0 / (fs * warp_sum(sw));
+  for (int sg = 0; sg < nseg; ++sg) {
+    const double* seg = ys + sg * hop;
+    double a = 0.0;
+    for (int i = lane; i < N; i += 32) a += seg[i];
+    const double mean = warp_sum(a) / (double)N;
+    if (fft) {
+      double2* fz = reinterpret_cast<double2*>(buf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        fz[__brev((unsigned)i) >> 24] = make_double2((seg[i] - mean) * (0.5 - 0.5 * tw[i].x), 0.0);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int st = 0; st < 8; ++st) {
+        const int half = 1 << st;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = lane + 32 * j;
+          const int pos = b & (half - 1);
+          const int i0 = ((b >> st) << (st + 1)) + pos, i1 = i0 + half;
+          const double2 t = tw[pos << (7 - st)];                 // exp(-2*pi*i*tw/256) = (t.x, -t.y)
+          const double2 xv = fz[i1], u = fz[i0];
+          const double tr = fma(t.x, xv.x, t.y * xv.y), ti = fma(t.x, xv.y, -t.y * xv.x);
+          fz[i0] = make_double2(u.x + tr, u.y + ti);
+          fz[i1] = make_double2(u.x - tr, u.y - ti);
+        }
+        __syncwarp();
+      }
+      for (int k = lane; k < F; k += 32) {
+        const double2 v = fz[k];
+        double pw = (v.x * v.x + v.y * v.y) * scale;
+        if (k >= 1 && k < F - 1) pw *= 2.0;
+        mags[k] += pw;
+      }
+      __syncwarp();
+    } else {
+      for (int i = lane; i < N; i += 32) z[i] = (seg[i] - mean) * (0.5 - 0.5 * dc[i]);
+      __syncwarp();
+      for (int k = lane; k < F; k += 32) {
+        double re = 0.0, im = 0.0;
+        int idx = 0;
+        for (int j = 0; j < N; ++j) {
+          const double v = z[j];
+          re = fma(v, dc[idx], re);
+          im = fma(-v, ds[idx], im);
+          idx += k; if (idx >= N) idx -= N;
+        }
+        double pw = (re * re + im * im) * scale;
+        const bool dbl = (N % 2 == 0) ? (k >= 1 && k < F - 1) : (k >= 1);
+        if (dbl) pw *= 2.0;
+        mags[k] += pw;
+      }
+      __syncwarp();
+    }
+  }
+  // rfftfreq(N, d=1/fs)[k] = k * (1/(N*d)); mean over segments; argmax with numpy's first-max rule over finite bins
+  const double fval = 1.0 / ((double)N * (1.0 / fs));
+  double bv = -INFINITY; int bi = 0x7fffffff, cnt = 0;
+  for (int k = lane; k < F; k += 32) {
+    const double v = mags[k] / (double)nseg;
+    if (spec_mag && k < max_bins) {
+      spec_f[sig * max_bins + k] = (float)((double)k * fval);
+      spec_mag[sig * max_bins + k] = (float)v;
+    }
+    if (isfinite(v)) { ++cnt; if (v > bv) { bv = v; bi = k; } }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    num_bins[sig] = F;
+    if (cnt >= 2) { peak_idx[sig] = bi; peak_freq[sig] = (double)bi * fval; peak_mag[sig] = bv; }
+    else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Lomb-Scargle
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double ls_freq(int k, int F, double fmin, double fmax) {  // np.linspace(fmin, fmax, F)[k]
@@ -491,6 +644,16 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   if (p->transform != BPV_PGRAM_LS) {
     const int need = p->transform == BPV_DFT_RFFT ? W / 2 + 1 : (W < 256 ? W : 256) / 2 + 1;
     BPV_REQUIRE(!spec_mag || max_bins >= need, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, need);
+    if (p->transform == BPV_PGRAM_WELCH && W <= 512) {   // warp per signal (x staging needs W <= 512 doubles)
+      const size_t smw = (size_t)(512 + WELCH_WPB * welch_warp_doubles(W)) * sizeof(double);
+      if (smw > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(welch_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      }
+      welch_warp_kernel<<<(unsigned)((nsig + WELCH_WPB - 1) / WELCH_WPB), 32 * WELCH_WPB, smw, st>>>(
+          proc_x, proc_y, *p, max_bins, nsig, spec_f, spec_mag, num_bins, peak_idx, peak_freq, peak_mag);
+      return check_launch("welch_warp_kernel");
+    }
     const size_t smem = (size_t)(4 * W + W / 2 + 2 + 256) * sizeof(double);
     BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window %d too large for the dense spectrum kernel", W);
     if (smem > 48 * 1024) {

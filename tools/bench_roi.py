@@ -18,6 +18,8 @@ ap.add_argument('--iters', type=int, default=20)
 ap.add_argument('--hint', type=int, default=0)
 ap.add_argument('--mode', type=int, default=1)
 ap.add_argument('--l2gran', type=int, default=0)
+ap.add_argument('--host', action='store_true', help='frames in pinned host memory (zero-copy reads over PCIe)')
+ap.add_argument('--box', default='', help='w,h: fixed-size boxes at random positions instead of the synthetic forehead/palm boxes')
 a = ap.parse_args()
 N, H, W = a.frames, a.H, a.W
 from bpv import _cabi  # noqa: E402
@@ -25,11 +27,23 @@ torch.cuda.init(); torch.zeros(1, device='cuda')
 if a.l2gran:
     _cabi.check(_cabi.lib().bpv_set_l2_fetch_granularity(a.l2gran), 'l2gran')
 print('l2 fetch granularity', _cabi.lib().bpv_get_l2_fetch_granularity())
-frames = torch.empty((N, H, W, 3), dtype=torch.uint8, device='cuda')
-for i in range(0, N, 64):
-    frames[i:i + 64].random_(0, 256)
+if a.host:
+    frames = torch.empty((N, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    tmp = torch.empty((64, H, W, 3), dtype=torch.uint8, device='cuda')
+    for i in range(0, N, 64):
+        tmp.random_(0, 256)
+        frames[i:i + 64].copy_(tmp[:min(64, N - i)])
+    del tmp
+else:
+    frames = torch.empty((N, H, W, 3), dtype=torch.uint8, device='cuda')
+    for i in range(0, N, 64):
+        frames[i:i + 64].random_(0, 256)
 rng = np.random.default_rng(0)
 boxes_np = synth.roi_boxes(rng, N, H, W)
+if a.box:
+    bw, bh = (int(v) for v in a.box.split(','))
+    x0 = rng.integers(0, W - bw + 1, (N, 2)); y0 = rng.integers(0, H - bh + 1, (N, 2))
+    boxes_np = np.stack([x0, y0, x0 + bw, y0 + bh], axis=-1).astype(np.int32)
 boxes = torch.from_numpy(boxes_np).cuda()
 
 
@@ -52,6 +66,7 @@ out = torch.empty((N, 2), dtype=torch.float64, device='cuda')
 for _ in range(3):
     ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
 torch.cuda.synchronize()
+print('checksum', repr(float(out.nan_to_num().double().sum().item())), int(out.isnan().sum().item()))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
 ev[0].record()
 for i in range(a.iters):
