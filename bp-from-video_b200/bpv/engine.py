@@ -51,7 +51,7 @@ class StepResult:
 
     def packed(self) -> torch.Tensor:
         """[J, 2R + 2P] float64 record (bpm, ptt_ms, peak_idx, lag_idx) — what the multi-GPU gather moves."""
-        return torch.cat([self.bpm, self.ptt_ms, self.peak_idx.double(), self.lag_idx.double()], dim=1)
+        return ops.pack_records(self.peak_freq, self.lag_sec, self.peak_idx, self.lag_idx)
 
 
 class BatchedSignalProcessor:
@@ -104,11 +104,16 @@ class BatchedSignalProcessor:
     def _params(self, head0: int, head_step: int, jobs: int) -> _cabi.WindowParams:
         return ops.make_params(self.S, self.R, self.cap, self.W, head0, head_step, jobs, self.methods, self.transform, **self.kw)
 
-    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor) -> StepResult:
+    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None) -> StepResult:
         """frames uint8 [S, T, H, W, 3] (HBM, or pinned host memory: the ROI kernel then reads the ROI rows
-        straight over PCIe), boxes int32 [S, T, R, 4] (device), timestamps float64 [S, T] (device)."""
+        straight over PCIe), boxes int32 [S, T, R, 4] (device), timestamps float64 [S, T] (device).
+        view = (view_w, view_h, left, flip_horizontally): the boxes are expressed in the reference VideoReader's
+        cropped / mirrored view of the decoded frames (video_reader.py:97-103) and are mapped back onto `frames`
+        on the device; nothing is copied."""
         S, T = frames.shape[:2]
         assert S == self.S and 1 <= T <= self.Tmax and boxes.shape == (S, T, self.R, 4)
+        if view is not None:
+            boxes = ops.view_boxes(boxes.contiguous(), *view)
         samples = self._samples[:, :T]
         if T != self.Tmax:
             samples = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)

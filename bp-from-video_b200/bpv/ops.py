@@ -138,14 +138,20 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
     mb = max_bins(p)
     o = out or {}
     if store:
-        o.setdefault('freqs', torch.empty((J, p.R, mb), dtype=torch.float32, device=dev))
-        o.setdefault('mags', torch.empty((J, p.R, mb), dtype=torch.float32, device=dev))
+        if 'freqs' not in o:
+            o['freqs'] = torch.empty((J, p.R, mb), dtype=torch.float32, device=dev)
+        if 'mags' not in o:
+            o['mags'] = torch.empty((J, p.R, mb), dtype=torch.float32, device=dev)
     else:
         o['freqs'] = o['mags'] = None
-    o.setdefault('num_bins', torch.empty((J, p.R), dtype=torch.int32, device=dev))
-    o.setdefault('peak_idx', torch.empty((J, p.R), dtype=torch.int32, device=dev))
-    o.setdefault('peak_freq', torch.empty((J, p.R), dtype=torch.float64, device=dev))
-    o.setdefault('peak_mag', torch.empty((J, p.R), dtype=torch.float64, device=dev))
+    if 'num_bins' not in o:
+        o['num_bins'] = torch.empty((J, p.R), dtype=torch.int32, device=dev)
+    if 'peak_idx' not in o:
+        o['peak_idx'] = torch.empty((J, p.R), dtype=torch.int32, device=dev)
+    if 'peak_freq' not in o:
+        o['peak_freq'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
+    if 'peak_mag' not in o:
+        o['peak_mag'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
     need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if not store else 0
     if need and (workspace is None or workspace.numel() < need):
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -164,14 +170,20 @@ def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
     L = 2 * p.window - 1
     o = out or {}
     if store:
-        o.setdefault('lags', torch.empty((J, P, L), dtype=torch.float32, device=dev))
-        o.setdefault('corr', torch.empty((J, P, L), dtype=torch.float32, device=dev))
+        if 'lags' not in o:
+            o['lags'] = torch.empty((J, P, L), dtype=torch.float32, device=dev)
+        if 'corr' not in o:
+            o['corr'] = torch.empty((J, P, L), dtype=torch.float32, device=dev)
     else:
         o['lags'] = o['corr'] = None
-    o.setdefault('num_lags', torch.empty((J, P), dtype=torch.int32, device=dev))
-    o.setdefault('lag_idx', torch.empty((J, P), dtype=torch.int32, device=dev))
-    o.setdefault('lag_sec', torch.empty((J, P), dtype=torch.float64, device=dev))
-    o.setdefault('lag_corr', torch.empty((J, P), dtype=torch.float64, device=dev))
+    if 'num_lags' not in o:
+        o['num_lags'] = torch.empty((J, P), dtype=torch.int32, device=dev)
+    if 'lag_idx' not in o:
+        o['lag_idx'] = torch.empty((J, P), dtype=torch.int32, device=dev)
+    if 'lag_sec' not in o:
+        o['lag_sec'] = torch.empty((J, P), dtype=torch.float64, device=dev)
+    if 'lag_corr' not in o:
+        o['lag_corr'] = torch.empty((J, P), dtype=torch.float64, device=dev)
     if P > 0:
         check(lib().bpv_window_xcorr(ptr(proc_x), ptr(proc_y), C.byref(p), ptr(o['lags']), ptr(o['corr']),
                                      ptr(o['num_lags']), ptr(o['lag_idx']), ptr(o['lag_sec']), ptr(o['lag_corr']),
@@ -188,4 +200,25 @@ def butter_sos_design(fs: torch.Tensor, p: WindowParams):
 def firls_design(fs: torch.Tensor, p: WindowParams):
     out = torch.empty((fs.numel(), p.fir_taps), dtype=torch.float64, device=fs.device)
     check(lib().bpv_firls_design(ptr(fs), fs.numel(), C.byref(p), ptr(out), stream_handle()), 'bpv_firls_design')
+    return out
+
+
+def view_boxes(boxes: torch.Tensor, view_w: int, view_h: int, left: int = 0, flip_horizontally: bool = False, out=None):
+    """Map boxes int32 [..., 4] expressed in the VideoReader view (portrait crop frame[:, left:left+view_w], optional
+    horizontal flip; video_reader.py:97-103) onto the decoded frame.  No pixel is copied."""
+    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[-1] == 4
+    out = torch.empty_like(boxes) if out is None else out
+    check(lib().bpv_view_boxes(ptr(boxes), boxes.numel() // 4, int(view_w), int(view_h), int(left), int(bool(flip_horizontally)),
+                               ptr(out), stream_handle()), 'bpv_view_boxes')
+    return out
+
+
+def pack_records(peak_freq, lag_sec, peak_idx, lag_idx, out=None):
+    """[J, 2R + 2P] float64 record (bpm, ptt_ms, peak_idx, lag_idx) (signal_processor.py:310, 312)."""
+    J, R = peak_freq.shape
+    P = lag_sec.shape[1]
+    if out is None:
+        out = torch.empty((J, 2 * R + 2 * P), dtype=torch.float64, device=peak_freq.device)
+    check(lib().bpv_pack_records(ptr(peak_freq), ptr(lag_sec) if P else None, ptr(peak_idx), ptr(lag_idx) if P else None,
+                                 J, R, P, ptr(out), stream_handle()), 'bpv_pack_records')
     return out

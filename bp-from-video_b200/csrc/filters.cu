@@ -60,7 +60,8 @@ constexpr int FIRLS_DPB = FIRLS_DPW * FIRLS_WARPS;  // designs per CTA
 // groups of a warp read different bank halves.  Sized so that 7 CTAs (56 designs) fit an SM: 8192 designs = one wave.
 constexpr int FIRLS_PAD = 16;
 constexpr int FIRLS_WS = 3 * (FIRLS_PAD + 128) + 64;
-__host__ __device__ constexpr int firls_smem_offset(int d) { return d * FIRLS_WS + (d & 1) * 8; }   // design d of the CTA
+// design d of the CTA: regions never overlap, bases are 0, 8, 8, 0 (mod 16 doubles) within a warp
+__host__ __device__ constexpr int firls_smem_offset(int d) { return d * FIRLS_WS + ((d + 1) >> 1) * 8; }
 __device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
   for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
   firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, smem + firls_smem_offset(d));
 }
 
-constexpr size_t FIRLS_SMEM = (size_t)(FIRLS_DPB * FIRLS_WS + 8) * sizeof(double);
+constexpr size_t FIRLS_SMEM = (size_t)(firls_smem_offset(FIRLS_DPB - 1) + FIRLS_WS) * sizeof(double);
 
 int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* sos_out, cudaStream_t st) {
   const int J = p.S * p.jobs_per_stream;

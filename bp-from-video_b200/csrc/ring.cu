@@ -94,3 +94,36 @@ extern "C" int bpv_running_mean(double* ring, int32_t S, int32_t C, int32_t H, i
   running_mean_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ring, S, C, H, g0, T, values, scale, mean, mean_int);
   return check_launch("bpv_running_mean");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Result record of a step: [J, 2R + 2P] float64 = (bpm[R], ptt_ms[P], peak_idx[R], lag_idx[P]) per window job —
+// what SignalProcessor.process appends to sg_bpm / sg_ptt (signal_processor.py:310, 312: f * 60, t * 1000) plus the
+// bit-exact bins; the record the multi-GPU gather and the host read-back move.
+namespace bpv {
+__global__ void pack_records_kernel(const double* __restrict__ peak_freq, const double* __restrict__ lag_sec,
+                                    const int32_t* __restrict__ peak_idx, const int32_t* __restrict__ lag_idx,
+                                    long long J, int R, int P, double* __restrict__ out) {
+  const int C = 2 * R + 2 * P;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= J * C) return;
+  const long long j = i / C;
+  const int c = (int)(i % C);
+  double v;
+  if (c < R) v = peak_freq[j * R + c] * 60;
+  else if (c < R + P) v = lag_sec[j * P + (c - R)] * 1000;
+  else if (c < 2 * R + P) v = (double)peak_idx[j * R + (c - R - P)];
+  else v = (double)lag_idx[j * P + (c - 2 * R - P)];
+  out[i] = v;
+}
+}  // namespace bpv
+
+extern "C" int bpv_pack_records(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx,
+                                const int32_t* lag_idx, int64_t J, int32_t R, int32_t P, double* out, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(peak_freq && peak_idx && out && (P == 0 || (lag_sec && lag_idx)), BPV_E_INVALID, "bpv_pack_records: NULL pointer");
+  BPV_REQUIRE(J >= 0 && R > 0 && P >= 0, BPV_E_INVALID, "bpv_pack_records: bad sizes");
+  if (J == 0) return 0;
+  const long long n = J * (2 * R + 2 * P);
+  pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(peak_freq, lag_sec, peak_idx, lag_idx, J, R, P, out);
+  return check_launch("bpv_pack_records");
+}

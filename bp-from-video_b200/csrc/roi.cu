@@ -289,8 +289,15 @@ __global__ void __launch_bounds__(256, MINB) roi_rows_kernel(const RoiArgs a) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16_64B(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+// 16-byte LDGSTS with a 64-byte L2 fill granule and an evict-first L2 policy: ROI bytes are read exactly once, so they
+// must not push the window pipeline's L2-resident scratch (proc_x / proc_y, ~80 MB, rewritten every step) out to DRAM.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_64B(uint32_t dst, const void* src, unsigned long long pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint.L2::64B [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(THREADS) roi_staged_kernel(const RoiArgs a, co
     if (STAGE == 1) {
       const long long step = (long long)rps * a.row_stride;
       const uint32_t slot0 = sbase + 16u * (uint32_t)gt;
+      const unsigned long long pol = l2_evict_first_policy();
       for (int v = v0; v < vpr; v += THREADS) {
         const int rel = 16 * v - off;
         const int lo = rel < 0 ? -rel : 0;
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(THREADS) roi_staged_kernel(const RoiArgs a, co
         for (int r = r0; r < nrows; r += rps * K) {
 #pragma unroll
           for (int u = 0; u < K; ++u)
-            if (r + u * rps < nrows) cp_async16_64B(slot0 + (uint32_t)(u * THREADS * 16), p + u * step);
+            if (r + u * rps < nrows) cp_async16_64B(slot0 + (uint32_t)(u * THREADS * 16), p + u * step, pol);
           cp_async_wait_all();
 #pragma unroll
           for (int u = 0; u < K; ++u) {

@@ -85,3 +85,45 @@ extern "C" int bpv_calc_rois(const uint8_t* present, const int32_t* bbox, const 
                                                                      hist, locations, smoothed, boxes);
   return check_launch("bpv_calc_rois");
 }
+
+// ---------------------------------------------------------------------------------------------
+// VideoReader view in front of F1 — SURVEY.md §8(f) row 2 (video_reader.py:97-103): the reference crops the decoded
+// frame to a centred portrait window (frame[:, left:right]) and mirrors it (cv2.flip(frame, 1)) BEFORE the signal
+// path sees it; ROI boxes are expressed in that view.  A ROI mean is invariant under mirroring the ROI, so instead
+// of materialising the cropped / flipped frame the box is mapped back onto the decoded frame in HBM:
+//   view column c  <->  source column  left + c            (no flip)
+//                       left + (view_w - 1 - c)            (flip)
+// The box is first normalised with Python slice semantics against the VIEW width (negative indices wrap around the
+// view, stops clamp), so the mapped box is a plain in-range box of the source frame; rows are untouched.
+namespace bpv {
+__global__ void view_boxes_kernel(const int32_t* __restrict__ boxes, long long n, int view_w, int view_h, int left, int flip,
+                                  int32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 b = reinterpret_cast<const int4*>(boxes)[i];
+  int4 o = b;
+  if (b.x != BPV_NO_BOX) {
+    long long xs = b.x, xe = b.z, ys = b.y, ye = b.w;
+    if (xs < 0) { xs += view_w; if (xs < 0) xs = 0; } else if (xs > view_w) xs = view_w;
+    if (xe < 0) { xe += view_w; if (xe < 0) xe = 0; } else if (xe > view_w) xe = view_w;
+    if (xe < xs) xe = xs;
+    if (ys < 0) { ys += view_h; if (ys < 0) ys = 0; } else if (ys > view_h) ys = view_h;
+    if (ye < 0) { ye += view_h; if (ye < 0) ye = 0; } else if (ye > view_h) ye = view_h;
+    if (ye < ys) ye = ys;
+    if (flip) { const long long t = view_w - xe; xe = view_w - xs; xs = t; }
+    o.x = (int)(xs + left); o.z = (int)(xe + left); o.y = (int)ys; o.w = (int)ye;
+  }
+  reinterpret_cast<int4*>(out)[i] = o;
+}
+}  // namespace bpv
+
+extern "C" int bpv_view_boxes(const int32_t* boxes, int64_t num_boxes, int32_t view_w, int32_t view_h, int32_t left,
+                              int32_t flip_horizontally, int32_t* out, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(boxes && out, BPV_E_INVALID, "bpv_view_boxes: NULL pointer");
+  BPV_REQUIRE(num_boxes >= 0 && view_w > 0 && view_h > 0 && left >= 0, BPV_E_INVALID, "bpv_view_boxes: bad sizes");
+  if (num_boxes == 0) return 0;
+  view_boxes_kernel<<<(unsigned)((num_boxes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes, num_boxes, view_w, view_h, left,
+                                                                                         flip_horizontally, out);
+  return check_launch("bpv_view_boxes");
+}

@@ -103,6 +103,16 @@ int bpv_calc_rois(const uint8_t* present, const int32_t* bbox, const int32_t* po
                   double* hist, double* locations, double* smoothed, int32_t* boxes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * VideoReader view in front of F1 — the reference crops the decoded frame to a centred portrait window
+ *     (frame[:, left:right], video_reader.py:97-101) and mirrors it (cv2.flip(frame, 1), :103) before the signal
+ *     path sees it; boxes are expressed in that view.  Maps boxes int32 [num_boxes, 4] (x0, y0, x1, y1; Python slice
+ *     semantics against the view_w x view_h VIEW) onto the decoded frame in HBM: out = in-range boxes of the source
+ *     frame whose ROI means equal the view's (a mean is invariant under mirroring the ROI).  No pixel is copied.
+ */
+int bpv_view_boxes(const int32_t* boxes, int64_t num_boxes, int32_t view_w, int32_t view_h, int32_t left,
+                   int32_t flip_horizontally, int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Ring buffers — replaces Signal.add_sample / SignalGroup.add_samples for sg_raw
  *     (signal_data.py:31-35, 94-98; deque(maxlen) prefilled with NaN, signal_data.py:18-19).
  *
@@ -187,6 +197,15 @@ int bpv_window_xcorr(const double* proc_x, const double* proc_y, const bpv_windo
  * fs float64 [n]; sos_out float64 [n, order, 6]; taps_out float64 [n, fir_taps]. */
 int bpv_butter_sos_design(const double* fs, int32_t n, const bpv_window_params* p, double* sos_out, void* stream);
 int bpv_firls_design(const double* fs, int32_t n, const bpv_window_params* p, double* taps_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Result record of a step — what SignalProcessor.process appends to sg_bpm / sg_ptt
+ *     (signal_processor.py:310, 312: f * 60, t * 1000) plus the bit-exact bins.
+ * out float64 [J, 2R + 2P] = (bpm[R], ptt_ms[P], peak_idx[R], lag_idx[P]) per window job: the record the multi-GPU
+ * gather and the host read-back move.
+ */
+int bpv_pack_records(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx, const int32_t* lag_idx,
+                     int64_t J, int32_t R, int32_t P, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,3 +93,44 @@ def test_unknown_channel_raises():
     boxes = torch.zeros((1, 1, 4), dtype=torch.int32, device='cuda')
     with pytest.raises(NotImplementedError):
         ops.roi_sample(frames, boxes, 7)
+
+
+@pytest.mark.parametrize('flip', [False, True])
+@pytest.mark.parametrize('shape', [(48, 64), (90, 160)])
+def test_videoreader_view_crop_flip_exact(flip, shape):
+    """boxes expressed in the reference VideoReader's view (portrait crop frame[:, left:right],
+    video_reader.py:97-101, then cv2.flip(frame, 1), :103) sampled straight from the decoded frame must equal the
+    reference sampling of the materialised view, bit for bit — including negative / clamped / empty boxes."""
+    from bpv import ops
+    H, W = shape
+    rng = np.random.default_rng(H * 7 + W + int(flip))
+    N = 12
+    frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    new_w = int(np.round(H / np.sqrt(2)))                   # video_reader.py:98-100
+    left, right = W // 2 - new_w // 2, W // 2 + new_w // 2
+    vw = right - left
+    boxes = np.empty((N, 2, 4), np.int32)
+    boxes[..., 0] = rng.integers(-vw - 5, vw + 5, (N, 2))
+    boxes[..., 2] = boxes[..., 0] + rng.integers(-3, vw, (N, 2))
+    boxes[..., 1] = rng.integers(-H - 5, H + 5, (N, 2))
+    boxes[..., 3] = boxes[..., 1] + rng.integers(-3, H, (N, 2))
+    boxes[0, 0] = (0, 0, vw, H)                            # whole view
+    boxes[1, 1] = (-10, -10, -2, -2)                       # negative wrap inside the view
+    boxes[2, 0] = (orc.np.iinfo(np.int32).min, 0, 0, 0)    # no detection
+    src_boxes = ops.view_boxes(torch.from_numpy(boxes).cuda(), vw, H, left, flip)
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        val, sums = ops.roi_sample(torch.from_numpy(frames).cuda(), src_boxes, mode, want_sums=True, roi_pixels_hint=600)
+        val, sums = val.cpu().numpy(), sums.cpu().numpy()
+        for f in range(N):
+            view = frames[f][:, left:right, :]
+            if flip:
+                view = view[:, ::-1, :]                    # == cv2.flip(view, 1)
+            for r in range(2):
+                b = boxes[f, r]
+                if b[0] == orc.np.iinfo(np.int32).min:
+                    assert np.isnan(val[f, r])
+                    continue
+                ref = orc.roi_sample(np.ascontiguousarray(view), (0, 0, *[int(v) for v in b]), mode)
+                assert h.same(val[f, r], ref), (f, r, b, val[f, r], ref)
+                sb, sg, sr, n = orc.roi_sums(np.ascontiguousarray(view), b)
+                assert tuple(int(v) for v in sums[f, r]) == (sb, sg, sr, n)

@@ -77,6 +77,22 @@ def test_firls_design():
         np.testing.assert_allclose(got[i], ref, rtol=0, atol=1e-9 * np.abs(ref).max())
 
 
+def test_firls_design_many_jobs_deterministic():
+    """Several designs share a warp and a CTA's shared memory: 4099 designs (ragged last CTA) of cycling sampling rates
+    must all equal the design of the same rate computed alone, bit for bit, on every run (caught a cross-warp
+    shared-memory overlap once)."""
+    from bpv import ops
+    p = params(1, 1, 8, [])
+    base = np.array([29.97, 8.7, 120.0, 30.0, 25.3, 61.7, 15.0])
+    alone = torch.stack([ops.firls_design(torch.tensor([f], dtype=torch.float64, device='cuda'), p)[0] for f in base])
+    fs = np.tile(base, 586)[:4099]
+    for _ in range(3):
+        got = ops.firls_design(torch.from_numpy(fs).cuda(), p)
+        assert torch.equal(got, alone[torch.arange(4099, device='cuda') % len(base)])
+    ref = orc.make_filter(orc.FILTER_FIR, 29.97)
+    np.testing.assert_allclose(alone[0].cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
 METHOD_SETS = [
     [], [orc.DIFF_1], [orc.DIFF_2], [orc.DETREND_CONST], [orc.DETREND_LINEAR], [orc.INTERP_LINEAR], [orc.INTERP_CUBIC],
     [orc.FILTER_BUTTER], [orc.FILTER_FIR],
