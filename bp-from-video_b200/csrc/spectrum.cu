@@ -241,9 +241,50 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
 // smem: CTA table tw[256] (cos, sin) | per warp: ys[W] | buf[512] | mags[130] | z[256]
 // ---------------------------------------------------------------------------------------------
 constexpr int WELCH_WPB = 4;
-__host__ __device__ inline int welch_warp_doubles(int W) { return W + 512 + 130 + 256; }
+__host__ __device__ inline int welch_warp_doubles(int W) { return W + 576 + 130 + 256; }
+// FFT buffer index padding: one spare complex slot per 8 keeps the strided accesses of the late passes and the
+// 4-element groups of the last pass on distinct banks
+__device__ __forceinline__ int wpad(int e) { return e + (e >> 3); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// d * conj(t) for a unit twiddle t = (cos, sin): multiplication by exp(-i * angle)
+__device__ __forceinline__ double2 cmulc(double2 d, double2 t) {
+  return make_double2(fma(d.x, t.x, d.y * t.y), fma(d.y, t.x, -(d.x * t.y)));
+}
+// Two fused radix-2 decimation-in-frequency stages (spans 2Q and Q) of a 256-point FFT held in shared memory:
+// each lane owns two groups of four elements i, i+Q, i+2Q, i+3Q (i mod 4Q < Q).  Natural-order input, after the four
+// passes Q = 64, 16, 4, 1 the output is in bit-reversed order.  Twiddles: A = W_4Q^p, -iA = W_4Q^(p+Q), C = W_2Q^p with
+// p = i mod Q, read from the CTA's table tw[k] = exp(+2 pi i k / 256).
+template <int Q>
+__device__ __forceinline__ void welch_fft_pass(double2* __restrict__ fz, const double2* __restrict__ tw, int lane) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int g = lane + 32 * j;
+    const int pq = g & (Q - 1);
+    const int i = (g / Q) * (4 * Q) + pq;
+    const int a0 = wpad(i), a1 = wpad(i + Q), a2 = wpad(i + 2 * Q), a3 = wpad(i + 3 * Q);
+    const double2 e0 = fz[a0], e1 = fz[a1], e2 = fz[a2], e3 = fz[a3];
+    const double2 t0 = cadd(e0, e2), t1 = cadd(e1, e3);
+    double2 t2 = csub(e0, e2), t3 = csub(e1, e3);
+    if (Q > 1) {
+      const double2 A = tw[pq * (64 / Q)];
+      t2 = cmulc(t2, A);
+      t3 = cmulc(t3, A);
+    }
+    t3 = make_double2(t3.y, -t3.x);                 // * (-i)
+    const double2 o0 = cadd(t0, t1), o2 = cadd(t2, t3);
+    double2 o1 = csub(t0, t1), o3 = csub(t2, t3);
+    if (Q > 1) {
+      const double2 C2 = tw[pq * (128 / Q)];
+      o1 = cmulc(o1, C2);
+      o3 = cmulc(o3, C2);
+    }
+    fz[a0] = o0; fz[a1] = o1; fz[a2] = o2; fz[a3] = o3;
+  }
+  __syncwarp();
+}
 
-__global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double* __restrict__ proc_x,
+__global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const double* __restrict__ proc_x,
                                                                     const double* __restrict__ proc_y,
                                                                     const bpv_window_params p, int max_bins, long long nsig,
                                                                     float* __restrict__ spec_f, float* __restrict__ spec_mag,
@@ -258,7 +299,7 @@ __global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double
   if (sig >= nsig) return;
   double* ys = sm + 512 + (size_t)wid * welch_warp_doubles(W);
   double* buf = ys + W;            // FFT: 256 complex (re, im interleaved); direct DFT: cos[256] | sin[256]
-  double* mags = buf + 512;
+  double* mags = buf + 576;
   double* z = mags + 130;
   const double* px = proc_x + sig * W;
   const double* py = proc_y + sig * W;
@@ -303,6 +344,7 @@ __global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double
   double sw = 0.0;
   for (int i = lane; i < N; i += 32) { const double wj = 0.5 - 0.5 * (fft ? tw[i].x : dc[i]); sw = fma(wj, wj, sw); }
   const double scale = 1.0 / (fs * warp_sum(sw));
+  double facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // FFT path: power sums of the bins this lane owns (positions lane + 32 j)
   for (int sg = 0; sg < nseg; ++sg) {
     const double* seg = ys + sg * hop;
     double a = 0.0;
@@ -313,30 +355,24 @@ __global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = lane + 32 * j;
-        fz[__brev((unsigned)i) >> 24] = make_double2((seg[i] - mean) * (0.5 - 0.5 * tw[i].x), 0.0);
+        fz[wpad(i)] = make_double2((seg[i] - mean) * (0.5 - 0.5 * tw[i].x), 0.0);
       }
       __syncwarp();
+      welch_fft_pass<64>(fz, tw, lane);
+      welch_fft_pass<16>(fz, tw, lane);
+      welch_fft_pass<4>(fz, tw, lane);
+      welch_fft_pass<1>(fz, tw, lane);
+      // bin k sits at position brev8(k): every lane takes the contiguous positions lane + 32 j and keeps its own bins
 #pragma unroll
-      for (int st = 0; st < 8; ++st) {
-        const int half = 1 << st;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int b = lane + 32 * j;
-          const int pos = b & (half - 1);
-          const int i0 = ((b >> st) << (st + 1)) + pos, i1 = i0 + half;
-          const double2 t = tw[pos << (7 - st)];                 // exp(-2*pi*i*tw/256) = (t.x, -t.y)
-          const double2 xv = fz[i1], u = fz[i0];
-          const double tr = fma(t.x, xv.x, t.y * xv.y), ti = fma(t.x, xv.y, -t.y * xv.x);
-          fz[i0] = make_double2(u.x + tr, u.y + ti);
-          fz[i1] = make_double2(u.x - tr, u.y - ti);
+      for (int j = 0; j < 8; ++j) {
+        const int pos = lane + 32 * j;
+        const int k = (int)(__brev((unsigned)pos) >> 24);
+        if (k < F) {
+          const double2 v = fz[wpad(pos)];
+          double pw = (v.x * v.x + v.y * v.y) * scale;
+          if (k >= 1 && k < F - 1) pw *= 2.0;
+          facc[j] += pw;
         }
-        __syncwarp();
-      }
-      for (int k = lane; k < F; k += 32) {
-        const double2 v = fz[k];
-        double pw = (v.x * v.x + v.y * v.y) * scale;
-        if (k >= 1 && k < F - 1) pw *= 2.0;
-        mags[k] += pw;
       }
       __syncwarp();
     } else {
@@ -362,13 +398,28 @@ __global__ void __launch_bounds__(32 * WELCH_WPB) welch_warp_kernel(const double
   // rfftfreq(N, d=1/fs)[k] = k * (1/(N*d)); mean over segments; argmax with numpy's first-max rule over finite bins
   const double fval = 1.0 / ((double)N * (1.0 / fs));
   double bv = -INFINITY; int bi = 0x7fffffff, cnt = 0;
-  for (int k = lane; k < F; k += 32) {
-    const double v = mags[k] / (double)nseg;
-    if (spec_mag && k < max_bins) {
-      spec_f[sig * max_bins + k] = (float)((double)k * fval);
-      spec_mag[sig * max_bins + k] = (float)v;
+  if (fft) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (int)(__brev((unsigned)(lane + 32 * j)) >> 24);
+      if (k < F) {
+        const double v = facc[j] / (double)nseg;
+        if (spec_mag && k < max_bins) {
+          spec_f[sig * max_bins + k] = (float)((double)k * fval);
+          spec_mag[sig * max_bins + k] = (float)v;
+        }
+        if (isfinite(v)) { ++cnt; if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; } }
+      }
     }
-    if (isfinite(v)) { ++cnt; if (v > bv) { bv = v; bi = k; } }
+  } else {
+    for (int k = lane; k < F; k += 32) {
+      const double v = mags[k] / (double)nseg;
+      if (spec_mag && k < max_bins) {
+        spec_f[sig * max_bins + k] = (float)((double)k * fval);
+        spec_mag[sig * max_bins + k] = (float)v;
+      }
+      if (isfinite(v)) { ++cnt; if (v > bv) { bv = v; bi = k; } }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_xor_sync(0xffffffffu, bv, o);

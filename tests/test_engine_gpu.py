@@ -199,3 +199,56 @@ def test_full_size_windows_signals_only(name, cfg):
             L = a['num_lags'][s, 0]
             assert L == len(el) and h.close(a['corr'][s, 0, :L], ec, rtol=1e-4, atol_frac=1e-5)
             assert lidx[s, 0] == li and h.close(ptt[s, 0], lx * 1000, rtol=1e-12, atol_frac=0)
+
+
+def test_three_rois_three_pairs_match_oracle():
+    """R = 3 ROI configs (e.g. forehead + cheek + palm, roi.py:24-28) give P = C(3,2) = 3 pairs in
+    itertools.combinations order (signal_processor.py:298-299): (0,1), (0,2), (1,2)."""
+    from bpv import synth
+    from bpv.engine import BatchedSignalProcessor
+    S, R, W, T, n, H, Wd = 2, 3, 36, 3, 45, 60, 80
+    channel, methods, transform = orc.GREEN, [orc.DETREND_LINEAR, orc.FILTER_BUTTER], orc.PGRAM_LS
+    rng = np.random.default_rng(7)
+    ts = np.stack([synth.timestamps(rng, n, 30.0, irregular=True, drop=0.05, origin=rng.uniform(0, 100)) for _ in range(S)])
+    frames = np.stack([synth.frames(rng, ts[s], H, Wd, f_pulse=1.1 + 0.3 * s) for s in range(S)])
+    b2 = np.stack([synth.roi_boxes(rng, n, H, Wd, p_none=0.04, p_oob=0.02) for _ in range(S)])      # [S, n, 2, 4]
+    third = b2[:, :, :1].copy()                                  # a cheek-like box: the forehead box shifted down
+    ok = third[..., 0] != synth.NO_BOX
+    third[..., 1] += np.where(ok, 14, 0); third[..., 3] += np.where(ok, 14, 0)
+    boxes = np.ascontiguousarray(np.concatenate([b2[:, :, :1], third, b2[:, :, 1:]], axis=2))          # [S, n, 3, 4]
+    eng = BatchedSignalProcessor(S, R, signal_max_samples=W, max_frames_per_step=T, color_channel=channel,
+                                 processing_methods=methods, spectrum_transform=transform, windows='every_frame')
+    oracles = [orc.OracleStream(R, 1, W, 50, channel, methods, transform) for _ in range(S)]
+    assert eng.P == 3
+    checked = 0
+    for g0 in range(0, n, T):
+        res = eng.step(torch.from_numpy(frames[:, g0:g0 + T]).cuda(), torch.from_numpy(boxes[:, g0:g0 + T]).cuda(),
+                       torch.from_numpy(ts[:, g0:g0 + T].copy()).cuda())
+        pidx = res.peak_idx.cpu().numpy().reshape(S, T, R)
+        lidx = res.lag_idx.cpu().numpy().reshape(S, T, 3)
+        ptt = res.ptt_ms.cpu().numpy().reshape(S, T, 3)
+        rec = res.packed().cpu().numpy().reshape(S, T, 2 * R + 6)
+        smp = res.samples.cpu().numpy()
+        for s in range(S):
+            for j in range(T):
+                b = boxes[s, g0 + j]
+                rois = [(np.nan,) * 6 if b[r, 0] == synth.NO_BOX else (0, 0, *[int(v) for v in b[r]]) for r in range(R)]
+                out = oracles[s].process(frames[s, g0 + j], float(ts[s, g0 + j]), rois)
+                assert h.same(smp[s, j], out['samples'])
+                raw = oracles[s].raw
+                residue = [not np.isfinite(out['proc_y'][r]).any() or
+                           np.nanmax(np.abs(out['proc_y'][r])) < RESIDUE * np.nanmax(np.abs(raw[r])) for r in range(R)]
+                for r in range(R):
+                    if int(np.isfinite(raw[r]).sum()) >= MIN_N and not residue[r]:
+                        assert pidx[s, j, r] == out['peak_idx'][r], (s, g0 + j, r)
+                for pi, (ra, rb) in enumerate([(0, 1), (0, 2), (1, 2)]):
+                    joint = int((np.isfinite(raw[ra]) & np.isfinite(raw[rb])).sum())
+                    if joint < MIN_N or residue[ra] or residue[rb]:
+                        continue
+                    assert lidx[s, j, pi] == out['lag_idx'][pi], (s, g0 + j, pi)
+                    assert h.close(ptt[s, j, pi], out['ptt'][pi], rtol=1e-12, atol_frac=0)
+                    checked += 1
+                # packed record layout: bpm[R] | ptt_ms[P] | peak_idx[R] | lag_idx[P]
+                np.testing.assert_array_equal(rec[s, j, R + 3:2 * R + 3], pidx[s, j].astype(np.float64))
+                np.testing.assert_array_equal(rec[s, j, 2 * R + 3:], lidx[s, j].astype(np.float64))
+    assert checked > 100
