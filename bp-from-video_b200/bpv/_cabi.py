@@ -42,6 +42,7 @@ _SIGS = {
     'bpv_running_mean': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, C.c_double, _P, _P, _P]),
     'bpv_view_boxes': (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'bpv_pack_records': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    'bpv_dft256_tc': (C.c_int, [_P, C.c_int32, _P, _P]),
     'bpv_ring_push': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P]),
     'bpv_window_workspace_bytes': (C.c_int64, [C.POINTER(WindowParams)]),
     'bpv_window_preprocess': (C.c_int, [_P, _P, C.POINTER(WindowParams), _P, C.c_int64, _P, _P, _P, _P]),

@@ -17,6 +17,7 @@ device allocations and the stream handle only; every computation is a libbpv ker
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -174,6 +175,9 @@ class BatchedSignalProcessor:
         self._spec, self._xc = sp, xc
         n_pre = 1 + sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
         n_spec = 2 if self.transform == _cabi.PGRAM_LS else 1
+        if (self.transform == _cabi.PGRAM_WELCH and not self.store_arrays and 256 <= self.W <= 383
+                and os.environ.get('BPV_WELCH_TC', '') == '1'):
+            n_spec = 2                  # welch_tc_kernel (tensor cores) + welch_warp_kernel for the windows it flags
         self.launches_per_step = (1 if _count_roi else 0) + 1 + n_pre + n_spec + (1 if self.P else 0)
         arrays = {}
         if self.store_arrays:

@@ -222,3 +222,12 @@ def pack_records(peak_freq, lag_sec, peak_idx, lag_idx, out=None):
     check(lib().bpv_pack_records(ptr(peak_freq), ptr(lag_sec) if P else None, ptr(peak_idx), ptr(lag_idx) if P else None,
                                  J, R, P, ptr(out), stream_handle()), 'bpv_pack_records')
     return out
+
+
+def dft256_tc(z: torch.Tensor) -> torch.Tensor:
+    """256-point DFT of real segments z f32 [rows, 256] on the tensor cores (tcgen05, 3xTF32): returns f32 [rows, 256] with
+    [:, :129] = Re X[0..128] and [:, 129:] = -Im X[1..127]."""
+    assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2 and z.shape[1] == 256
+    d = torch.empty_like(z)
+    check(lib().bpv_dft256_tc(ptr(z), z.shape[0], ptr(d), stream_handle()), 'bpv_dft256_tc')
+    return d

@@ -1,0 +1,441 @@
+// Tensor-core (tcgen05 + TMEM) 256-point DFT of many real segments — the dense contraction inside the Welch
+// periodogram (scipy.signal.welch defaults: nperseg = 256; signal_processor.py:260) and the "batched DFT against a
+// twiddle matrix" the north_star assigns to the 5th-generation tensor cores:
+//
+//     D[m, c] = sum_j Z[m, j] * T[j, c],    m = segment (M = 128 per CTA),  j = sample 0..255 (K),  c = 0..255 (N)
+//     T[j, c] = cos(2 pi j c / 256)          for c = 0..128      (real parts of bins 0..128)
+//             = sin(2 pi j (c-128) / 256)    for c = 129..255    (imaginary parts of bins 1..127, sign dropped)
+//
+// so one M=128, N=256 accumulator tile (256 TMEM columns of fp32) holds the whole one-sided spectrum of 128 segments.
+// Precision: kind::tf32 keeps 11 mantissa bits.  Two uses, two recipes:
+//   tc_dft256<NT, true>   both operands split hi + lo (hi = fp32 with the low 13 mantissa bits cleared, lo = the residual),
+//                         three MMAs per k-step: Zhi*Thi + Zlo*Thi + Zhi*Tlo -> 3.6e-6 of the row maximum (bpv_dft256_tc)
+//   tc_dft256<NT, false>  one MMA per k-step straight from the fp32 segment tile (the tensor core truncates to tf32) against
+//                         the tf32-rounded twiddles: |dX| <= 1.5e-3 * sum|z|, i.e. <= 3.4 % of the power of any bin that
+//                         competes for the maximum (|X| >= rms X = 22.6 rms z).  Enough to SELECT the candidate bins; the
+//                         Welch kernel below then decides among them in float64.
+// Operand layout (no TMA, no swizzle): K-major "interleaved" canonical layout — 16-byte chunks of 4 consecutive k for
+// one row; the 8 rows of a core matrix contiguous (128 B), 8-row groups SBO = 128 B apart, k-chunks LBO apart
+// (LBO = rows * 16 B).  I.e. operand[chunk][row][4].  Tiles are written by ordinary threads (generic proxy) and made
+// visible to the tensor core with fence.proxy.async; one thread issues the MMAs; tcgen05.commit -> mbarrier tells the
+// CTA when the chunk buffers may be overwritten and when the accumulator is complete; tcgen05.ld (32 lanes x 32 columns
+// per warp) brings each row's spectrum back to the thread that owns that segment.
+#include "common.cuh"
+
+namespace bpv {
+
+constexpr int TC_M = 128, TC_N = 256, TC_K = 256;
+constexpr uint32_t TC_A_LBO = TC_M * 16, TC_B_LBO = TC_N * 16, TC_SBO = 128;
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10, K-major A and B,
+// n_dim = N >> 3 @17, m_dim = M >> 4 @24
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+// shared-memory plan (bytes).  The chunk area holds, per pipeline stage (2 stages): A hi | A lo | B hi | B lo of one
+// 16-sample k block (split mode) or B of one 32-sample k block (single mode) — 24 KB / 32 KB per stage.
+constexpr int TC_OFF_Z = 0;                                    // float [64 chunks][128 rows][4]   all of K, full fp32
+constexpr int TC_OFF_CHUNK = TC_OFF_Z + TC_M * TC_K * 4;
+constexpr int TC_STAGE = 32 * 1024;
+constexpr int TC_OFF_TW = TC_OFF_CHUNK + 2 * TC_STAGE;         // double2 [256] exp(+2 pi i k / 256)
+constexpr int TC_OFF_BAR = TC_OFF_TW + 256 * 16;               // 2 x uint64 mbarrier, uint32 tmem slot
+constexpr int TC_SMEM = TC_OFF_BAR + 32;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// cute::UMMA::SmemDescriptor, version 1, SWIZZLE_NONE: start >> 4 @0, LBO >> 4 @16, SBO >> 4 @32
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ float tc_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// TMEM allocation (warp 0) + mbarrier init; every thread returns the TMEM base address.  Ends with a CTA barrier.
+__device__ __forceinline__ uint32_t tc_setup(uint8_t* smem) {
+  const uint32_t bar = tc_smem_u32(smem + TC_OFF_BAR), slot = bar + 16;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *reinterpret_cast<volatile uint32_t*>(smem + TC_OFF_BAR + 16);
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TC_N) : "memory");
+}
+
+// The contraction: Z (full fp32, [64][128][4] in shared memory) x twiddles -> the CTA's TMEM accumulator.
+// Called by all NT threads of the CTA; on return the accumulator is complete and visible (after_thread_sync done).
+// Two-stage pipeline over k blocks: while the tensor core consumes stage s, the threads build stage s^1 (operand
+// chunks from the float64 twiddle table); an mbarrier per stage (tcgen05.commit) says when a stage may be rebuilt.
+template <int NT, bool SPLIT>
+__device__ __forceinline__ void tc_dft256(uint8_t* smem, uint32_t tmem) {
+  constexpr int KB = SPLIT ? 8 : 32;                   // samples per k block
+  constexpr int CH = KB / 4;                           // 16-byte chunks per block
+  constexpr int NB = TC_K / KB;
+  constexpr int OFF_ALO = CH * TC_M * 16, OFF_BHI = 2 * CH * TC_M * 16, OFF_BLO = OFF_BHI + CH * TC_N * 16;
+  static_assert((SPLIT ? OFF_BLO + CH * TC_N * 16 : CH * TC_N * 16) <= TC_STAGE, "stage too small");
+  const int tid = threadIdx.x;
+  const float4* Z = reinterpret_cast<const float4*>(smem + TC_OFF_Z);
+  const double2* tw = reinterpret_cast<const double2*>(smem + TC_OFF_TW);
+  const uint32_t bar = tc_smem_u32(smem + TC_OFF_BAR);
+  const uint32_t z_addr = tc_smem_u32(smem + TC_OFF_Z);
+  for (int kb = 0; kb < NB; ++kb) {
+    const int st = kb & 1;
+    uint8_t* stage = smem + TC_OFF_CHUNK + st * TC_STAGE;
+    if (kb >= 2) tc_wait(bar + 8 * st, (uint32_t)(((kb - 2) >> 1) & 1));   // the MMAs of block kb-2 have consumed this stage
+    if (SPLIT) {
+      float4* Ahi = reinterpret_cast<float4*>(stage);
+      float4* Alo = reinterpret_cast<float4*>(stage + OFF_ALO);
+      for (int it = tid; it < CH * TC_M; it += NT) {
+        const float4 z = Z[kb * CH * TC_M + it];
+        const float4 h = make_float4(tc_hi(z.x), tc_hi(z.y), tc_hi(z.z), tc_hi(z.w));
+        Ahi[it] = h;
+        Alo[it] = make_float4(z.x - h.x, z.y - h.y, z.z - h.z, z.w - h.w);
+      }
+    }
+    // B: the twiddle matrix rows j0 .. j0+3 of chunk c, column n, from the float64 table
+    float4* Bhi = reinterpret_cast<float4*>(stage + (SPLIT ? OFF_BHI : 0));
+    float4* Blo = reinterpret_cast<float4*>(stage + OFF_BLO);
+    for (int it = tid; it < CH * TC_N; it += NT) {
+      const int c = it / TC_N, n = it % TC_N;
+      const int j0 = kb * KB + c * 4;
+      const int kbin = n <= 128 ? n : n - 128;
+      float hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double2 t = tw[((j0 + e) * kbin) & 255];
+        const double v = n <= 128 ? t.x : t.y;
+        if (SPLIT) { hv[e] = tc_hi((float)v); lv[e] = (float)(v - (double)hv[e]); }
+        else {                                          // round to nearest tf32 (half an ulp of the 10-bit mantissa)
+          hv[e] = __uint_as_float((__float_as_uint((float)v) + 0x1000u) & 0xFFFFE000u);
+        }
+      }
+      Bhi[it] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      if (SPLIT) Blo[it] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = tc_smem_u32(stage);
+#pragma unroll
+      for (int ks = 0; ks < KB / 8; ++ks) {                         // UMMA K = 8 for tf32 = 2 chunks
+        if (SPLIT) {
+          const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + OFF_ALO + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
+          const uint64_t dbh = tc_desc(sa + OFF_BHI + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sa + OFF_BLO + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
+          tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
+          tc_mma_tf32(tmem, dal, dbh, 1);
+          tc_mma_tf32(tmem, dah, dbl, 1);
+        } else {                                                    // A straight from the fp32 segment tile
+          const uint64_t da = tc_desc(z_addr + (kb * CH + ks * 2) * TC_A_LBO, TC_A_LBO, TC_SBO);
+          const uint64_t db = tc_desc(sa + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
+          tc_mma_tf32(tmem, da, db, (kb | ks) != 0);
+        }
+      }
+      tc_commit(bar + 8 * st);
+    }
+  }
+  // the last commit (stage (NB-1)&1) completes after every earlier MMA: accumulator done
+  tc_wait(bar + 8 * ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// 32 consecutive accumulator columns of this thread's row (lane = 32 * warp + lane id)
+__device__ __forceinline__ void tc_load32(uint32_t tmem, int col, float (&v)[32]) {
+  const uint32_t addr = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)col;
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(addr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Development / test entry: D[rows, 256] = Z[rows, 256] x T (see the header comment), one CTA per 128 rows.
+__global__ void __launch_bounds__(TC_M, 1) dft256_tc_kernel(const float* __restrict__ z, int rows, float* __restrict__ d) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  double2* tw = reinterpret_cast<double2*>(smem + TC_OFF_TW);
+  for (int i = tid; i < 256; i += TC_M) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  float* Z = reinterpret_cast<float*>(smem + TC_OFF_Z);
+  const long long row0 = (long long)blockIdx.x * TC_M;
+  for (int m = 0; m < TC_M; ++m) {                       // coalesced: thread = sample pair
+    const long long row = row0 + m;
+    for (int j = tid; j < TC_K; j += TC_M) Z[(j >> 2) * (TC_M * 4) + m * 4 + (j & 3)] = row < rows ? z[row * TC_K + j] : 0.f;
+  }
+  const uint32_t tmem = tc_setup(smem);
+  tc_dft256<TC_M, true>(smem, tmem);
+  const long long row = row0 + tid;
+  for (int c0 = 0; c0 < TC_N; c0 += 32) {
+    float v[32];
+    tc_load32(tmem, c0, v);
+    if (row < rows)
+      for (int i = 0; i < 32; ++i) d[row * TC_N + c0 + i] = v[i];
+  }
+  tc_teardown(tmem);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// PGRAM_WELCH on the tensor cores: scipy.signal.welch(y, fs) with every default (signal_processor.py:260) for windows
+// whose valid count n gives exactly one 256-sample segment (256 <= n < 384: nperseg = 256, noverlap = 128 ->
+// (n - 128) / 128 == 1), which is every steady-state window of the 300-sample configurations.
+//   prologue  each of the 16 warps prepares 8 of the CTA's 128 signals: coalesced window loads held in registers,
+//             ballot compaction of the finite samples, segment mean, Hann, and the fp32 segment written straight into
+//             the K-major operand tile; per-row fs / mean kept in shared memory
+//   contract  tc_dft256<.., false>: 32 tcgen05.mma kind::tf32 (M 128, N 256, K 8) into a 128 x 256 fp32 TMEM accumulator
+//   epilogue  thread = signal (warps 0-3 own the four TMEM lane quarters): one-sided density from the accumulator row,
+//             coarse maximum, candidate list = every bin within WELCH_TC_BAND of it
+//   decide    each warp re-reads its 8 windows and evaluates the candidate bins as float64 dot products, so the reported
+//             peak bin and value are float64 decisions (first-max rule), exactly as the Lomb-Scargle and xcorr kernels do.
+// Signals outside the one-segment range (warm-up) are flagged num_bins = -2 and taken by welch_warp_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int WTC_THREADS = 512;
+constexpr int WTC_MAXW = 383;                          // largest window with at most one segment
+constexpr int WTC_REG = (WTC_MAXW + 31) / 32;           // window samples per lane
+constexpr int WTC_MAXC = 7;                             // candidate bins re-evaluated per window before falling back
+constexpr float WELCH_TC_BAND = 0.10f;                  // relative band below the coarse maximum (single-pass tf32: <= 3.4 % per bin)
+constexpr int WTC_OFF_MEAN = TC_SMEM;                   // double [128]
+constexpr int WTC_OFF_FS = WTC_OFF_MEAN + 128 * 8;      // double [128]
+constexpr int WTC_OFF_N = WTC_OFF_FS + 128 * 8;         // int [128]: 1 = eligible row
+constexpr int WTC_OFF_SW = WTC_OFF_N + 128 * 4;         // double: sum of squared window
+constexpr int WTC_SMEM = WTC_OFF_SW + 16;
+
+__global__ void __launch_bounds__(WTC_THREADS, 1) welch_tc_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+                                                                  int W, long long nsig,
+                                                                  int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
+                                                                  double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double2* tw = reinterpret_cast<double2*>(smem + TC_OFF_TW);
+  float* Z = reinterpret_cast<float*>(smem + TC_OFF_Z);
+  double* s_mean = reinterpret_cast<double*>(smem + WTC_OFF_MEAN);
+  double* s_fs = reinterpret_cast<double*>(smem + WTC_OFF_FS);
+  int* s_ok = reinterpret_cast<int*>(smem + WTC_OFF_N);
+  double* s_sw = reinterpret_cast<double*>(smem + WTC_OFF_SW);
+  for (int i = tid; i < 256; i += WTC_THREADS) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  const uint32_t tmem = tc_setup(smem);                 // CTA barrier inside: the twiddle table is complete after it
+  if (wid == 0) {                                       // sum of the squared periodic Hann window (as welch_warp_kernel)
+    double sw = 0.0;
+    for (int i = lane; i < 256; i += 32) { const double wj = 0.5 - 0.5 * tw[i].x; sw = fma(wj, wj, sw); }
+    sw = warp_sum(sw);
+    if (lane == 0) *s_sw = sw;
+  }
+  const long long sig0 = (long long)blockIdx.x * TC_M;
+  // ---- prologue: warp wid prepares rows wid*8 .. wid*8+7
+  const unsigned lt = (1u << lane) - 1u;
+  for (int q = 0; q < TC_M / (WTC_THREADS / 32); ++q) {
+    const int row = wid * (TC_M / (WTC_THREADS / 32)) + q;
+    const long long sig = sig0 + row;
+    double xr[WTC_REG], yr[WTC_REG];
+    if (sig < nsig) {
+      const double* px = proc_x + sig * W;
+      const double* py = proc_y + sig * W;
+#pragma unroll
+      for (int u = 0; u < WTC_REG; ++u) {
+        const int k = lane + 32 * u;
+        xr[u] = k < W ? px[k] : nan_f64();
+        yr[u] = k < W ? py[k] : nan_f64();
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < WTC_REG; ++u) { xr[u] = nan_f64(); yr[u] = nan_f64(); }
+    }
+    int n = 0, m = 0, ci[WTC_REG];
+    double xfirst = 0.0, xlast = 0.0;
+#pragma unroll
+    for (int u = 0; u < WTC_REG; ++u) {
+      const bool fx = isfinite(xr[u]), fy = isfinite(yr[u]);
+      const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+      if (bx) {
+        const double xf = __shfl_sync(0xffffffffu, xr[u], __ffs(bx) - 1), xl = __shfl_sync(0xffffffffu, xr[u], 31 - __clz(bx));
+        if (m == 0) xfirst = xf;
+        xlast = xl;
+      }
+      ci[u] = fy ? n + __popc(by & lt) : -1;            // compacted index of this sample
+      n += __popc(by); m += __popc(bx);
+    }
+    const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
+    const bool guard = n >= 2 && isfinite(fs);          // signal_processor.py:252
+    const bool ok = guard && n >= 256 && sig < nsig;    // one 256-sample segment (n < 384 by the host's W <= 383)
+    double a = 0.0;
+#pragma unroll
+    for (int u = 0; u < WTC_REG; ++u) if (ci[u] >= 0 && ci[u] < 256) a += yr[u];
+    const double mean = warp_sum(a) / 256.0;
+#pragma unroll
+    for (int u = 0; u < WTC_REG; ++u) {
+      const int j = ci[u];
+      if (ok && j >= 0 && j < 256) Z[(j >> 2) * (TC_M * 4) + row * 4 + (j & 3)] = (float)((yr[u] - mean) * (0.5 - 0.5 * tw[j].x));
+    }
+    if (!ok) {                                          // the tensor core still reads the row: zeros
+      for (int j = lane; j < 256; j += 32) Z[(j >> 2) * (TC_M * 4) + row * 4 + (j & 3)] = 0.f;
+      if (lane == 0 && sig < nsig) {
+        if (guard) num_bins[sig] = -2;                  // short window: welch_warp_kernel takes it
+        else { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+      }
+    }
+    if (lane == 0) { s_mean[row] = mean; s_fs[row] = fs; s_ok[row] = ok ? 1 : 0; }
+  }
+  __syncthreads();
+  // ---- contraction on the tensor cores
+  tc_dft256<WTC_THREADS, false>(smem, tmem);
+  // ---- epilogue: thread = signal row (warps 0..3 <-> TMEM lanes 0..127)
+  if (tid < TC_M) {
+    const int row = tid;
+    const long long sig = sig0 + row;
+    const bool ok = s_ok[row] != 0;
+    const double fs = s_fs[row], mean = s_mean[row];
+    const float scale = ok ? (float)(1.0 / (fs * *s_sw)) : 0.f;
+    // pass 1: fp32 maximum of the one-sided density
+    float pmax = -INFINITY;
+    for (int c = 0; c < 4; ++c) {
+      float re[32], im[32];
+      tc_load32(tmem, 32 * c, re);
+      tc_load32(tmem, 128 + 32 * c, im);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = 32 * c + i;
+        float pw = k == 0 ? re[i] * re[i] * scale : 2.f * (re[i] * re[i] + im[i] * im[i]) * scale;
+        pmax = fmaxf(pmax, pw);
+        if (k == 0) pmax = fmaxf(pmax, im[0] * im[0] * scale);       // column 128 = Re X[128]
+      }
+    }
+    // pass 2: list the candidate bins (within WELCH_TC_BAND of the fp32 maximum) of this row in shared memory (the chunk
+    // buffers are free now).  tcgen05.ld is warp-collective: every lane executes the loads, uniform control flow.
+    const float thr = pmax - WELCH_TC_BAND * fabsf(pmax);
+    int nc = 0;
+    int* clist = reinterpret_cast<int*>(smem + TC_OFF_CHUNK) + row * (WTC_MAXC + 1);
+    for (int c = 0; c < 5; ++c) {
+      float re[32], im[32];
+      unsigned cand = 0;
+      __syncwarp();
+      if (c < 4) {
+        tc_load32(tmem, 32 * c, re);
+        tc_load32(tmem, 128 + 32 * c, im);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = 32 * c + i;
+          const float pw = k == 0 ? re[i] * re[i] * scale : 2.f * (re[i] * re[i] + im[i] * im[i]) * scale;
+          if (pw >= thr) cand |= 1u << i;
+        }
+      } else {
+        tc_load32(tmem, 128, im);                                 // bin 128
+        if (im[0] * im[0] * scale >= thr) cand = 1u;
+      }
+      if (!ok) cand = 0;
+      while (cand) {
+        const int i = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (nc < WTC_MAXC) clist[1 + nc] = c < 4 ? 32 * c + i : 128;
+        ++nc;
+      }
+    }
+    clist[0] = ok ? nc : 0;
+  }
+  __syncthreads();
+  // ---- float64 decision: warp wid re-reads its 8 windows (coalesced), rebuilds the compaction and evaluates the
+  // candidate bins of each as float64 dot products against the table; first-max rule.  A window with more than
+  // WTC_MAXC candidates (flat spectrum) is handed to the float64 kernel (num_bins = -2).
+  for (int q = 0; q < TC_M / (WTC_THREADS / 32); ++q) {
+    const int row = wid * (TC_M / (WTC_THREADS / 32)) + q;
+    const long long sig = sig0 + row;
+    const int* clist = reinterpret_cast<const int*>(smem + TC_OFF_CHUNK) + row * (WTC_MAXC + 1);
+    const int nc = clist[0];
+    if (nc == 0) continue;                                        // not a tensor-core row (warp uniform)
+    if (nc > WTC_MAXC) { if (lane == 0) num_bins[sig] = -2; continue; }
+    const double* py = proc_y + sig * W;
+    double yr[WTC_REG];
+#pragma unroll
+    for (int u = 0; u < WTC_REG; ++u) { const int k = lane + 32 * u; yr[u] = k < W ? py[k] : nan_f64(); }
+    const double mean = s_mean[row], fs = s_fs[row];
+    double zr[WTC_REG]; int ci[WTC_REG];
+    int n = 0;
+#pragma unroll
+    for (int u = 0; u < WTC_REG; ++u) {
+      const bool fy = isfinite(yr[u]);
+      const unsigned by = __ballot_sync(0xffffffffu, fy);
+      const int j = n + __popc(by & lt);
+      ci[u] = fy && j < 256 ? j : -1;
+      zr[u] = ci[u] >= 0 ? (yr[u] - mean) * (0.5 - 0.5 * tw[ci[u]].x) : 0.0;
+      n += __popc(by);
+    }
+    const double scale64 = 1.0 / (fs * *s_sw);
+    double best = -INFINITY; int bi = 0x7fffffff;
+    for (int e = 0; e < nc; ++e) {
+      const int k = clist[1 + e];
+      double sre = 0.0, sim = 0.0;
+#pragma unroll
+      for (int u = 0; u < WTC_REG; ++u) {
+        if (ci[u] >= 0) { const double2 t = tw[(ci[u] * k) & 255]; sre = fma(zr[u], t.x, sre); sim = fma(zr[u], t.y, sim); }
+      }
+      sre = warp_sum(sre); sim = warp_sum(sim);
+      double pw = (sre * sre + sim * sim) * scale64;
+      if (k >= 1 && k < 128) pw *= 2.0;
+      if (isfinite(pw) && (pw > best || (pw == best && k < bi))) { best = pw; bi = k; }
+    }
+    if (lane == 0) {
+      const double fval = 1.0 / (256.0 * (1.0 / fs));             // rfftfreq(256, d=1/fs)[k] = k * (1/(256*d))
+      num_bins[sig] = 129;
+      if (bi != 0x7fffffff) { peak_idx[sig] = bi; peak_freq[sig] = (double)bi * fval; peak_mag[sig] = best; }
+      else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    }
+  }
+  tc_teardown(tmem);
+}
+
+int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
+                    double* peak_freq, double* peak_mag, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(welch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTC_SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  welch_tc_kernel<<<(unsigned)((nsig + TC_M - 1) / TC_M), WTC_THREADS, WTC_SMEM, st>>>(proc_x, proc_y, W, nsig, num_bins, peak_idx,
+                                                                                      peak_freq, peak_mag);
+  return check_launch("welch_tc_kernel");
+}
+
+}  // namespace bpv
+
+extern "C" int bpv_dft256_tc(const float* z, int32_t rows, float* d, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(z && d && rows >= 0, BPV_E_INVALID, "bpv_dft256_tc: bad arguments");
+  if (rows == 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dft256_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  dft256_tc_kernel<<<(rows + TC_M - 1) / TC_M, TC_M, TC_SMEM, (cudaStream_t)stream>>>(z, rows, d);
+  return check_launch("bpv_dft256_tc");
+}

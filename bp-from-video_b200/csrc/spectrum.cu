@@ -12,9 +12,13 @@
 //                           (scipy/signal/_spectral_py.py:284-349).  Peak pass: candidates within
 //                           LS_DELTA of the fp32 maximum are re-evaluated in float64 with scipy's own
 //                           two-pass formulation so that the winning bin is decided in float64.
+#include <stdlib.h>
 #include "filters.cuh"
 
 namespace bpv {
+
+int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
+                    double* peak_freq, double* peak_mag, cudaStream_t st);
 
 constexpr float LS_DELTA = 1.0e-4f;     // candidate band below the fp32 maximum (PSD is in [0, 1])
 constexpr int LS_SMALL_N = 24;          // below this every bin is evaluated in float64
@@ -287,16 +291,19 @@ __device__ __forceinline__ void welch_fft_pass(double2* __restrict__ fz, const d
 __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const double* __restrict__ proc_x,
                                                                     const double* __restrict__ proc_y,
                                                                     const bpv_window_params p, int max_bins, long long nsig,
-                                                                    float* __restrict__ spec_f, float* __restrict__ spec_mag,
+                                                                    int only_flagged, float* __restrict__ spec_f, float* __restrict__ spec_mag,
                                                                     int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
                                                                     double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
   extern __shared__ __align__(16) double sm[];
   const int W = p.window, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double2* tw = reinterpret_cast<double2*>(sm);                 // [256] exp(+2*pi*i*k/256) as (cos, sin)
+  const long long sig = (long long)blockIdx.x * WELCH_WPB + wid;
+  // only_flagged: second pass behind welch_tc_kernel, which marks the windows it does not take with num_bins = -2
+  const bool mine = sig < nsig && (!only_flagged || num_bins[sig] == -2);
+  if (!__syncthreads_or(mine)) return;
   for (int i = tid; i < 256; i += blockDim.x) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
   __syncthreads();
-  const long long sig = (long long)blockIdx.x * WELCH_WPB + wid;
-  if (sig >= nsig) return;
+  if (!mine) return;
   double* ys = sm + 512 + (size_t)wid * welch_warp_doubles(W);
   double* buf = ys + W;            // FFT: 256 complex (re, im interleaved); direct DFT: cos[256] | sin[256]
   double* mags = buf + 576;
@@ -701,8 +708,19 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
         cudaError_t e = cudaFuncSetAttribute(welch_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
       }
+      // BPV_WELCH_TC=1: peak-only calls on one-segment windows run the 256-point DFT on the tensor cores (dft_tc.cu:
+      // tcgen05 candidates + float64 decision, same peaks bit for bit); the warp kernel then only takes the windows that
+      // kernel flagged (warm-up, n < 256).  Opt-in: measured 82 + 8 us against 76 us for the float64 FFT kernel per
+      // 16 384 windows — the contraction is 19 us of that, the per-window front end (gather, compaction, detrend, window)
+      // and the float64 decision dominate both kernels (profiles/README.md).
+      int only_flagged = 0;
+      const char* tc_env = getenv("BPV_WELCH_TC");
+      if (!spec_mag && W >= 256 && W <= 383 && tc_env && tc_env[0] == '1') {
+        if (int rc = launch_welch_tc(proc_x, proc_y, W, nsig, num_bins, peak_idx, peak_freq, peak_mag, st)) return rc;
+        only_flagged = 1;
+      }
       welch_warp_kernel<<<(unsigned)((nsig + WELCH_WPB - 1) / WELCH_WPB), 32 * WELCH_WPB, smw, st>>>(
-          proc_x, proc_y, *p, max_bins, nsig, spec_f, spec_mag, num_bins, peak_idx, peak_freq, peak_mag);
+          proc_x, proc_y, *p, max_bins, nsig, only_flagged, spec_f, spec_mag, num_bins, peak_idx, peak_freq, peak_mag);
       return check_launch("welch_warp_kernel");
     }
     const size_t smem = (size_t)(4 * W + W / 2 + 2 + 256) * sizeof(double);

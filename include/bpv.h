@@ -207,6 +207,14 @@ int bpv_firls_design(const double* fs, int32_t n, const bpv_window_params* p, do
 int bpv_pack_records(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx, const int32_t* lag_idx,
                      int64_t J, int32_t R, int32_t P, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core building block of the spectra: 256-point DFT of `rows` real segments as one dense contraction on the
+ * 5th-generation tensor cores (tcgen05.mma kind::tf32 with hi/lo split operands, fp32 accumulators in TMEM) — the
+ * transform inside scipy.signal.welch(y, fs) as the reference calls it (signal_processor.py:260, nperseg = 256).
+ * z float32 [rows, 256]; d float32 [rows, 256]: d[:, 0..128] = Re X[0..128], d[:, 129..255] = -Im X[1..127].
+ */
+int bpv_dft256_tc(const float* z, int32_t rows, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
