@@ -363,7 +363,9 @@ def run_gpu(args, wl):
                              'achieved': kernels[dom]['gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': kernels[dom]['frac_hbm'],
                              'note': 'dominant kernel family of the step by CUDA-event time'},
         'kernels': kernels,
-        'gpu_launches': eng.launches_per_step * args.steps,
+        # libbpv kernels launched inside the timed region: the engine's step (roi, ring push, firls design, preprocess,
+        # spectrum, xcorr) + pack_records for the result record
+        'gpu_launches': (eng.launches_per_step + 1) * args.steps,
         'clocks': clk,
         'e2e': {'value': world * S * Te / e2e_s, 'unit': UNIT,
                 'h2d_bytes_per_step': int(e2e_roi_bytes + host_boxes.numel() * 4 + host_ts.numel() * 8),
