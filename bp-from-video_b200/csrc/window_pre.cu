@@ -110,22 +110,24 @@ __device__ void detrend_const(Warp& w) {  // scipy.signal.detrend(type='constant
 
 __device__ void detrend_linear(Warp& w) {
   // scipy.signal.detrend(type='linear'): least squares of y on [i/N, 1], i = 1..N (sample index, not
-  // time; scipy/signal/_signaltools.py:4307-4314), solved in centred closed form.
-  const double N = (double)w.n;
+  // time; scipy/signal/_signaltools.py:4307-4314), solved in centred closed form: with u_i = i/N,
+  // du_i = u_i - mean(u), sum(du^2) = (N^2 - 1) / (12 N) exactly, slope = sum(du (y - ybar)) / sum(du^2).
+  // Two reductions, no per-element division (u_i = i * (1/N)).
+  const double N = (double)w.n, invN = 1.0 / N;
   double s = 0.0;
   for (int i = w.lane; i < w.n; i += 32) s += w.yv[i];
-  const double ybar = warp_sum(s) / N;
-  const double ubar = (N + 1.0) / (2.0 * N);
-  double sxy = 0.0, sxx = 0.0;
+  const double ybar = warp_sum(s) * invN;
+  const double ubar = (N + 1.0) * 0.5 * invN;
+  double sxy = 0.0;
   for (int i = w.lane; i < w.n; i += 32) {
-    const double du = (double)(i + 1) / N - ubar;
-    sxy += du * (w.yv[i] - ybar);
-    sxx += du * du;
+    const double du = fma((double)(i + 1), invN, -ubar);
+    sxy = fma(du, w.yv[i] - ybar, sxy);
   }
-  sxy = warp_sum(sxy); sxx = warp_sum(sxx);
+  sxy = warp_sum(sxy);
+  const double sxx = (N * N - 1.0) / (12.0 * N);
   const double slope = sxx > 0.0 ? sxy / sxx : 0.0;
   for (int i = w.lane; i < w.n; i += 32) {
-    const double du = (double)(i + 1) / N - ubar;
+    const double du = fma((double)(i + 1), invN, -ubar);
     w.yv[i] = (w.yv[i] - ybar) - slope * du;
   }
   __syncwarp();

@@ -176,6 +176,165 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-pair version (default): the CTA-per-pair kernel above spends most of its time in __syncthreads between short
+// phases (staging, single-warp compaction, five block reductions, peak search: the tile phase is 18 % of its samples).
+// Here one warp owns a (job, pair): every phase is warp-local (ballot compaction, shuffle reductions), each lane owns ONE
+// tile of XW_RT = 20 consecutive lags so a 300-sample window (599 lags) is a single round of the register-tiled sliding
+// dot product (2 LDS per 20 FFMA), and the float64 re-evaluation of the candidate lags is a warp-cooperative dot product.
+// smem per warp: doubles a64[W] | b64[W]; u16 pos[W]; floats cv[2W] | c[K] | XT[RT * LD]
+// ---------------------------------------------------------------------------------------------
+constexpr int XW_RT = 20;
+struct XwLayout { int b64, pos, cv, c, xt, total, K, LD; };
+__host__ __device__ inline XwLayout xw_layout(int W) {
+  XwLayout L;
+  L.K = (W + XW_RT - 1) / XW_RT * XW_RT;
+  L.LD = (L.K + 2 * W + XW_RT) / XW_RT + 2;
+  int o = W * 8;
+  L.b64 = o; o += W * 8;
+  L.pos = o; o += (W * 2 + 15) / 16 * 16;
+  L.cv = o; o += 2 * W * 4;
+  L.c = o; o += L.K * 4;
+  L.xt = o; o += XW_RT * L.LD * 4;
+  L.total = (o + 15) / 16 * 16;
+  return L;
+}
+
+__global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+                                                         const bpv_window_params p, const XwLayout Lw, long long npairs,
+                                                         float* __restrict__ corr_lag, float* __restrict__ corr_val,
+                                                         int32_t* __restrict__ num_lags, int32_t* __restrict__ lag_idx,
+                                                         double* __restrict__ lag_sec, double* __restrict__ lag_corr) {
+  extern __shared__ __align__(16) unsigned char xsm[];
+  constexpr int RT = XW_RT;
+  const int W = p.window, R = p.R, P = R * (R - 1) / 2, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long jp = (long long)blockIdx.x * (blockDim.x >> 5) + wid;   // job * P + pair
+  if (jp >= npairs) return;
+  const long long job = jp / P;
+  int pr = (int)(jp % P), ra = 0, rb = 1;
+  for (ra = 0; ra < R - 1; ++ra) {             // itertools.combinations order
+    const int cnt = R - 1 - ra;
+    if (pr < cnt) { rb = ra + 1 + pr; break; }
+    pr -= cnt;
+  }
+  const double* xa_g = proc_x + (job * R + ra) * W;
+  const double* ya_g = proc_y + (job * R + ra) * W;
+  const double* yb_g = proc_y + (job * R + rb) * W;
+  unsigned char* sm = xsm + (size_t)wid * Lw.total;
+  double* a64 = reinterpret_cast<double*>(sm);
+  double* b64 = reinterpret_cast<double*>(sm + Lw.b64);
+  unsigned short* pos = reinterpret_cast<unsigned short*>(sm + Lw.pos);
+  float* cv = reinterpret_cast<float*>(sm + Lw.cv);
+  float* c = reinterpret_cast<float*>(sm + Lw.c);
+  float* XT = reinterpret_cast<float*>(sm + Lw.xt);
+  const int Kw = Lw.K, LD = Lw.LD;
+  // stage both windows (independent coalesced loads), clear the fp32 operand buffers
+  for (int k = lane; k < W; k += 32) { a64[k] = ya_g[k]; b64[k] = yb_g[k]; }
+  for (int i = lane; i < Kw; i += 32) c[i] = 0.f;
+  for (int i = lane; i < RT * LD; i += 32) XT[i] = 0.f;
+  __syncwarp();
+  // jointly valid samples (valid = a.w & b.w), compacted in place
+  int n = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int k0 = 0; k0 < W; k0 += 32) {
+    const int k = k0 + lane;
+    double va = nan_f64(), vb = nan_f64();
+    if (k < W) { va = a64[k]; vb = b64[k]; }
+    const bool ok = isfinite(va) && isfinite(vb);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (ok) { const int i = n + __popc(bal & lt); a64[i] = va; b64[i] = vb; pos[i] = (unsigned short)k; }
+    __syncwarp();
+    n += __popc(bal);
+  }
+  if (n < 2) {                                  // guard signal_processor.py:284 -> empty
+    if (lane == 0) { num_lags[jp] = 0; lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
+    return;
+  }
+  const int K = (n + RT - 1) / RT * RT;
+  double daa = 0, dbb = 0, dab = 0, amax = 0, bmax = 0;
+  for (int i = lane; i < n; i += 32) {
+    const double va = a64[i], vb = b64[i];
+    daa = fma(va, va, daa); dbb = fma(vb, vb, dbb); dab = fma(va, vb, dab);
+    amax = fmax(amax, fabs(va)); bmax = fmax(bmax, fabs(vb));
+  }
+  daa = warp_sum(daa); dbb = warp_sum(dbb); dab = warp_sum(dab);
+  for (int o = 16; o > 0; o >>= 1) { amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o)); bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); }
+  const double den = fmax(fmax(daa, dbb), dab);
+  // fp32 operands scaled to O(1) so tiny band-passed signals neither underflow nor lose bits
+  const double sa = amax > 0 ? 1.0 / amax : 1.0, sb = bmax > 0 ? 1.0 / bmax : 1.0;
+  for (int i = lane; i < n; i += 32) {
+    XT[xt_index<RT>(i + n - 1 + K, LD)] = (float)(a64[i] * sa);     // storage index = u + K
+    c[n - 1 - i] = (float)(b64[i] * sb);
+  }
+  __syncwarp();
+  const float unscale = (float)(1.0 / (sa * sb * den));
+  const int L = 2 * n - 1;
+  const long long ob = jp * (2LL * W - 1);
+  const double x_last = xa_g[pos[n - 1]];
+  // COARSE pass in fp32:  corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1
+  const int jbase = (n - 1 + K) / RT * RT;      // storage index of the tile that holds li = 0
+  for (int J0 = jbase + RT * lane; J0 <= (L - 1) + (n - 1) + K; J0 += RT * 32) {
+    float acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.f;
+    const int u0 = J0 - K;                       // logical index of the tile's first output operand
+    int kb_lo = (u0 - (2 * n - 2)) / RT; if (kb_lo < 0) kb_lo = 0;
+    int kb_hi = (u0 + RT - 1 - (n - 1)) / RT + 1; if (kb_hi < 0) kb_hi = 0;
+    corr_tile<RT, float>(acc, c, K, XT, LD, J0, kb_lo, kb_hi);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int li = u0 + r - (n - 1);
+      if (li >= 0 && li < L) {
+        const float cc = acc[r] * unscale;
+        cv[li] = cc;
+        if (corr_val) {
+          const int k = li - (n - 1), ak = k < 0 ? -k : k;
+          const double lag = (x_last - xa_g[pos[n - 1 - ak]]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
+          corr_lag[ob + li] = (float)lag;
+          corr_val[ob + li] = cc;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // PEAK in float64: every lag whose coarse value is within XC_DELTA of the coarse maximum is re-evaluated as a
+  // float64 dot product (warp cooperative); the first maximum among those decides (Signal.get_peak after the range reset).
+  float cmax = -INFINITY; int cnt = 0;
+  for (int li = lane; li < L; li += 32) { const float v = cv[li]; if (isfinite(v)) { ++cnt; cmax = fmaxf(cmax, v); } }
+  for (int o = 16; o > 0; o >>= 1) { cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  double bv = -INFINITY; int bi = 0x7fffffff;
+  for (int li0 = 0; li0 < L; li0 += 32) {
+    const int li = li0 + lane;
+    bool cand = false;
+    if (li < L) { const float v = cv[li]; cand = cnt >= 2 ? (isfinite(v) && v >= cmax - XC_DELTA) : true; }
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      const int lc = li0 + __ffs(m) - 1;
+      m &= m - 1;
+      const int k = lc - (n - 1);
+      const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
+      double acc = 0.0;
+      for (int l = l0 + lane; l < l1; l += 32) acc = fma(a64[l + k], b64[l], acc);
+      acc = warp_sum(acc);
+      const double cc = acc / den;
+      if (isfinite(cc) && (cc > bv || (cc == bv && lc < bi))) { bv = cc; bi = lc; }
+    }
+  }
+  if (lane == 0) {
+    // finite-lag count in float64 terms: den == 0 or non-finite makes every lag non-finite (NaN / inf)
+    const bool any = isfinite(den) && den != 0.0 && bi != 0x7fffffff;
+    num_lags[jp] = L;
+    if (any && L >= 2) {
+      const int k = bi - (n - 1), ak = k < 0 ? -k : k;
+      lag_idx[jp] = bi;
+      lag_sec[jp] = (x_last - xa_g[pos[n - 1 - ak]]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
+      lag_corr[jp] = bv;
+    } else { lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
+  }
+}
+
 }  // namespace bpv
 
 extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, const bpv_window_params* p,
@@ -188,6 +347,23 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   if (P == 0) return 0;
   const long long n = (long long)p->S * p->jobs_per_stream * P;
   BPV_REQUIRE(W > 0 && n > 0, BPV_E_INVALID, "bpv_window_xcorr: bad sizes");
+  {  // warp-per-pair kernel whenever one pair fits the shared memory of a CTA
+    const XwLayout Lw = xw_layout(W);
+    int wpb = (200 * 1024) / Lw.total;
+    if (wpb > 4) wpb = 4;
+    if (wpb >= 1) {
+      const size_t smw = (size_t)wpb * Lw.total;
+      static size_t configured = 0;
+      if (smw > 48 * 1024 && smw > configured) {
+        cudaError_t e = cudaFuncSetAttribute(xcorr_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = smw;
+      }
+      xcorr_warp_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smw, (cudaStream_t)stream>>>(
+          proc_x, proc_y, *p, Lw, n, corr_lag, corr_val, num_lags, lag_idx, lag_sec, lag_corr);
+      return check_launch("bpv_window_xcorr");
+    }
+  }
   const int Kw = (W + 7) / 8 * 8;
   const size_t smem = (size_t)(3 * W) * sizeof(double) + (size_t)(2 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(float);
   BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_xcorr: window %d too large for shared memory", W);
