@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   const double x_last = xa_g[pos[n - 1]];
   // COARSE pass in fp32:  corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1
   const int jbase = (n - 1 + K) / RT * RT;      // storage index of the tile that holds li = 0
+  float cmax = -INFINITY; int cnt = 0;          // coarse maximum / finite count, gathered while the tiles are written
   for (int J0 = jbase + RT * lane; J0 <= (L - 1) + (n - 1) + K; J0 += RT * 32) {
     float acc[RT];
 #pragma unroll
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
       if (li >= 0 && li < L) {
         const float cc = acc[r] * unscale;
         cv[li] = cc;
+        if (isfinite(cc)) { ++cnt; cmax = fmaxf(cmax, cc); }
         if (corr_val) {
           const int k = li - (n - 1), ak = k < 0 ? -k : k;
           const double lag = (x_last - xa_g[pos[n - 1 - ak]]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
@@ -301,25 +303,33 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   __syncwarp();
   // PEAK in float64: every lag whose coarse value is within XC_DELTA of the coarse maximum is re-evaluated as a
   // float64 dot product (warp cooperative); the first maximum among those decides (Signal.get_peak after the range reset).
-  float cmax = -INFINITY; int cnt = 0;
-  for (int li = lane; li < L; li += 32) { const float v = cv[li]; if (isfinite(v)) { ++cnt; cmax = fmaxf(cmax, v); } }
   for (int o = 16; o > 0; o >>= 1) { cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
   double bv = -INFINITY; int bi = 0x7fffffff;
-  for (int li0 = 0; li0 < L; li0 += 32) {
-    const int li = li0 + lane;
-    bool cand = false;
-    if (li < L) { const float v = cv[li]; cand = cnt >= 2 ? (isfinite(v) && v >= cmax - XC_DELTA) : true; }
-    unsigned m = __ballot_sync(0xffffffffu, cand);
-    while (m) {
-      const int lc = li0 + __ffs(m) - 1;
+  const float thr = cmax - XC_DELTA;
+  for (int li0 = 0; li0 < L; li0 += 128) {       // 4 consecutive lags per lane per step
+    const int lb = li0 + 4 * lane;
+    unsigned flags = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int li = lb + e;
+      if (li < L) { const float v = cv[li]; if (cnt >= 2 ? (isfinite(v) && v >= thr) : true) flags |= 1u << e; }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, flags != 0);
+    while (m) {                                  // lanes in increasing lag order, lags of a lane in increasing order
+      const int src = __ffs(m) - 1;
       m &= m - 1;
-      const int k = lc - (n - 1);
-      const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
-      double acc = 0.0;
-      for (int l = l0 + lane; l < l1; l += 32) acc = fma(a64[l + k], b64[l], acc);
-      acc = warp_sum(acc);
-      const double cc = acc / den;
-      if (isfinite(cc) && (cc > bv || (cc == bv && lc < bi))) { bv = cc; bi = lc; }
+      unsigned f = __shfl_sync(0xffffffffu, flags, src);
+      while (f) {
+        const int lc = li0 + 4 * src + __ffs(f) - 1;
+        f &= f - 1;
+        const int k = lc - (n - 1);
+        const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
+        double acc = 0.0;
+        for (int l = l0 + lane; l < l1; l += 32) acc = fma(a64[l + k], b64[l], acc);
+        acc = warp_sum(acc);
+        const double cc = acc / den;
+        if (isfinite(cc) && (cc > bv || (cc == bv && lc < bi))) { bv = cc; bi = lc; }
+      }
     }
   }
   if (lane == 0) {

@@ -134,3 +134,18 @@ def test_videoreader_view_crop_flip_exact(flip, shape):
                 assert h.same(val[f, r], ref), (f, r, b, val[f, r], ref)
                 sb, sg, sr, n = orc.roi_sums(np.ascontiguousarray(view), b)
                 assert tuple(int(v) for v in sums[f, r]) == (sb, sg, sr, n)
+
+
+@pytest.mark.parametrize('hint', [0, 4000, 400000])
+def test_staged_kernel_wide_tall_and_full_frame_boxes(hint):
+    """The shared-memory staged F1 kernel (row stride % 16 == 0): ROI rows longer than a CTA's vector columns (> 2 KB),
+    ROIs taller than one cp.async batch, 1-pixel-wide columns, the whole frame, unaligned starts."""
+    H, W, N = 260, 1920, 3
+    rng = np.random.default_rng(77 + hint)
+    frames = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    boxes = np.array([[(0, 0, W, H), (0, 100, 1920, 110), (5, 0, 6, H), (1, 3, 1919, 259)],
+                      [(683, 7, 1367, 255), (1279, 0, 1920, H), (-700, -200, -1, -1), (333, 17, 334, 18)],
+                      [(0, 0, 1, 1), (W - 1, H - 1, W, H), (17, 0, 1900, 1), (960, 0, 961, H)]], dtype=np.int32)
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        val, sums = _run(frames, boxes, mode, hint)
+        _check(frames, boxes, mode, val, sums)
