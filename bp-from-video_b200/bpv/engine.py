@@ -105,16 +105,23 @@ class BatchedSignalProcessor:
     def _params(self, head0: int, head_step: int, jobs: int) -> _cabi.WindowParams:
         return ops.make_params(self.S, self.R, self.cap, self.W, head0, head_step, jobs, self.methods, self.transform, **self.kw)
 
-    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None) -> StepResult:
+    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None, nv12_size=None) -> StepResult:
         """frames uint8 [S, T, H, W, 3] (HBM, or pinned host memory: the ROI kernel then reads the ROI rows
         straight over PCIe), boxes int32 [S, T, R, 4] (device), timestamps float64 [S, T] (device).
         view = (view_w, view_h, left, flip_horizontally): the boxes are expressed in the reference VideoReader's
         cropped / mirrored view of the decoded frames (video_reader.py:97-103) and are mapped back onto `frames`
-        on the device; nothing is copied."""
+        on the device; nothing is copied.
+        nv12_size = (H, W): frames are NV12 decoder buffers uint8 [S, T, 3H/2, pitch]; the ROI is sampled from the planes
+        with OpenCV's integer BT.601 conversion, i.e. as from the BGR frame cv2.VideoCapture would have produced."""
         S, T = frames.shape[:2]
         assert S == self.S and 1 <= T <= self.Tmax and boxes.shape == (S, T, self.R, 4)
         if view is not None:
             boxes = ops.view_boxes(boxes.contiguous(), *view)
+        if nv12_size is not None:
+            H, W = nv12_size
+            val, _ = ops.roi_sample_nv12(frames.view(S * T, *frames.shape[2:]), H, W, boxes.reshape(S * T, self.R, 4).contiguous(),
+                                         self.color_channel)
+            return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
         samples = self._samples[:, :T]
         if T != self.Tmax:
             samples = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)

@@ -231,3 +231,19 @@ def dft256_tc(z: torch.Tensor) -> torch.Tensor:
     d = torch.empty_like(z)
     check(lib().bpv_dft256_tc(ptr(z), z.shape[0], ptr(d), stream_handle()), 'bpv_dft256_tc')
     return d
+
+
+def roi_sample_nv12(frames: torch.Tensor, H: int, W: int, boxes: torch.Tensor, mode: int, *, want_sums: bool = False):
+    """F1 on NV12 frames: frames uint8 [N, 3H/2, pitch] (Y plane rows then interleaved UV rows; CUDA or pinned host
+    memory), boxes int32 [N, R, 4] in pixel coordinates of the H x W image.  Returns (value f64 [N,R], sums | None): the
+    sums of the BGR frame cv2.cvtColor(nv12, COLOR_YUV2BGR_NV12) would give."""
+    assert frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[1] == H * 3 // 2 and frames.stride(2) == 1
+    assert _dev_accessible(frames) and boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous()
+    N, R = boxes.shape[0], boxes.shape[1]
+    assert frames.shape[0] == N
+    out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
+    sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
+    fstride = frames.stride(0) if N > 1 else frames.shape[1] * frames.stride(1)
+    check(lib().bpv_roi_sample_nv12(ptr(frames), fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode), ptr(sums),
+                                    ptr(out_value), stream_handle()), 'bpv_roi_sample_nv12')
+    return out_value, sums

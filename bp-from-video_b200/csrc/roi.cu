@@ -530,7 +530,111 @@ static bool launch_variant(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   return false;
 }
 
+// ---------------------------------------------------------------------------------------------
+// F1 on NV12 frames: decoders (NVDEC, V4L2) hand out NV12 — a full-resolution Y plane followed
+// by a half-resolution interleaved UV plane — and the reference only ever sees the BGR frame cv2.VideoCapture makes
+// of it (video_reader.py:93).  Sampling the ROI straight from the NV12 planes reads 1.5 bytes per pixel instead of 3
+// and never materialises the BGR frame; the per-pixel conversion is OpenCV's integer BT.601 (cvtColor
+// COLOR_YUV2BGR_NV12, imgproc/src/color_yuv.simd.hpp: 20-bit fixed point, limited-range Y), so the sums are those of
+// the BGR frame the reference would have sampled, bit for bit.
+// One 128-thread CTA per ROI, threads laid out rows x 16-pixel vector columns as in the BGR kernels.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sat_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+template <bool WANT_SUMS>
+__global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch,
+                                                       int H, int W, int R, int mode, long long num_rois,
+                                                       const int32_t* __restrict__ boxes,
+                                                       unsigned long long* __restrict__ out_sums, double* __restrict__ out_value) {
+  constexpr int THREADS = 128, WARPS = THREADS / 32;
+  const int gt = threadIdx.x;
+  const long long roi = blockIdx.x;
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  bool has_box = false;
+  const int4 b = __ldg(reinterpret_cast<const int4*>(boxes) + roi);
+  has_box = b.x != BPV_NO_BOX;
+  if (has_box) { py_slice(b.x, b.z, W, xs, xe); py_slice(b.y, b.w, H, ys, ye); }
+  const uint8_t* yp = frames + (roi / R) * frame_stride;
+  const uint8_t* uvp = yp + (long long)H * pitch;
+  const int nrows = ye - ys, ncols = xe - xs;
+  uint32_t sB = 0, sG = 0, sR = 0;
+  if (nrows > 0 && ncols > 0) {
+    const int x0 = xs & ~15;                                  // 16-pixel aligned vector columns (x0 even: UV pairs intact)
+    const int vpr = (xe - x0 + 15) >> 4;
+    int rps, r0, v0;
+    if (vpr >= THREADS) { rps = 1; r0 = 0; v0 = gt; }
+    else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
+    for (int v = v0; v < vpr; v += THREADS) {
+      const int xv = x0 + 16 * v;
+      for (int r = r0; r < nrows; r += rps) {
+        const int y = ys + r;
+        const uint8_t* yrow = yp + (long long)y * pitch + xv;
+        const uint8_t* uvrow = uvp + (long long)(y >> 1) * pitch + xv;
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+          const int x = xv + 2 * pr;
+          if (x + 1 < xs || x >= xe) continue;
+          const int uu = (int)uvrow[2 * pr] - 128, vv = (int)uvrow[2 * pr + 1] - 128;
+          const int ruv = (1 << 19) + 1673527 * vv;
+          const int guv = (1 << 19) - 852492 * vv - 409993 * uu;
+          const int buv = (1 << 19) + 2116026 * uu;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int xx = x + e;
+            if (xx < xs || xx >= xe) continue;
+            const int yy = (int)yrow[2 * pr + e] - 16;
+            const int yc = (yy > 0 ? yy : 0) * 1220542;
+            sR += (uint32_t)sat_u8((yc + ruv) >> 20);
+            sG += (uint32_t)sat_u8((yc + guv) >> 20);
+            sB += (uint32_t)sat_u8((yc + buv) >> 20);
+          }
+        }
+      }
+    }
+  }
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(ncols > 0 ? ncols : 0);
+  unsigned long long tB = warp_sum_u64(sB), tG = warp_sum_u64(sG), tR = warp_sum_u64(sR);
+  __shared__ unsigned long long part[WARPS][3];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { part[wid][0] = tB; part[wid][1] = tG; part[wid][2] = tR; }
+  __syncthreads();
+  if (gt == 0) {
+    tB = tG = tR = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { tB += part[w][0]; tG += part[w][1]; tR += part[w][2]; }
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tR; o.w = N;
+      *reinterpret_cast<ulonglong4*>(out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(2 * (long long)tG - (long long)tB - (long long)tR + 2 * (long long)N) / (double)(4 * N);
+    out_value[roi] = val;
+  }
+}
+
 }  // namespace bpv
+
+extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_bytes, int64_t pitch_bytes,
+                                   int32_t H, int32_t W, int64_t num_frames, const int32_t* boxes, int32_t R, int32_t mode,
+                                   uint64_t* out_sums, double* out_value, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(frames && boxes && out_value, BPV_E_INVALID, "bpv_roi_sample_nv12: NULL pointer");
+  BPV_REQUIRE(H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0 && R > 0 && num_frames >= 0, BPV_E_INVALID,
+              "bpv_roi_sample_nv12: H and W must be positive and even");
+  BPV_REQUIRE(pitch_bytes >= W && frame_stride_bytes >= pitch_bytes * (H + H / 2), BPV_E_INVALID,
+              "bpv_roi_sample_nv12: pitch < W or frame stride < pitch * 3H/2");
+  BPV_REQUIRE(mode == BPV_GREEN || mode == BPV_CHROM_GREEN, BPV_E_UNSUPPORTED,
+              "bpv_roi_sample_nv12: unknown color channel %d (NotImplementedError, signal_processor.py:185)", mode);
+  if (num_frames == 0) return 0;
+  const long long n = num_frames * R;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_sums) roi_nv12_kernel<true><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes,
+                                                                   (unsigned long long*)out_sums, out_value);
+  else roi_nv12_kernel<false><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, nullptr, out_value);
+  return check_launch("bpv_roi_sample_nv12");
+}
 
 extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
                                  int64_t frame_stride_bytes, int64_t row_stride_bytes,

@@ -86,6 +86,15 @@ int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
                       uint64_t* out_sums, double* out_value,
                       int64_t roi_pixels_hint, void* stream);
 
+/* F1 on NV12 frames (decoder output: Y plane [H, pitch] followed by the interleaved half-resolution UV plane
+ * [H/2, pitch]; frame f at frames + f*frame_stride_bytes).  The reference only ever sees the BGR frame
+ * cv2.VideoCapture makes of such a buffer (video_reader.py:93); this samples the ROI from the planes directly with
+ * OpenCV's integer BT.601 conversion (cvtColor COLOR_YUV2BGR_NV12), so sums and values equal those of that BGR
+ * frame bit for bit.  boxes / mode / out_sums / out_value as bpv_roi_sample_u8.  H and W even. */
+int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_bytes, int64_t pitch_bytes,
+                        int32_t H, int32_t W, int64_t num_frames, const int32_t* boxes, int32_t R, int32_t mode,
+                        uint64_t* out_sums, double* out_value, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ROI geometry for batched landmark tensors — replaces SignalProcessor.calc_rois and the ROI smoothing
  *     sg_roi.add_samples + get_means(as_int=True) (signal_processor.py:133-155, 304-305; signal_data.py:60-63).

@@ -98,6 +98,24 @@ def roi_sums(frame, box):
     return int(s[0]), int(s[1]), int(s[2]), int(n)
 
 
+def nv12_to_bgr(nv12, H, W):
+    """uint8 [3H/2, W] NV12 -> uint8 [H, W, 3] BGR exactly as OpenCV's cvtColor(COLOR_YUV2BGR_NV12) — the conversion a
+    cv2.VideoCapture applies to decoder output before the reference sees the frame (video_reader.py:93).  Integer BT.601,
+    20-bit fixed point (opencv/modules/imgproc/src/color_yuv.simd.hpp: ITUR_BT_601_C*; uvToRGBuv / yRGBuvToRGBA).
+    Pinned against cv2 in tests/test_oracle_golden.py."""
+    nv12 = np.asarray(nv12)
+    Y = nv12[:H, :W].astype(np.int64)
+    UV = nv12[H:H + H // 2, :W].reshape(H // 2, W // 2, 2).astype(np.int64)
+    U = np.repeat(np.repeat(UV[..., 0], 2, axis=0), 2, axis=1) - 128
+    V = np.repeat(np.repeat(UV[..., 1], 2, axis=0), 2, axis=1) - 128
+    y = np.maximum(0, Y - 16) * 1220542
+    half = 1 << 19
+    r = (y + half + 1673527 * V) >> 20
+    g = (y + half - 852492 * V - 409993 * U) >> 20
+    b = (y + half + 2116026 * U) >> 20
+    return np.clip(np.stack([b, g, r], axis=-1), 0, 255).astype(np.uint8)
+
+
 def roi_sample(frame, sroi, channel=GREEN):
     """signal_processor.py:176-189, called exactly as the reference does (numpy slicing +
     np.mean in float64).  `sroi` is the 6-tuple Location; NaN anywhere -> NaN."""

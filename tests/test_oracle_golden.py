@@ -47,3 +47,17 @@ def test_roi_sample_matches_reference():
             assert h.same(orc.roi_sample(frame, sroi, c), ref)
             assert h.same(orc.value_from_sums(sB, sG, sR, n, c), ref), (k, box, c)
     assert 0 < n_empty < len(g['boxes'])
+
+
+def test_nv12_conversion_matches_opencv():
+    """The oracle's NV12 -> BGR restatement against OpenCV itself (cv2 is the decoder-side converter the reference sits
+    behind, video_reader.py:93): bit-exact on random planes, extreme values and odd plane sizes."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(12)
+    for H, W in [(2, 2), (6, 10), (48, 64), (270, 480)]:
+        nv = rng.integers(0, 256, (H * 3 // 2, W), dtype=np.uint8)
+        assert np.array_equal(orc.nv12_to_bgr(nv, H, W), cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12)), (H, W)
+    for fill in (0, 16, 128, 235, 255):
+        nv = np.full((12, 8), fill, np.uint8)
+        nv[8:] = rng.choice([0, 255, 128], size=(4, 8)).astype(np.uint8)
+        assert np.array_equal(orc.nv12_to_bgr(nv, 8, 8), cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12)), fill

@@ -149,3 +149,27 @@ def test_staged_kernel_wide_tall_and_full_frame_boxes(hint):
     for mode in (orc.GREEN, orc.CHROM_GREEN):
         val, sums = _run(frames, boxes, mode, hint)
         _check(frames, boxes, mode, val, sums)
+
+
+@pytest.mark.parametrize('shape', [(48, 64), (90, 160), (270, 482)])
+def test_nv12_roi_sampling_equals_bgr_of_converted_frame(shape):
+    """F1 straight from NV12 planes == the reference sampling of the BGR frame OpenCV would have made
+    of them (oracle restatement of cvtColor COLOR_YUV2BGR_NV12, pinned against cv2 in the CPU suite) — integer sums and
+    float64 samples bit-exact, Python-slice box semantics, padded pitch."""
+    from bpv import ops
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    N, R, pitch = 5, 4, W + 22
+    buf = rng.integers(0, 256, (N, H * 3 // 2, pitch), dtype=np.uint8)
+    boxes = np.stack([rng.integers(-W - 3, W + 5, (N, R)), rng.integers(-H - 3, H + 5, (N, R)),
+                      rng.integers(-W - 3, W + 5, (N, R)), rng.integers(-H - 3, H + 5, (N, R))], axis=-1).astype(np.int32)
+    boxes[0, 0] = (0, 0, W, H)
+    boxes[1, 1] = (np.iinfo(np.int32).min, 0, 0, 0)
+    boxes[2, 2] = (1, 1, 2, 2)
+    boxes[3, 3] = (W - 3, H - 3, W, H)
+    bgr = np.stack([orc.nv12_to_bgr(buf[f][:, :W], H, W) for f in range(N)])
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        val, sums = ops.roi_sample_nv12(torch.from_numpy(buf).cuda(), H, W, torch.from_numpy(boxes).cuda(), mode, want_sums=True)
+        _check(bgr, boxes, mode, val.cpu().numpy(), sums.cpu().numpy())
+        val2, _ = ops.roi_sample_nv12(torch.from_numpy(buf).cuda(), H, W, torch.from_numpy(boxes).cuda(), mode)
+        assert h.same(val2.cpu().numpy(), val.cpu().numpy())

@@ -10,7 +10,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > $o/bench_c2_${tag}_ref.j
 python bench.py --steps 3 --warmup 3 --no-cpu > $o/plain_$tag.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KF" -c 400 --csv --log-file $o/launches_$tag.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $o/ncu_ll_$tag.log 2>&1
-# ring prefill = 10 step_signals x 6 kernels; each warm-up step = 7 kernels -> skip 60 + 7, capture one full step
-ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 67 --launch-count 7 -f -o $o/c2_$tag \
+# ring prefill = 10 step_signals x 5 kernels; each warm-up step = 6 kernels -> skip 50 + 6, capture one full step
+ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 56 --launch-count 6 -f -o $o/c2_$tag \
     python bench.py --steps 1 --warmup 3 --no-cpu > $o/ncu_full_$tag.log 2>&1
 tail -3 $o/ncu_full_$tag.log | cut -c1-300
