@@ -424,6 +424,243 @@ int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long
   return check_launch("welch_tc_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// DFT_RFFT on the tensor cores (signal_processor.py:254-258: mags = 2 |rfft(y)| / n) for windows whose n valid samples
+// fill the whole window (n == W: every steady-state window of a pipeline that resamples with INTERP_*, and every clean
+// window otherwise), so that all signals of a launch share ONE twiddle matrix exp(-2 pi i j k / W) — the dense
+// contraction [signals x W] . [W x 2F] the north_star assigns to tcgen05.
+//   dft_tc_kernel   grid (signal tiles of 128, bin chunks of 128): K loop over 16-sample blocks, two-stage pipeline;
+//                   A block = the float64 samples split hi/lo on the fly, B block = cos / sin columns from a float64
+//                   table (running index j*k mod n per column), 6 tcgen05.mma (3xTF32) per block into 256 TMEM columns
+//                   (re, im interleaved); epilogue: fp32 magnitudes 2 |X| / n straight into the spectrum rows.
+//                   Rows with a non-finite sample are flagged num_bins = -2 for the float64 kernel.
+//   dft_peak_kernel warp per signal: fs and the frequency axis, fp32 maximum, float64 re-evaluation of every bin within
+//                   DFT_TC_BAND of it (the peak bin and value are float64 decisions, first-max rule).
+// ---------------------------------------------------------------------------------------------
+constexpr int DTC_THREADS = 256;
+constexpr int DTC_KB = 16;                               // samples per k block
+constexpr int DTC_MAXW = 2048;
+constexpr float DFT_TC_BAND = 1.0e-4f;                   // relative band below the fp32 maximum (3xTF32: 4e-6 of the maximum)
+constexpr int DTC_STAGE = 48 * 1024;                     // A hi | A lo [4][128][4] + B hi | B lo [4][256][4]
+constexpr int DTC_OFF_TW = 2 * DTC_STAGE;                // double2 [W]
+__host__ __device__ inline int dtc_smem(int W) { return DTC_OFF_TW + W * 16 + 128 * 4 + 32; }
+
+__global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __restrict__ proc_y, int W, long long nsig, int max_bins,
+                                                                float* __restrict__ mags, int32_t* __restrict__ num_bins) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int n = W, F = n / 2 + 1;
+  double2* tw = reinterpret_cast<double2*>(smem + DTC_OFF_TW);
+  int* bad = reinterpret_cast<int*>(smem + DTC_OFF_TW + W * 16);
+  uint8_t* barp = smem + DTC_OFF_TW + W * 16 + 128 * 4;
+  const uint32_t bar = tc_smem_u32(barp), slot = bar + 16;
+  for (int i = tid; i < n; i += DTC_THREADS) { double s_, c_; sincospi(2.0 * (double)i / (double)n, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  if (tid < 128) bad[tid] = 0;
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 16);
+
+  const long long sig0 = (long long)blockIdx.x * TC_M;
+  const int k0 = blockIdx.y * 128;                        // first bin of this chunk
+  // this thread's B column: bin kcol, part (0 = cos, 1 = sin); running table index (j * kcol) mod n
+  const int kcol = k0 + (tid >> 1), part = tid & 1;
+  const bool col_live = kcol < F;
+  const int kstep = col_live ? kcol : 0;             // kcol <= n/2 for live columns: one conditional subtraction keeps idx < n
+  int idx = 0;
+  // this thread's A items: row arow, chunks 2*ahalf and 2*ahalf+1 of every k block
+  const int arow = tid >> 1, ahalf = tid & 1;
+  const long long asig = sig0 + arow;
+  const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
+  int mybad = 0;
+  const int NB = (n + DTC_KB - 1) / DTC_KB;
+  for (int kb = 0; kb < NB; ++kb) {
+    const int st = kb & 1;
+    uint8_t* stage = smem + st * DTC_STAGE;
+    if (kb >= 2) tc_wait(bar + 8 * st, (uint32_t)(((kb - 2) >> 1) & 1));
+    float4* Ahi = reinterpret_cast<float4*>(stage);
+    float4* Alo = reinterpret_cast<float4*>(stage + 8192);
+    float4* Bhi = reinterpret_cast<float4*>(stage + 16384);
+    float4* Blo = reinterpret_cast<float4*>(stage + 32768);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int ch = 2 * ahalf + cc, j0 = kb * DTC_KB + 4 * ch;
+      float hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        double v = 0.0;
+        if (j < n && asig < nsig) { v = ay[j]; if (!isfinite(v)) mybad = 1; }
+        hv[e] = tc_hi((float)v);
+        lv[e] = (float)(v - (double)hv[e]);
+      }
+      Ahi[ch * TC_M + arow] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      Alo[ch * TC_M + arow] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      float hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double2 t = tw[idx];
+        const double v = col_live ? (part ? t.y : t.x) : 0.0;
+        hv[e] = tc_hi((float)v);
+        lv[e] = (float)(v - (double)hv[e]);
+        idx += kstep; if (idx >= n) idx -= n;
+      }
+      Bhi[ch * TC_N + tid] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      Blo[ch * TC_N + tid] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = tc_smem_u32(stage);
+#pragma unroll
+      for (int ks = 0; ks < DTC_KB / 8; ++ks) {
+        const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
+        const uint64_t dbh = tc_desc(sa + 16384 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sa + 32768 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
+        tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
+        tc_mma_tf32(tmem, dal, dbh, 1);
+        tc_mma_tf32(tmem, dah, dbl, 1);
+      }
+      tc_commit(bar + 8 * st);
+    }
+  }
+  if (mybad) bad[arow] = 1;
+  tc_wait(bar + 8 * ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();                                         // bad[] complete
+  if (tid < TC_M) {
+    const long long sig = sig0 + tid;
+    const bool rowbad = bad[tid] != 0;
+    const float sc = 2.f / (float)n;
+    for (int c32 = 0; c32 < 8; ++c32) {
+      float v[32];
+      __syncwarp();
+      tc_load32(tmem, 32 * c32, v);
+      if (sig < nsig && !rowbad) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = k0 + 16 * c32 + i;
+          if (k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]);
+        }
+      }
+    }
+    if (sig < nsig && rowbad && blockIdx.y == 0) num_bins[sig] = -2;     // the float64 kernel takes this window
+    if (sig < nsig && !rowbad && blockIdx.y == 0) num_bins[sig] = -1;    // marker: coarse spectrum ready for dft_peak_kernel
+  }
+  tc_teardown(tmem);
+}
+
+// warp per signal; smem: double2 tw[W] shared by the CTA's warps
+__global__ void __launch_bounds__(128) dft_peak_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y, int W,
+                                                       long long nsig, int max_bins, float* __restrict__ spec_f,
+                                                       float* __restrict__ mags, int32_t* __restrict__ num_bins,
+                                                       int32_t* __restrict__ peak_idx, double* __restrict__ peak_freq,
+                                                       double* __restrict__ peak_mag) {
+  extern __shared__ __align__(16) uint8_t psm[];
+  double2* tw = reinterpret_cast<double2*>(psm);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = W, F = n / 2 + 1;
+  for (int i = tid; i < n; i += blockDim.x) { double s_, c_; sincospi(2.0 * (double)i / (double)n, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  __syncthreads();
+  const long long sig = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  if (sig >= nsig || num_bins[sig] != -1) return;          // -2: float64 kernel; anything else: not ours
+  const double* px = proc_x + sig * W;
+  const double* py = proc_y + sig * W;
+  // fs over the finite-x mask (Signal.get_fs); y is finite everywhere here
+  int m = 0; double xfirst = 0.0, xlast = 0.0;
+  for (int k0 = 0; k0 < W; k0 += 32) {
+    const int k = k0 + lane;
+    const double x = k < W ? px[k] : nan_f64();
+    const unsigned bx = __ballot_sync(0xffffffffu, isfinite(x));
+    if (bx) {
+      const double xf = __shfl_sync(0xffffffffu, x, __ffs(bx) - 1), xl = __shfl_sync(0xffffffffu, x, 31 - __clz(bx));
+      if (m == 0) xfirst = xf;
+      xlast = xl;
+    }
+    m += __popc(bx);
+  }
+  const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
+  if (!(n >= 2 && isfinite(fs))) {                         // guard signal_processor.py:252 -> empty spectrum
+    if (lane == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    return;
+  }
+  const double fval = 1.0 / ((double)n * (1.0 / fs));      // rfftfreq(n, d=1/fs)[k] = k * (1/(n*d))
+  float* row = mags + sig * max_bins;
+  float cmax = -INFINITY; int cnt = 0;
+  for (int k = lane; k < F; k += 32) {
+    const float v = row[k];
+    if (isfinite(v)) { ++cnt; cmax = fmaxf(cmax, v); }
+    if (spec_f) spec_f[sig * max_bins + k] = (float)((double)k * fval);
+  }
+  for (int o = 16; o > 0; o >>= 1) { cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  const float thr = cmax - DFT_TC_BAND * fabsf(cmax);
+  double best = -INFINITY; int bi = 0x7fffffff;
+  for (int kk0 = 0; kk0 < F; kk0 += 32) {
+    const int k = kk0 + lane;
+    bool cand = false;
+    if (k < F) { const float v = row[k]; cand = cnt >= 2 ? (isfinite(v) && v >= thr) : true; }
+    unsigned mk = __ballot_sync(0xffffffffu, cand);
+    while (mk) {
+      const int kc = kk0 + __ffs(mk) - 1;
+      mk &= mk - 1;
+      double re = 0.0, im = 0.0;
+      int idx = (int)(((long long)lane * kc) % n);
+      const int step = (int)((32LL * kc) % n);
+      for (int j = lane; j < n; j += 32) {
+        const double2 t = tw[idx];
+        const double v = py[j];
+        re = fma(v, t.x, re); im = fma(-v, t.y, im);
+        idx += step; if (idx >= n) idx -= n;
+      }
+      re = warp_sum(re); im = warp_sum(im);
+      const double mg = 2.0 * hypot(re, im) / (double)n;
+      if (lane == 0) row[kc] = (float)mg;
+      if (isfinite(mg) && (mg > best || (mg == best && kc < bi))) { best = mg; bi = kc; }
+    }
+  }
+  if (lane == 0) {
+    num_bins[sig] = F;
+    if (cnt >= 2 && bi != 0x7fffffff) { peak_idx[sig] = bi; peak_freq[sig] = (double)bi * fval; peak_mag[sig] = best; }
+    else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+  }
+}
+
+int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, cudaStream_t st) {
+  const int smem = dtc_smem(W), smem_p = W * 16;
+  static int configured = 0, configured_p = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(dft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = smem;
+  }
+  if (smem_p > 48 * 1024 && smem_p > configured_p) {
+    cudaError_t e = cudaFuncSetAttribute(dft_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured_p = smem_p;
+  }
+  const int F = W / 2 + 1;
+  dim3 grid((unsigned)((nsig + TC_M - 1) / TC_M), (unsigned)((F + 127) / 128));
+  dft_tc_kernel<<<grid, DTC_THREADS, smem, st>>>(proc_y, W, nsig, max_bins, mags, num_bins);
+  if (int rc = check_launch("dft_tc_kernel")) return rc;
+  dft_peak_kernel<<<(unsigned)((nsig + 3) / 4), 128, smem_p, st>>>(proc_x, proc_y, W, nsig, max_bins, spec_f, mags, num_bins, peak_idx,
+                                                                 peak_freq, peak_mag);
+  return check_launch("dft_peak_kernel");
+}
+
 }  // namespace bpv
 
 extern "C" int bpv_dft256_tc(const float* z, int32_t rows, float* d, void* stream) {

@@ -17,6 +17,8 @@
 
 namespace bpv {
 
+int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, cudaStream_t st);
 int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
                     double* peak_freq, double* peak_mag, cudaStream_t st);
 
@@ -105,12 +107,13 @@ __device__ Peak block_argmax(const double* vals, int F, double* s_val, int* s_id
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __restrict__ proc_x,
                                                              const double* __restrict__ proc_y,
-                                                             const bpv_window_params p, int max_bins,
+                                                             const bpv_window_params p, int max_bins, int only_flagged,
                                                              float* __restrict__ spec_f, float* __restrict__ spec_mag,
                                                              int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
                                                              double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_cnt[4];
+  if (only_flagged && num_bins[blockIdx.x] != -2) return;   // second pass behind dft_tc_kernel (CTA uniform)
   __shared__ double s_d[2];
   __shared__ double s_val[33];
   __shared__ int s_idx[64];
@@ -681,8 +684,8 @@ __global__ void __launch_bounds__(128) ls_peak_kernel(const double* __restrict__
 
 extern "C" int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins) {
   if (!p) return -1;
-  if (p->transform != BPV_PGRAM_LS) return 0;
-  return (int64_t)p->S * p->jobs_per_stream * p->R * max_bins * 4;
+  if (p->transform == BPV_PGRAM_WELCH) return 0;
+  return (int64_t)p->S * p->jobs_per_stream * p->R * max_bins * 4;    // LS psd / DFT coarse magnitudes when not stored
 }
 
 extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,
@@ -729,7 +732,27 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
       cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    spectrum_dense_kernel<<<(unsigned)nsig, 128, smem, st>>>(proc_x, proc_y, *p, max_bins, spec_f, spec_mag, num_bins,
+    // DFT_RFFT as one dense contraction on the tensor cores (dft_tc.cu) when the windows of the launch share n = W: by
+    // default for pipelines that resample (INTERP_*: valid = block, so every warmed-up window is full), or forced /
+    // disabled with BPV_DFT_TC=1 / 0.  Windows with a non-finite sample are flagged and taken by the float64 kernel.
+    int only_flagged = 0;
+    if (p->transform == BPV_DFT_RFFT && W >= 16 && W <= 2048) {
+      bool interp = false;
+      for (int i = 0; i < p->num_methods; ++i) interp |= (p->methods[i] == BPV_INTERP_LINEAR || p->methods[i] == BPV_INTERP_CUBIC);
+      const char* env = getenv("BPV_DFT_TC");
+      const bool use_tc = env ? env[0] == '1' : interp;
+      if (use_tc) {
+        float* coarse = spec_mag;
+        if (!coarse) {
+          BPV_REQUIRE(workspace && workspace_bytes >= (int64_t)nsig * max_bins * 4, BPV_E_INVALID,
+                      "bpv_window_spectrum: workspace too small (see bpv_spectrum_workspace_bytes)");
+          coarse = (float*)workspace;
+        }
+        if (int rc = launch_dft_tc(proc_x, proc_y, W, nsig, max_bins, spec_f, coarse, num_bins, peak_idx, peak_freq, peak_mag, st)) return rc;
+        only_flagged = 1;
+      }
+    }
+    spectrum_dense_kernel<<<(unsigned)nsig, 128, smem, st>>>(proc_x, proc_y, *p, max_bins, only_flagged, spec_f, spec_mag, num_bins,
                                                             peak_idx, peak_freq, peak_mag);
     return check_launch("spectrum_dense_kernel");
   }

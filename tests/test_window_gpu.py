@@ -286,6 +286,44 @@ def test_spectrum_and_peak_match_oracle(transform, methods, kw, W, fps):
                     np.testing.assert_allclose(pm[s, r], ey, rtol=1e-7, atol=1e-9 * max(1.0, abs(ey)))
 
 
+@pytest.mark.parametrize('W,fps', [(40, 30.0), (300, 30.0), (1200, 120.0)])
+@pytest.mark.parametrize('methods,force', [([orc.INTERP_CUBIC, orc.FILTER_BUTTER], None), ([orc.INTERP_LINEAR, orc.DETREND_CONST], None),
+                                           ([orc.DIFF_1], '1'), ([], '1')], ids=['cubic_butter', 'linear_const', 'diff1_forced', 'none_forced'])
+def test_dft_tensor_core_path_matches_oracle(methods, force, W, fps, monkeypatch):
+    """DFT_RFFT as a tcgen05 contraction (dft_tc_kernel: 3xTF32, one twiddle matrix per launch because full windows
+    share n = W) + float64 decision (dft_peak_kernel); default for resampling pipelines, forced here for the others.
+    Peak bins exact, magnitudes within the spec tolerance, short / holed windows through the float64 kernel."""
+    from bpv import ops
+    if force is not None:
+        monkeypatch.setenv('BPV_DFT_TC', force)
+    S, R = 12, 2
+    fill = [min(f, W) for f in [W, W, W, W - 1, W // 2, 257, 130, 40, 5, 3, 2, 1]]
+    t, y = make_windows(W * 19 + len(methods), S, W, R, fps=fps, fill=fill, p_nan=0.0 if not methods else 0.03)
+    if not methods:
+        y[1, 0, W // 3] = np.nan                        # a hole in an otherwise full window -> float64 kernel
+    px, py = oracle_proc(t, y, methods)
+    p = params(S, R, W, methods, orc.DFT_RFFT)
+    dx, dy = torch.from_numpy(px).cuda(), torch.from_numpy(py).cuda()
+    for store in (True, False):
+        o = ops.window_spectrum(dx, dy, p, store=store)
+        torch.cuda.synchronize()
+        nb, pi = o['num_bins'].cpu().numpy(), o['peak_idx'].cpu().numpy()
+        pf, pm = o['peak_freq'].cpu().numpy(), o['peak_mag'].cpu().numpy()
+        for s in range(S):
+            for r in range(R):
+                ef, em = orc.spectrum(px[s, r], py[s, r], orc.DFT_RFFT)
+                ex, ey, ei = orc.peak(ef, em)
+                assert nb[s, r] == len(ef), (s, r, nb[s, r], len(ef))
+                if store:
+                    gf, gm = o['freqs'].cpu().numpy()[s, r, :len(ef)], o['mags'].cpu().numpy()[s, r, :len(ef)]
+                    assert h.close(gf, ef, rtol=1e-6, atol_frac=0), (s, r, 'freqs')
+                    assert h.close(gm, em, rtol=RTOL, atol_frac=1e-5, atol=1e-30), (s, r, fill[s], 'mags', np.nanmax(np.abs(gm - em)))
+                assert pi[s, r] == ei, (s, r, fill[s], pi[s, r], ei)
+                if ei >= 0:
+                    np.testing.assert_allclose(pf[s, r], ex, rtol=4e-16 * 8)
+                    np.testing.assert_allclose(pm[s, r], ey, rtol=1e-7, atol=1e-9 * max(1.0, abs(ey)))
+
+
 @pytest.mark.parametrize('W,fps', [(64, 30.0), (300, 30.0), (600, 120.0)])
 @pytest.mark.parametrize('methods', [[orc.FILTER_BUTTER], [orc.DETREND_LINEAR, orc.FILTER_FIR], [orc.INTERP_CUBIC, orc.FILTER_BUTTER], []],
                          ids=lambda m: '-'.join(map(str, m)) or 'none')
