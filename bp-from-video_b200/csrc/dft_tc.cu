@@ -484,9 +484,21 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
   const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
   int mybad = 0;
   const int NB = (n + DTC_KB - 1) / DTC_KB;
+  // software prefetch: the 8 samples of the NEXT k block are requested before this block is converted and issued, so the
+  // global-load latency hides behind the operand generation and the MMAs of the current block
+  double cur[8], nxt[8];
+  auto fetch = [&](int kb, double (&dst)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = kb * DTC_KB + 8 * ahalf + e;
+      dst[e] = (j < n && asig < nsig) ? ay[j] : 0.0;
+    }
+  };
+  fetch(0, cur);
   for (int kb = 0; kb < NB; ++kb) {
     const int st = kb & 1;
     uint8_t* stage = smem + st * DTC_STAGE;
+    if (kb + 1 < NB) fetch(kb + 1, nxt);
     if (kb >= 2) tc_wait(bar + 8 * st, (uint32_t)(((kb - 2) >> 1) & 1));
     float4* Ahi = reinterpret_cast<float4*>(stage);
     float4* Alo = reinterpret_cast<float4*>(stage + 8192);
@@ -494,13 +506,12 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
     float4* Blo = reinterpret_cast<float4*>(stage + 32768);
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-      const int ch = 2 * ahalf + cc, j0 = kb * DTC_KB + 4 * ch;
+      const int ch = 2 * ahalf + cc;
       float hv[4], lv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int j = j0 + e;
-        double v = 0.0;
-        if (j < n && asig < nsig) { v = ay[j]; if (!isfinite(v)) mybad = 1; }
+        const double v = cur[4 * cc + e];
+        if (!isfinite(v)) mybad = 1;
         hv[e] = tc_hi((float)v);
         lv[e] = (float)(v - (double)hv[e]);
       }
@@ -536,6 +547,8 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
       }
       tc_commit(bar + 8 * st);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
   }
   if (mybad) bad[arow] = 1;
   tc_wait(bar + 8 * ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
