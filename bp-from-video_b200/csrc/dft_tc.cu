@@ -433,12 +433,12 @@ int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long
 //   dft_tc_kernel   grid (signal tiles of 128, bin chunks of 128): K loop over 16-sample blocks, two-stage pipeline;
 //                   A block = the float64 samples split hi/lo on the fly, B block = cos / sin columns from a float64
 //                   table (running index j*k mod n per column), 6 tcgen05.mma (3xTF32) per block into 256 TMEM columns
-//                   (re, im interleaved); epilogue: fp32 magnitudes 2 |X| / n straight into the spectrum rows.
+//                   (re columns 0..127, im columns 128..255); epilogue: fp32 magnitudes 2 |X| / n straight into the spectrum rows.
 //                   Rows with a non-finite sample are flagged num_bins = -2 for the float64 kernel.
 //   dft_peak_kernel warp per signal: fs and the frequency axis, fp32 maximum, float64 re-evaluation of every bin within
 //                   DFT_TC_BAND of it (the peak bin and value are float64 decisions, first-max rule).
 // ---------------------------------------------------------------------------------------------
-constexpr int DTC_THREADS = 256;
+constexpr int DTC_THREADS = 512;
 constexpr int DTC_KB = 16;                               // samples per k block
 constexpr int DTC_MAXW = 2048;
 constexpr float DFT_TC_BAND = 1.0e-4f;                   // relative band below the fp32 maximum (3xTF32: 4e-6 of the maximum)
@@ -451,11 +451,16 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
   const int n = W, F = n / 2 + 1;
-  double2* tw = reinterpret_cast<double2*>(smem + DTC_OFF_TW);
+  float4* tw = reinterpret_cast<float4*>(smem + DTC_OFF_TW);   // exp(2 pi i j / n) pre-split: (cos_hi, sin_hi, cos_lo, sin_lo)
   int* bad = reinterpret_cast<int*>(smem + DTC_OFF_TW + W * 16);
   uint8_t* barp = smem + DTC_OFF_TW + W * 16 + 128 * 4;
   const uint32_t bar = tc_smem_u32(barp), slot = bar + 16;
-  for (int i = tid; i < n; i += DTC_THREADS) { double s_, c_; sincospi(2.0 * (double)i / (double)n, &s_, &c_); tw[i] = make_double2(c_, s_); }
+  for (int i = tid; i < n; i += DTC_THREADS) {
+    double s_, c_;
+    sincospi(2.0 * (double)i / (double)n, &s_, &c_);
+    const float ch_ = tc_hi((float)c_), sh_ = tc_hi((float)s_);
+    tw[i] = make_float4(ch_, sh_, (float)(c_ - (double)ch_), (float)(s_ - (double)sh_));
+  }
   if (tid < 128) bad[tid] = 0;
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
@@ -473,24 +478,27 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
 
   const long long sig0 = (long long)blockIdx.x * TC_M;
   const int k0 = blockIdx.y * 128;                        // first bin of this chunk
-  // this thread's B column: bin kcol, part (0 = cos, 1 = sin); running table index (j * kcol) mod n
-  const int kcol = k0 + (tid >> 1), part = tid & 1;
+  // this thread's B item: bin kcol = k0 + bbin (column bbin = cos, column 128 + bbin = sin: consecutive lanes write
+  // consecutive 16-byte slots), chunk bch of every k block (4 consecutive samples); running table index (j * kcol) mod n,
+  // advanced past the other chunks' 12 samples per block
+  const int bbin = tid & 127, bch = tid >> 7;
+  const int kcol = k0 + bbin;
   const bool col_live = kcol < F;
   const int kstep = col_live ? kcol : 0;             // kcol <= n/2 for live columns: one conditional subtraction keeps idx < n
-  int idx = 0;
-  // this thread's A items: row arow, chunks 2*ahalf and 2*ahalf+1 of every k block
-  const int arow = tid >> 1, ahalf = tid & 1;
+  const int kskip = (int)((12LL * kstep) % n);
+  int idx = (int)((4LL * bch * kstep) % n);
+  // this thread's A item: row arow (consecutive lanes = consecutive rows), chunk ach of every k block (4 samples)
+  const int arow = tid & 127, ach = tid >> 7;
   const long long asig = sig0 + arow;
   const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
   int mybad = 0;
   const int NB = (n + DTC_KB - 1) / DTC_KB;
-  // software prefetch: the 8 samples of the NEXT k block are requested before this block is converted and issued, so the
-  // global-load latency hides behind the operand generation and the MMAs of the current block
-  double cur[8], nxt[8];
-  auto fetch = [&](int kb, double (&dst)[8]) {
+  // software prefetch: the samples of the NEXT k block are requested before this block is converted and issued
+  double cur[4], nxt[4];
+  auto fetch = [&](int kb, double (&dst)[4]) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = kb * DTC_KB + 8 * ahalf + e;
+    for (int e = 0; e < 4; ++e) {
+      const int j = kb * DTC_KB + 4 * ach + e;
       dst[e] = (j < n && asig < nsig) ? ay[j] : 0.0;
     }
   };
@@ -504,33 +512,31 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
     float4* Alo = reinterpret_cast<float4*>(stage + 8192);
     float4* Bhi = reinterpret_cast<float4*>(stage + 16384);
     float4* Blo = reinterpret_cast<float4*>(stage + 32768);
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int ch = 2 * ahalf + cc;
+    {
       float hv[4], lv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const double v = cur[4 * cc + e];
+        const double v = cur[e];
         if (!isfinite(v)) mybad = 1;
         hv[e] = tc_hi((float)v);
         lv[e] = (float)(v - (double)hv[e]);
       }
-      Ahi[ch * TC_M + arow] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      Alo[ch * TC_M + arow] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      Ahi[ach * TC_M + arow] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      Alo[ach * TC_M + arow] = make_float4(lv[0], lv[1], lv[2], lv[3]);
     }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      float hv[4], lv[4];
+    {
+      float4 t4[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const double2 t = tw[idx];
-        const double v = col_live ? (part ? t.y : t.x) : 0.0;
-        hv[e] = tc_hi((float)v);
-        lv[e] = (float)(v - (double)hv[e]);
+        t4[e] = col_live ? tw[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
         idx += kstep; if (idx >= n) idx -= n;
       }
-      Bhi[ch * TC_N + tid] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      Blo[ch * TC_N + tid] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      idx += kskip; if (idx >= n) idx -= n;            // the 12 samples of this block that the other chunks generate
+      const int o = bch * TC_N + bbin;
+      Bhi[o] = make_float4(t4[0].x, t4[1].x, t4[2].x, t4[3].x);
+      Bhi[o + 128] = make_float4(t4[0].y, t4[1].y, t4[2].y, t4[3].y);
+      Blo[o] = make_float4(t4[0].z, t4[1].z, t4[2].z, t4[3].z);
+      Blo[o + 128] = make_float4(t4[0].w, t4[1].w, t4[2].w, t4[3].w);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
       tc_commit(bar + 8 * st);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+    for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
   }
   if (mybad) bad[arow] = 1;
   tc_wait(bar + 8 * ((NB - 1) & 1), (uint32_t)(((NB - 1) >> 1) & 1));
@@ -558,15 +564,16 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
     const long long sig = sig0 + tid;
     const bool rowbad = bad[tid] != 0;
     const float sc = 2.f / (float)n;
-    for (int c32 = 0; c32 < 8; ++c32) {
-      float v[32];
+    for (int c32 = 0; c32 < 4; ++c32) {
+      float re[32], im[32];
       __syncwarp();
-      tc_load32(tmem, 32 * c32, v);
+      tc_load32(tmem, 32 * c32, re);
+      tc_load32(tmem, 128 + 32 * c32, im);
       if (sig < nsig && !rowbad) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k = k0 + 16 * c32 + i;
-          if (k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]);
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + 32 * c32 + i;
+          if (k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(re[i] * re[i] + im[i] * im[i]);
         }
       }
     }
