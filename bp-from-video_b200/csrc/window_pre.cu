@@ -50,7 +50,7 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   L.xv = o; o += interp ? W * 8 : 0;
   L.buf0 = o; o += (butter || fir || interp) ? L.buf_len * 8 : 0;
   L.buf1 = o; o += (fir || cubic) ? L.buf_len * 8 : 0;
-  L.coef = o; o += (butter || fir) ? 256 * 8 : 0;
+  L.coef = o; o += (butter || fir) ? 272 * 8 : 0;      // FIR: taps [130 padded] | lfilter_zi at +136
   L.posv = o; o += ((W * 2 + 7) / 8) * 8;
   L.posb = o; o += interp ? ((W * 2 + 7) / 8) * 8 : 0;
   L.total = o;
@@ -374,23 +374,26 @@ __device__ void sos_filtfilt(Warp& w, const double* __restrict__ sos_g, int N) {
 // Only forward outputs that can reach the cropped result are evaluated (F[p .. p+n-1+T-1]).  Both passes
 // are the register-tiled sliding dot product of corr_tile.cuh: each lane owns 8 consecutive outputs, the
 // operand buffers are de-interleaved by 8 and zero padded in front so no tap needs a bounds check.
-constexpr int FIR_RT = 8;
+constexpr int FIR_RT = 8;     // forward pass: n + T - 1 outputs (426 for n = 300) = 2 rounds of 32 lanes x 8
+constexpr int FIR_RTB = 10;   // backward pass: n outputs (300) = ONE round of 30 lanes x 10 instead of 32 + 6 lanes x 8
 __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) {
   const int Kp = (T + FIR_RT - 1) / FIR_RT * FIR_RT;
-  double* b = w.coef;          // [Kp] zero padded
-  double* zi = w.coef + 128;   // [T-1]
-  for (int i = w.lane; i < Kp; i += 32) b[i] = i < T ? taps_g[i] : 0.0;
+  const int KpB = (T + FIR_RTB - 1) / FIR_RTB * FIR_RTB;
+  double* b = w.coef;          // [max(Kp, KpB)] zero padded
+  double* zi = w.coef + 136;   // [T-1]
+  for (int i = w.lane; i < 136; i += 32) b[i] = i < T ? taps_g[i] : 0.0;
   for (int i = w.lane; i < T - 1; i += 32) zi[i] = taps_g[128 + i];   // lfilter_zi, from the design kernel
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
   const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);   // forward outputs needed
   const int ba = p, bb = p + n - 1;                                                      // backward outputs needed
-  // Only the operands those outputs can touch are staged: ext[fa-Kp .. fb+7] and G[ba-Kp .. bb+7]
+  // Only the operands those outputs can touch are staged: ext[fa-Kp .. fb+7] and G[ba-KpB .. bb+9]
   // (negative logical indices are the zero history of lfilter).  storage index = logical index - base.
-  const int xbase = fa - Kp, gbase = ba - Kp;
+  const int xbase = fa - Kp, gbase = ba - KpB;
   const int LD = (Kp + n + T + 15) / FIR_RT + 1;
+  const int LDB = (KpB + n + T + 2 * FIR_RTB) / FIR_RTB + 1;
   double* XT = w.buf0;   // ext, de-interleaved by FIR_RT
-  double* GT = w.buf1;   // reversed forward output G[g] = F[L-1-g], same layout
+  double* GT = w.buf1;   // reversed forward output G[g] = F[L-1-g], de-interleaved by FIR_RTB
   const double y_first = w.yv[0], y_last = w.yv[n - 1];
   for (int jj = w.lane; jj < FIR_RT * LD; jj += 32) {
     const int i = jj + xbase;
@@ -400,10 +403,9 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
       else if (i < p + n) v = w.yv[i - p];
       else v = 2.0 * y_last - w.yv[n - 2 - (i - p - n)];
     }
-    const int a = xt_index<FIR_RT>(jj, LD);
-    XT[a] = v;
-    GT[a] = 0.0;
+    XT[xt_index<FIR_RT>(jj, LD)] = v;
   }
+  for (int jj = w.lane; jj < FIR_RTB * LDB; jj += 32) GT[jj] = 0.0;
   __syncwarp();
   const double x0 = p >= 1 ? 2.0 * y_first - w.yv[p] : y_first;       // ext[0]
   for (int I = Kp; I <= fb - xbase; I += 32 * FIR_RT) {               // storage Kp <-> logical fa
@@ -419,23 +421,23 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
         if (i <= fb) {
           const double v = acc[r] + (i < T - 1 ? zi[i] * x0 : 0.0);
           const int g = L - 1 - i;                                    // >= ba - (T-1) >= gbase
-          GT[xt_index<FIR_RT>(g - gbase, LD)] = v;
+          GT[xt_index<FIR_RTB>(g - gbase, LDB)] = v;
         }
       }
     }
   }
   __syncwarp();
   // F[L-1] = G[0]; only used when p < T-1 (then fb == L-1, so it has been computed)
-  const double yend = (0 - gbase >= 0) ? GT[xt_index<FIR_RT>(0 - gbase, LD)] : 0.0;
-  for (int I = Kp; I <= bb - gbase; I += 32 * FIR_RT) {
-    const int j0 = I + FIR_RT * w.lane, i0 = j0 + gbase;
+  const double yend = (0 - gbase >= 0) ? GT[xt_index<FIR_RTB>(0 - gbase, LDB)] : 0.0;
+  for (int I = KpB; I <= bb - gbase; I += 32 * FIR_RTB) {
+    const int j0 = I + FIR_RTB * w.lane, i0 = j0 + gbase;
     if (i0 <= bb) {
-      double acc[FIR_RT];
+      double acc[FIR_RTB];
 #pragma unroll
-      for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
-      corr_tile<FIR_RT, double>(acc, b, Kp, GT, LD, j0);
+      for (int r = 0; r < FIR_RTB; ++r) acc[r] = 0.0;
+      corr_tile<FIR_RTB, double>(acc, b, KpB, GT, LDB, j0);
 #pragma unroll
-      for (int r = 0; r < FIR_RT; ++r) {
+      for (int r = 0; r < FIR_RTB; ++r) {
         const int i = i0 + r;
         if (i <= bb) w.yv[L - 1 - p - i] = acc[r] + (i < T - 1 ? zi[i] * yend : 0.0);
       }
@@ -607,9 +609,9 @@ extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y,
   const int max_smem = 200 * 1024;
   BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
               p->window, L.total);
-  // warps (signals) per CTA: the value in 1..8 that keeps the most warps resident per SM
+  // warps (signals) per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
   int wpb = 1, best = 0;
-  for (int c = 1; c <= 8; ++c) {
+  for (int c = 1; c <= 4; ++c) {
     const int per_block = c * L.total + 1024;                  // + per-CTA reservation
     if (per_block > max_smem) break;
     int blocks = (227 * 1024) / per_block;
