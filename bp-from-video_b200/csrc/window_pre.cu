@@ -203,37 +203,50 @@ __device__ bool interp_cubic(Warp& w) {
       const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
       const double s1 = (dx0 * sl1 + dx1 * sl0) / (dx0 + dx1);   // parabola through the 3 points
       s[1] = s1; s[0] = 2.0 * sl0 - s1; s[2] = 2.0 * sl1 - s1;
-    } else {
-      double dxp = x[1] - x[0], slp = (y[1] - y[0]) / dxp;      // dx[i-1], slope[i-1]
-      double dxc = x[2] - x[1], slc = (y[2] - y[1]) / dxc;      // dx[i],   slope[i]
+    }
+  }
+  if (n > 3) {
+    // Rows 1..n-2 of the tridiagonal system are independent of each other: every lane builds its share in place —
+    // cp[i] <- diagonal 2(dx[i-1]+dx[i]), s[i] <- right-hand side 3(dx[i] sl[i-1] + dx[i-1] sl[i]) — and only the
+    // Thomas recurrence itself stays serial on lane 0, with one reciprocal per row on its critical path.
+    for (int i = 1 + w.lane; i <= n - 2; i += 32) {
+      const double dxp = x[i] - x[i - 1], dxc = x[i + 1] - x[i];
+      const double slp = (y[i] - y[i - 1]) / dxp, slc = (y[i + 1] - y[i]) / dxc;
+      cp[i] = 2.0 * (dxp + dxc);
+      s[i] = 3.0 * (dxc * slp + dxp * slc);
+    }
+    __syncwarp();
+    if (w.lane == 0) {
+      double cprev, sprev;
       {  // row 0: dx1*s0 + (x2-x0)*s1 = ((dx0+2d)*dx1*sl0 + dx0^2*sl1)/d
+        const double dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+        const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
         const double d = x[2] - x[0];
-        const double diag = dxc, up = d;
-        const double rhs = ((dxp + 2.0 * d) * dxc * slp + dxp * dxp * slc) / d;
-        cp[0] = up / diag;
-        s[0] = rhs / diag;
+        const double rhs = ((dx0 + 2.0 * d) * dx1 * sl0 + dx0 * dx0 * sl1) / d;
+        const double inv = 1.0 / dx1;
+        cprev = d * inv; sprev = rhs * inv;
+        cp[0] = cprev; s[0] = sprev;
       }
+      double xm = x[0], xc = x[1], xn = x[2];                   // x[i-1], x[i], x[i+1]
       for (int i = 1; i <= n - 2; ++i) {
-        // dx[i]*s[i-1] + 2(dx[i-1]+dx[i])*s[i] + dx[i-1]*s[i+1] = 3(dx[i]*sl[i-1] + dx[i-1]*sl[i])
-        const double lo = dxc, diag = 2.0 * (dxp + dxc), up = dxp;
-        const double rhs = 3.0 * (dxc * slp + dxp * slc);
-        const double den = diag - lo * cp[i - 1];
-        cp[i] = up / den;
-        s[i] = (rhs - lo * s[i - 1]) / den;
-        if (i < n - 2) {
-          dxp = dxc; slp = slc;
-          dxc = x[i + 2] - x[i + 1];
-          slc = (y[i + 2] - y[i + 1]) / dxc;
-        }
+        // dx[i]*s[i-1] + 2(dx[i-1]+dx[i])*s[i] + dx[i-1]*s[i+1] = rhs[i]
+        const double lo = xn - xc, up = xc - xm;
+        const double inv = 1.0 / fma(-lo, cprev, cp[i]);
+        cprev = up * inv;
+        sprev = fma(-lo, sprev, s[i]) * inv;
+        cp[i] = cprev; s[i] = sprev;
+        xm = xc; xc = xn; xn = x[i + 2 < n ? i + 2 : n - 1];
       }
       {  // last row: (x[n-1]-x[n-3])*s[n-2] + dx[n-3]*s[n-1] = (dx[n-2]^2*sl[n-3] + (2d+dx[n-2])*dx[n-3]*sl[n-2])/d
+        const double dxp = x[n - 2] - x[n - 3], dxc = x[n - 1] - x[n - 2];
+        const double slp = (y[n - 2] - y[n - 3]) / dxp, slc = (y[n - 1] - y[n - 2]) / dxc;
         const double d = x[n - 1] - x[n - 3];
-        const double lo = d, diag = dxp;   // dxp = dx[n-3], dxc = dx[n-2], slp = sl[n-3], slc = sl[n-2]
         const double rhs = (dxc * dxc * slp + (2.0 * d + dxc) * dxp * slc) / d;
-        const double den = diag - lo * cp[n - 2];
-        s[n - 1] = (rhs - lo * s[n - 2]) / den;
+        const double den = dxp - d * cprev;
+        double sn = (rhs - d * sprev) / den;
+        s[n - 1] = sn;
+        for (int i = n - 2; i >= 0; --i) { sn = fma(-cp[i], sn, s[i]); s[i] = sn; }
       }
-      for (int i = n - 2; i >= 0; --i) s[i] -= cp[i] * s[i + 1];
     }
   }
   __syncwarp();
