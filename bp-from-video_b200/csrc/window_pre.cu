@@ -228,6 +228,7 @@ __device__ bool interp_cubic(Warp& w) {
         cp[0] = cprev; s[0] = sprev;
       }
       double xm = x[0], xc = x[1], xn = x[2];                   // x[i-1], x[i], x[i+1]
+#pragma unroll 4
       for (int i = 1; i <= n - 2; ++i) {
         // dx[i]*s[i-1] + 2(dx[i-1]+dx[i])*s[i] + dx[i-1]*s[i+1] = rhs[i]
         const double lo = xn - xc, up = xc - xm;
@@ -245,6 +246,7 @@ __device__ bool interp_cubic(Warp& w) {
         const double den = dxp - d * cprev;
         double sn = (rhs - d * sprev) / den;
         s[n - 1] = sn;
+#pragma unroll 4
         for (int i = n - 2; i >= 0; --i) { sn = fma(-cp[i], sn, s[i]); s[i] = sn; }
       }
     }
