@@ -500,7 +500,7 @@ __device__ double ls_eval_f64(const double* __restrict__ t, const double* __rest
 // per thread, then LS_NF-1 complex rotations (4 FP32 ops each) — the kernel is issue-bound, and this cuts
 // the instructions per (sample, frequency) pair from ~26 to ~13.
 // smem: doubles xs[W] | ys[W] (gather scratch), then float4 {t_hi, t_lo, y - mean, 0}[W], float2 rot[W].
-constexpr int LS_NF = 4;
+constexpr int LS_NF = 8;
 __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                         const bpv_window_params p, int max_bins,
                                                         float* __restrict__ spec_f, float* __restrict__ psd) {
