@@ -511,7 +511,11 @@ static void launch_rows(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   else roi_rows_kernel<GROUP, 4, false, LDMODE, 4><<<grid, 256, smem, st>>>(a);
 }
 
-// development-only tuning variants (BPV_ROI_VARIANT=<ldmode><unroll><minblocks>, e.g. "084"), GROUP=128
+// Tuning variants (register path load modes / unroll / occupancy, cp.async staging depth and CTA size, cp.async.bulk
+// rows) are compiled only with -DBPV_ROI_TUNING and selected with BPV_ROI_VARIANT (tools/roi_variants.sh produced
+// profiles/r1d_roi_variants.txt, r1e_roi_variants.txt, r1e_roi_host_variants.txt with them); the product library
+// contains only the paths it dispatches to.
+#ifdef BPV_ROI_TUNING
 static bool launch_variant(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   static const char* v = getenv("BPV_ROI_VARIANT");
   if (!v) return false;
@@ -529,6 +533,9 @@ static bool launch_variant(const RoiArgs& a, unsigned grid, cudaStream_t st) {
 #undef V
   return false;
 }
+#else
+static inline bool launch_variant(const RoiArgs&, unsigned, cudaStream_t) { return false; }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // F1 on NV12 frames: decoders (NVDEC, V4L2) hand out NV12 — a full-resolution Y plane followed

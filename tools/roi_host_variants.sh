@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a tuning build of the library: BPV_NVCC_EXTRA=-DBPV_ROI_TUNING python -m bpv.build --force  (from bp-from-video_b200/)
 # dev aid: F1 reading ROI rows zero-copy from pinned host memory over PCIe, per tuning variant
 out=gpurun_out/roi_host_variants_r1e.txt
 : > $out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a tuning build of the library: BPV_NVCC_EXTRA=-DBPV_ROI_TUNING python -m bpv.build --force  (from bp-from-video_b200/)
 # dev aid: time the F1 tuning variants (one process each; BPV_ROI_VARIANT is read once per process)
 out=gpurun_out/roi_variants_r1e.txt
 : > $out
