@@ -105,7 +105,8 @@ class BatchedSignalProcessor:
     def _params(self, head0: int, head_step: int, jobs: int) -> _cabi.WindowParams:
         return ops.make_params(self.S, self.R, self.cap, self.W, head0, head_step, jobs, self.methods, self.transform, **self.kw)
 
-    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None, nv12_size=None) -> StepResult:
+    def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None, nv12_size=None,
+             resize_to=None) -> StepResult:
         """frames uint8 [S, T, H, W, 3] (HBM, or pinned host memory: the ROI kernel then reads the ROI rows
         straight over PCIe), boxes int32 [S, T, R, 4] (device), timestamps float64 [S, T] (device).
         view = (view_w, view_h, left, flip_horizontally): the boxes are expressed in the reference VideoReader's
@@ -117,6 +118,13 @@ class BatchedSignalProcessor:
         assert S == self.S and 1 <= T <= self.Tmax and boxes.shape == (S, T, self.R, 4)
         if view is not None:
             boxes = ops.view_boxes(boxes.contiguous(), *view)
+        if resize_to is not None:
+            # boxes live in the frame cv2.resize(frame, (dst_w, dst_h)) would produce (video_reader.py:95-96); pixels are
+            # generated on the fly with OpenCV's integer bilinear arithmetic, the resized frame is never materialised
+            dst_h, dst_w = resize_to
+            val, _ = ops.roi_sample_resized(frames.view(S * T, *frames.shape[2:]), dst_h, dst_w,
+                                            boxes.reshape(S * T, self.R, 4).contiguous(), self.color_channel)
+            return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
         if nv12_size is not None:
             H, W = nv12_size
             val, _ = ops.roi_sample_nv12(frames.view(S * T, *frames.shape[2:]), H, W, boxes.reshape(S * T, self.R, 4).contiguous(),

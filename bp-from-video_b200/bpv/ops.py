@@ -247,3 +247,20 @@ def roi_sample_nv12(frames: torch.Tensor, H: int, W: int, boxes: torch.Tensor, m
     check(lib().bpv_roi_sample_nv12(ptr(frames), fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode), ptr(sums),
                                     ptr(out_value), stream_handle()), 'bpv_roi_sample_nv12')
     return out_value, sums
+
+
+def roi_sample_resized(frames: torch.Tensor, dst_h: int, dst_w: int, boxes: torch.Tensor, mode: int, *, want_sums: bool = False):
+    """F1 on frames the reference would first have resized with cv2.resize(frame, (dst_w, dst_h)) (video_reader.py:95-96):
+    frames uint8 [N, H, W, 3] source frames, boxes int32 [N, R, 4] in the RESIZED frame.  Bit-exact with sampling
+    cv2.resize's output; the resized frame is never materialised."""
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and _dev_accessible(frames)
+    assert frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR'
+    N, H, W, _ = frames.shape
+    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4
+    R = boxes.shape[1]
+    out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
+    sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
+    fstride = frames.stride(0) if N > 1 else H * frames.stride(1)
+    check(lib().bpv_roi_sample_resized_u8(ptr(frames), fstride, frames.stride(1), H, W, int(dst_h), int(dst_w), N, ptr(boxes), R,
+                                          int(mode), ptr(sums), ptr(out_value), stream_handle()), 'bpv_roi_sample_resized_u8')
+    return out_value, sums

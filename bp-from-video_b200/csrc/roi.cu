@@ -621,6 +621,109 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// F1 on a frame the reference would first have resized: VideoReader runs
+// cv2.resize(frame, target_res[::-1]) on file input (video_reader.py:95-96) and the ROI boxes live in the resized
+// frame.  The resized frame is never materialised: every ROI pixel is produced on the fly with OpenCV's own integer
+// bilinear arithmetic (imgproc/src/resize.cpp: 11-bit coefficients from float32 fractions, horizontal pass in 2048ths,
+// vertical pass ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2; exact 2x decimation = INTER_AREA fast
+// path), so the sums equal those of the frame cv2.resize would have produced, bit for bit.
+// One 128-thread CTA per ROI; the ROI's column / row taps (source index + 11-bit weights) are tabulated in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct ResizeTap { int i0, i1; short w0, w1; };
+
+__device__ __forceinline__ ResizeTap resize_tap(int d, double scale, int sn, bool clamp_fraction) {
+  // fx = (float)((dx + 0.5) * scale - 0.5); sx = cvFloor(fx); fx -= sx;  (resize.cpp)
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);   // no FMA contraction: OpenCV rounds the product
+  int s0 = (int)floorf(f);
+  float fr = f - (float)s0;
+  ResizeTap t;
+  if (clamp_fraction) {                       // columns: fraction dropped at the borders
+    if (s0 < 0) { fr = 0.f; s0 = 0; }
+    if (s0 >= sn - 1) { fr = 0.f; s0 = sn - 1; }
+    t.i0 = s0; t.i1 = s0 + 1 < sn ? s0 + 1 : sn - 1;
+  } else {                                    // rows: weights kept, indices clipped
+    t.i0 = s0 < 0 ? 0 : (s0 > sn - 1 ? sn - 1 : s0);
+    t.i1 = s0 + 1 < 0 ? 0 : (s0 + 1 > sn - 1 ? sn - 1 : s0 + 1);
+  }
+  t.w0 = (short)__float2int_rn((1.f - fr) * 2048.f);
+  t.w1 = (short)__float2int_rn(fr * 2048.f);
+  return t;
+}
+
+template <bool WANT_SUMS>
+__global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+                                                          int sh, int sw, int dh, int dw, int R, int mode, long long num_rois,
+                                                          const int32_t* __restrict__ boxes,
+                                                          unsigned long long* __restrict__ out_sums, double* __restrict__ out_value) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  constexpr int THREADS = 128, WARPS = THREADS / 32;
+  const int gt = threadIdx.x;
+  const long long roi = blockIdx.x;
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  const int4 b = __ldg(reinterpret_cast<const int4*>(boxes) + roi);
+  const bool has_box = b.x != BPV_NO_BOX;
+  if (has_box) { py_slice(b.x, b.z, dw, xs, xe); py_slice(b.y, b.w, dh, ys, ye); }   // box lives in the RESIZED frame
+  const int nrows = ye - ys, ncols = xe - xs;
+  ResizeTap* ctap = reinterpret_cast<ResizeTap*>(rsm);          // [ncols]
+  ResizeTap* rtap = ctap + (ncols > 0 ? ncols : 0);             // [nrows]
+  const uint8_t* fp = frames + (roi / R) * frame_stride;
+  const bool area2 = sw == 2 * dw && sh == 2 * dh;
+  uint32_t sB = 0, sG = 0, sR = 0;
+  if (nrows > 0 && ncols > 0) {
+    if (!area2) {
+      const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);
+      for (int c = gt; c < ncols; c += THREADS) ctap[c] = resize_tap(xs + c, scale_x, sw, true);
+      for (int r = gt; r < nrows; r += THREADS) rtap[r] = resize_tap(ys + r, scale_y, sh, false);
+    }
+    __syncthreads();
+    const long long npix = (long long)nrows * ncols;
+    for (long long i = gt; i < npix; i += THREADS) {
+      const int r = (int)(i / ncols), c = (int)(i - (long long)r * ncols);
+      int px[3];
+      if (area2) {
+        const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride + 6LL * (xs + c);
+        const uint8_t* p1 = p0 + row_stride;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) px[ch] = ((int)p0[ch] + (int)p0[3 + ch] + (int)p1[ch] + (int)p1[3 + ch] + 2) >> 2;
+      } else {
+        const ResizeTap tc = ctap[c], tr = rtap[r];
+        const uint8_t* r0 = fp + (long long)tr.i0 * row_stride;
+        const uint8_t* r1 = fp + (long long)tr.i1 * row_stride;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int h0 = (int)r0[3 * tc.i0 + ch] * tc.w0 + (int)r0[3 * tc.i1 + ch] * tc.w1;
+          const int h1 = (int)r1[3 * tc.i0 + ch] * tc.w0 + (int)r1[3 * tc.i1 + ch] * tc.w1;
+          const int v = (((tr.w0 * (h0 >> 4)) >> 16) + ((tr.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+          px[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+      }
+      sB += (uint32_t)px[0]; sG += (uint32_t)px[1]; sR += (uint32_t)px[2];
+    }
+  }
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(ncols > 0 ? ncols : 0);
+  unsigned long long tB = warp_sum_u64(sB), tG = warp_sum_u64(sG), tR = warp_sum_u64(sR);
+  __shared__ unsigned long long part[WARPS][3];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { part[wid][0] = tB; part[wid][1] = tG; part[wid][2] = tR; }
+  __syncthreads();
+  if (gt == 0) {
+    tB = tG = tR = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { tB += part[w][0]; tG += part[w][1]; tR += part[w][2]; }
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tR; o.w = N;
+      *reinterpret_cast<ulonglong4*>(out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(2 * (long long)tG - (long long)tB - (long long)tR + 2 * (long long)N) / (double)(4 * N);
+    out_value[roi] = val;
+  }
+}
+
 }  // namespace bpv
 
 extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_bytes, int64_t pitch_bytes,
@@ -641,6 +744,36 @@ extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_b
                                                                    (unsigned long long*)out_sums, out_value);
   else roi_nv12_kernel<false><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, nullptr, out_value);
   return check_launch("bpv_roi_sample_nv12");
+}
+
+extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                                         int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w, int64_t num_frames,
+                                         const int32_t* boxes, int32_t R, int32_t mode,
+                                         uint64_t* out_sums, double* out_value, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(frames && boxes && out_value, BPV_E_INVALID, "bpv_roi_sample_resized_u8: NULL pointer");
+  BPV_REQUIRE(src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0 && R > 0 && num_frames >= 0, BPV_E_INVALID,
+              "bpv_roi_sample_resized_u8: bad sizes");
+  BPV_REQUIRE(row_stride_bytes >= 3ll * src_w, BPV_E_INVALID, "bpv_roi_sample_resized_u8: row_stride_bytes < 3*src_w");
+  BPV_REQUIRE(mode == BPV_GREEN || mode == BPV_CHROM_GREEN, BPV_E_UNSUPPORTED,
+              "bpv_roi_sample_resized_u8: unknown color channel %d (NotImplementedError, signal_processor.py:185)", mode);
+  BPV_REQUIRE((int64_t)(dst_h + dst_w) * (int64_t)sizeof(ResizeTap) <= 200 * 1024, BPV_E_TOO_LARGE,
+              "bpv_roi_sample_resized_u8: target size too large for the tap tables");
+  if (num_frames == 0) return 0;
+  const long long n = num_frames * R;
+  const int smem = (dst_h + dst_w) * (int)sizeof(ResizeTap);        // worst case: a ROI spanning the whole resized frame
+  static int configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(roi_resized_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(roi_resized_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = smem;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_sums) roi_resized_kernel<true><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, dst_w,
+                                                                      R, mode, n, boxes, (unsigned long long*)out_sums, out_value);
+  else roi_resized_kernel<false><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, dst_w,
+                                                                 R, mode, n, boxes, nullptr, out_value);
+  return check_launch("bpv_roi_sample_resized_u8");
 }
 
 extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,

@@ -95,6 +95,16 @@ int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_bytes, int64
                         int32_t H, int32_t W, int64_t num_frames, const int32_t* boxes, int32_t R, int32_t mode,
                         uint64_t* out_sums, double* out_value, void* stream);
 
+/* F1 on a frame the reference would first have resized: VideoReader applies cv2.resize(frame, target_res[::-1])
+ * (INTER_LINEAR) to file input (video_reader.py:95-96) and boxes are expressed in the resized dst_h x dst_w frame.
+ * The resized frame is never materialised: each ROI pixel is produced with OpenCV's integer bilinear arithmetic
+ * (11-bit coefficients; exact 2x decimation = area fast path), so sums and values equal those of cv2.resize's output
+ * bit for bit.  frames uint8 HWC BGR [num_frames] of src_h x src_w; other arguments as bpv_roi_sample_u8. */
+int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                              int32_t src_h, int32_t src_w, int32_t dst_h, int32_t dst_w, int64_t num_frames,
+                              const int32_t* boxes, int32_t R, int32_t mode,
+                              uint64_t* out_sums, double* out_value, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ROI geometry for batched landmark tensors — replaces SignalProcessor.calc_rois and the ROI smoothing
  *     sg_roi.add_samples + get_means(as_int=True) (signal_processor.py:133-155, 304-305; signal_data.py:60-63).

@@ -98,6 +98,43 @@ def roi_sums(frame, box):
     return int(s[0]), int(s[1]), int(s[2]), int(n)
 
 
+def resize_linear_u8(src, dsize_w, dsize_h):
+    """cv2.resize(src, (dsize_w, dsize_h)) with the default INTER_LINEAR for uint8 HWC images — what VideoReader applies to
+    file input when target_res is set (video_reader.py:95-96) — restated in integer arithmetic
+    (opencv/modules/imgproc/src/resize.cpp: resizeGeneric_ / HResizeLinear / VResizeLinear with 11-bit coefficients;
+    exact 2x decimation takes the INTER_AREA fast path).  Pinned against cv2 in tests/test_oracle_golden.py."""
+    src = np.asarray(src)
+    sh, sw = src.shape[:2]
+    if sw == 2 * dsize_w and sh == 2 * dsize_h:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    def frac(dn, sn):
+        scale = 1.0 / (float(dn) / float(sn))                       # scale = 1 / inv_scale, as cv::resize computes it
+        f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int64)
+        return s0, (f - s0.astype(np.float32)).astype(np.float32)
+
+    def icoef(fr):                                                   # saturate_cast<short>(c * 2048) = round half to even
+        return (np.rint((np.float32(1.0) - fr) * np.float32(2048)).astype(np.int64),
+                np.rint(fr * np.float32(2048)).astype(np.int64))
+    x0, fx = frac(dsize_w, sw)
+    lo = x0 < 0
+    fx[lo] = 0; x0[lo] = 0
+    hi = x0 >= sw - 1
+    fx[hi] = 0; x0[hi] = sw - 1
+    a0, a1 = icoef(fx)
+    x1 = np.minimum(x0 + 1, sw - 1)
+    y0, fy = frac(dsize_h, sh)                                       # rows: weights kept, indices clipped
+    b0, b1 = icoef(fy)
+    y1 = np.clip(y0 + 1, 0, sh - 1)
+    y0 = np.clip(y0, 0, sh - 1)
+    s = src.astype(np.int64)
+    h = s[:, x0] * a0[None, :, None] + s[:, x1] * a1[None, :, None]
+    out = (((b0[:, None, None] * (h[y0] >> 4)) >> 16) + ((b1[:, None, None] * (h[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def nv12_to_bgr(nv12, H, W):
     """uint8 [3H/2, W] NV12 -> uint8 [H, W, 3] BGR exactly as OpenCV's cvtColor(COLOR_YUV2BGR_NV12) — the conversion a
     cv2.VideoCapture applies to decoder output before the reference sees the frame (video_reader.py:93).  Integer BT.601,

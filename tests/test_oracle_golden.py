@@ -61,3 +61,15 @@ def test_nv12_conversion_matches_opencv():
         nv = np.full((12, 8), fill, np.uint8)
         nv[8:] = rng.choice([0, 255, 128], size=(4, 8)).astype(np.uint8)
         assert np.array_equal(orc.nv12_to_bgr(nv, 8, 8), cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12)), fill
+
+
+def test_resize_restatement_matches_opencv():
+    """The oracle's cv2.resize (INTER_LINEAR, uint8) restatement against OpenCV itself: bit-exact for down- and
+    up-scaling, mixed, identity, exact 2x decimation (area fast path) and tiny images."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(21)
+    for (sh, sw), (dh, dw) in [((48, 64), (30, 40)), ((48, 64), (96, 128)), ((270, 480), (180, 320)), ((37, 53), (50, 31)),
+                               ((100, 100), (333, 77)), ((64, 64), (32, 32)), ((64, 64), (32, 33)), ((5, 7), (50, 70)),
+                               ((90, 160), (90, 160)), ((216, 384), (54, 96))]:
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(orc.resize_linear_u8(src, dw, dh), cv2.resize(src, (dw, dh))), ((sh, sw), (dh, dw))

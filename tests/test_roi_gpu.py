@@ -173,3 +173,26 @@ def test_nv12_roi_sampling_equals_bgr_of_converted_frame(shape):
         _check(bgr, boxes, mode, val.cpu().numpy(), sums.cpu().numpy())
         val2, _ = ops.roi_sample_nv12(torch.from_numpy(buf).cuda(), H, W, torch.from_numpy(boxes).cuda(), mode)
         assert h.same(val2.cpu().numpy(), val.cpu().numpy())
+
+
+@pytest.mark.parametrize('src,dst', [((48, 64), (30, 40)), ((48, 64), (96, 128)), ((90, 160), (45, 80)), ((37, 53), (50, 31)),
+                                     ((120, 160), (120, 160))])
+def test_resized_roi_sampling_equals_sampling_of_cv2_resize_output(src, dst):
+    """F1 with the VideoReader resize (cv2.resize, INTER_LINEAR; video_reader.py:95-96) fused in front —
+    boxes in the resized frame, pixels produced on the fly — equals the reference sampling of the resized frame (oracle
+    restatement of cv2.resize, pinned against cv2 in the CPU suite): integer sums and float64 samples bit-exact."""
+    from bpv import ops
+    (sh, sw), (dh, dw) = src, dst
+    rng = np.random.default_rng(sh * dw + sw)
+    N, R = 4, 4
+    frames = rng.integers(0, 256, (N, sh, sw, 3), dtype=np.uint8)
+    boxes = np.stack([rng.integers(-dw - 3, dw + 5, (N, R)), rng.integers(-dh - 3, dh + 5, (N, R)),
+                      rng.integers(-dw - 3, dw + 5, (N, R)), rng.integers(-dh - 3, dh + 5, (N, R))], axis=-1).astype(np.int32)
+    boxes[0, 0] = (0, 0, dw, dh)
+    boxes[1, 1] = (np.iinfo(np.int32).min, 0, 0, 0)
+    boxes[2, 2] = (dw - 2, dh - 2, dw, dh)
+    boxes[3, 3] = (0, 0, 1, 1)
+    resized = np.stack([orc.resize_linear_u8(frames[f], dw, dh) for f in range(N)])
+    for mode in (orc.GREEN, orc.CHROM_GREEN):
+        val, sums = ops.roi_sample_resized(torch.from_numpy(frames).cuda(), dh, dw, torch.from_numpy(boxes).cuda(), mode, want_sums=True)
+        _check(resized, boxes, mode, val.cpu().numpy(), sums.cpu().numpy())
