@@ -487,19 +487,28 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
   const int kstep = col_live ? kcol : 0;             // kcol <= n/2 for live columns: one conditional subtraction keeps idx < n
   const int kskip = (int)((12LL * kstep) % n);
   int idx = (int)((4LL * bch * kstep) % n);
-  // this thread's A item: row arow (consecutive lanes = consecutive rows), chunk ach of every k block (4 samples)
-  const int arow = tid & 127, ach = tid >> 7;
+  // this thread's A items: row arow, samples {2q, 2q+1} and {8+2q, 8+2q+1} of every 16-sample k block (q = tid & 3):
+  // the four lanes of a row read 64 contiguous bytes per 16-byte vector load, so a warp-level load touches 8 rows x 2
+  // full sectors instead of 32 scattered sectors (the per-row loads were the bottleneck: rows are 8 W bytes apart)
+  const int arow = tid >> 2, aq = tid & 3;
   const long long asig = sig0 + arow;
   const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
+  const bool vec_ok = (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0;   // 16-byte aligned rows
   int mybad = 0;
   const int NB = (n + DTC_KB - 1) / DTC_KB;
   // software prefetch: the samples of the NEXT k block are requested before this block is converted and issued
   double cur[4], nxt[4];
   auto fetch = [&](int kb, double (&dst)[4]) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = kb * DTC_KB + 4 * ach + e;
-      dst[e] = (j < n && asig < nsig) ? ay[j] : 0.0;
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int j = kb * DTC_KB + 8 * hlf + 2 * aq;
+      if (asig < nsig && j + 1 < n && vec_ok) {
+        const double2 v = *reinterpret_cast<const double2*>(ay + j);
+        dst[2 * hlf] = v.x; dst[2 * hlf + 1] = v.y;
+      } else {
+        dst[2 * hlf] = (asig < nsig && j < n) ? ay[j] : 0.0;
+        dst[2 * hlf + 1] = (asig < nsig && j + 1 < n) ? ay[j + 1] : 0.0;
+      }
     }
   };
   fetch(0, cur);
@@ -521,8 +530,12 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_kernel(const double* __
         hv[e] = tc_hi((float)v);
         lv[e] = (float)(v - (double)hv[e]);
       }
-      Ahi[ach * TC_M + arow] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      Alo[ach * TC_M + arow] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      // samples 2q, 2q+1 -> chunk q >> 1, slots 2 (q & 1) ..; samples 8 + 2q .. -> chunk 2 + (q >> 1)
+      float2* Ah2 = reinterpret_cast<float2*>(Ahi);
+      float2* Al2 = reinterpret_cast<float2*>(Alo);
+      const int o0 = (((aq >> 1) * TC_M + arow) << 1) + (aq & 1), o1 = (((2 + (aq >> 1)) * TC_M + arow) << 1) + (aq & 1);
+      Ah2[o0] = make_float2(hv[0], hv[1]); Al2[o0] = make_float2(lv[0], lv[1]);
+      Ah2[o1] = make_float2(hv[2], hv[3]); Al2[o1] = make_float2(lv[2], lv[3]);
     }
     {
       float4 t4[4];
