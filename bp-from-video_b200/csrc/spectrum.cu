@@ -680,6 +680,91 @@ __global__ void __launch_bounds__(128) ls_peak_kernel(const double* __restrict__
     for (int k = tid; k < F; k += blockDim.x) spec_f[sig * max_bins + k] = (float)ls_freq(k, F, p.min_freq, p.max_freq);
 }
 
+
+// Warp-per-signal version of the Lomb-Scargle peak pass (default): the CTA-per-signal kernel above spends most of its time
+// in __syncthreads between short phases (gather, three block reductions, candidate list); here every phase is warp-local.
+// smem per warp: doubles ts[W] | ys[W].
+constexpr int LSP_WPB = 4;
+__global__ void __launch_bounds__(32 * LSP_WPB) ls_peak_warp_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+                                                                    const bpv_window_params p, int max_bins, long long nsig,
+                                                                    float* __restrict__ spec_f, float* __restrict__ psd,
+                                                                    int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
+                                                                    double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
+  extern __shared__ __align__(16) double sm[];
+  const int W = p.window, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long sig = (long long)blockIdx.x * LSP_WPB + wid;
+  if (sig >= nsig) return;
+  double* xs = sm + (size_t)wid * 2 * W;
+  double* ys = xs + W;
+  const double* px = proc_x + sig * W;
+  const double* py = proc_y + sig * W;
+  for (int k = lane; k < W; k += 32) { xs[k] = px[k]; ys[k] = py[k]; }
+  __syncwarp();
+  int n = 0, m = 0;
+  double xfirst = 0.0, xlast = 0.0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int k0 = 0; k0 < W; k0 += 32) {
+    const int k = k0 + lane;
+    double x = nan_f64(), y = nan_f64();
+    if (k < W) { x = xs[k]; y = ys[k]; }
+    const bool fx = isfinite(x), fy = isfinite(y);
+    const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+    if (bx) {
+      const double xf = shfl_dd(x, __ffs(bx) - 1), xl = shfl_dd(x, 31 - __clz(bx));
+      if (m == 0) xfirst = xf;
+      xlast = xl;
+    }
+    __syncwarp();
+    if (fy) { const int i = n + __popc(by & lt); ys[i] = y; xs[i] = x; }
+    __syncwarp();
+    n += __popc(by); m += __popc(bx);
+  }
+  const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
+  if (!(n >= 2 && isfinite(fs))) {
+    if (lane == 0) { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+    return;
+  }
+  const int F = p.ls_num_freqs > 0 ? p.ls_num_freqs : n;
+  float* row = psd + sig * max_bins;
+  float bv = -INFINITY; int cnt = 0;
+  for (int k = lane; k < F; k += 32) { const float v = row[k]; if (isfinite(v)) { ++cnt; bv = fmaxf(bv, v); } }
+  for (int o = 16; o > 0; o >>= 1) { bv = fmaxf(bv, __shfl_xor_sync(0xffffffffu, bv, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  // moments for the float64 evaluation (relative time; Y, YY as scipy Eq. 7 / 10; centred second moment)
+  const double t0 = xs[0];
+  double a = 0.0;
+  for (int j = lane; j < n; j += 32) a += ys[j];
+  const double Y = warp_sum(a) / (double)n;
+  double q2 = 0.0;
+  for (int j = lane; j < n; j += 32) { const double d = ys[j] - Y; q2 = fma(d, d, q2); }
+  const double YY = warp_sum(q2) / (double)n;
+  for (int j = lane; j < n; j += 32) xs[j] -= t0;
+  __syncwarp();
+  const bool all = n < LS_SMALL_N || cnt < 2;
+  double best = -INFINITY; int bi = 0x7fffffff, nf64 = 0;
+  for (int k0 = 0; k0 < F; k0 += 32) {
+    const int k = k0 + lane;
+    bool cand = false;
+    if (k < F) { const float v = row[k]; cand = all || (isfinite(v) && v >= bv - LS_DELTA); }
+    unsigned mk = __ballot_sync(0xffffffffu, cand);
+    while (mk) {
+      const int kc = k0 + __ffs(mk) - 1;
+      mk &= mk - 1;
+      const double v = ls_eval_f64(xs, ys, n, ls_freq(kc, F, p.min_freq, p.max_freq), Y, YY);
+      if (lane == 0) row[kc] = (float)v;
+      if (isfinite(v)) { ++nf64; if (v > best || (v == best && kc < bi)) { best = v; bi = kc; } }
+    }
+  }
+  const int nfinite = all ? nf64 : cnt;
+  if (lane == 0) {
+    num_bins[sig] = F;
+    if (nfinite >= 2 && bi != 0x7fffffff) {
+      peak_idx[sig] = bi; peak_freq[sig] = ls_freq(bi, F, p.min_freq, p.max_freq); peak_mag[sig] = best;
+    } else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
+  }
+  if (all && spec_f)
+    for (int k = lane; k < F; k += 32) spec_f[sig * max_bins + k] = (float)ls_freq(k, F, p.min_freq, p.max_freq);
+}
+
 }  // namespace bpv
 
 extern "C" int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins) {
@@ -774,6 +859,17 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   dim3 grid((unsigned)nsig, (Fmax + LS_NF * bd - 1) / (LS_NF * bd));
   ls_coarse_kernel<<<grid, bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
   if (int rc = check_launch("ls_coarse_kernel")) return rc;
+  const size_t smem_w = (size_t)LSP_WPB * 2 * W * sizeof(double);
+  if (smem_w <= 200 * 1024) {          // warp per signal
+    static size_t configured_w = 0;
+    if (smem_w > 48 * 1024 && smem_w > configured_w) {
+      cudaFuncSetAttribute(ls_peak_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+      configured_w = smem_w;
+    }
+    ls_peak_warp_kernel<<<(unsigned)((nsig + LSP_WPB - 1) / LSP_WPB), 32 * LSP_WPB, smem_w, st>>>(proc_x, proc_y, *p, max_bins, nsig, spec_f,
+                                                                                                 psd, num_bins, peak_idx, peak_freq, peak_mag);
+    return check_launch("ls_peak_warp_kernel");
+  }
   ls_peak_kernel<<<(unsigned)nsig, 128, smem_p, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd, num_bins, peak_idx, peak_freq, peak_mag);
   return check_launch("ls_peak_kernel");
 }
