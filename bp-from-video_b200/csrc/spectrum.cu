@@ -493,14 +493,14 @@ __device__ double ls_eval_f64(const double* __restrict__ t, const double* __rest
   return 2.0 * (a * YC + b * YS) * (0.5 / YY);
 }
 
-// Coarse fp32 pass.  grid = (nsig, ceil(Fmax / (LS_NF * blockDim))), thread t of tile T owns the LS_NF
+// Coarse fp32 pass (LS_NF = 4 or 8, chosen per launch).  grid = (nsig, ceil(Fmax / (LS_NF * blockDim))), thread t of tile T owns the LS_NF
 // frequencies k = T*LS_NF*blockDim + t + m*blockDim, m = 0..LS_NF-1.  The grid is uniform, so consecutive
 // frequencies of a thread differ by D = blockDim*df and exp(i*2pi*(f+D)*t_j) = exp(i*2pi*f*t_j) * rot_j with
 // rot_j = exp(i*2pi*D*t_j) shared by the whole CTA: one sincos (2 MUFU + exact phase reduction) per sample
 // per thread, then LS_NF-1 complex rotations (4 FP32 ops each) — the kernel is issue-bound, and this cuts
 // the instructions per (sample, frequency) pair from ~26 to ~13.
 // smem: doubles xs[W] | ys[W] (gather scratch), then float4 {t_hi, t_lo, y - mean, 0}[W], float2 rot[W].
-constexpr int LS_NF = 8;
+template <int LS_NF>
 __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                         const bpv_window_params p, int max_bins,
                                                         float* __restrict__ spec_f, float* __restrict__ psd) {
@@ -852,12 +852,22 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   const size_t smem_c = (size_t)W * (2 * sizeof(double) + sizeof(float4) + sizeof(float2));
   const size_t smem_p = (size_t)W * 2 * sizeof(double) + (size_t)max_bins * (sizeof(double) + sizeof(int));
   BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
-  if (smem_c > 48 * 1024) cudaFuncSetAttribute(ls_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+  if (smem_c > 48 * 1024) {
+    cudaFuncSetAttribute(ls_coarse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(ls_coarse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+  }
   if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-  int bd = ((Fmax + LS_NF - 1) / LS_NF + 31) / 32 * 32;     // threads per CTA: enough for Fmax in one tile, up to 128
-  if (bd > 128) bd = 128;
-  dim3 grid((unsigned)nsig, (Fmax + LS_NF * bd - 1) / (LS_NF * bd));
-  ls_coarse_kernel<<<grid, bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
+  // frequencies per thread (4 or 8): the one with the smaller padded cost tiles * NF * threads * (instructions per pair)
+  auto plan = [&](int nf, int& bd, int& tiles) {
+    bd = ((Fmax + nf - 1) / nf + 31) / 32 * 32;          // threads per CTA: enough for Fmax in one tile, up to 128
+    if (bd > 128) bd = 128;
+    tiles = (Fmax + nf * bd - 1) / (nf * bd);
+    return (double)tiles * nf * bd * (nf == 8 ? 11.5 : 13.0);
+  };
+  int bd4, t4, bd8, t8;
+  const double c4 = plan(4, bd4, t4), c8 = plan(8, bd8, t8);
+  if (c8 < c4) ls_coarse_kernel<8><<<dim3((unsigned)nsig, t8), bd8, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
+  else ls_coarse_kernel<4><<<dim3((unsigned)nsig, t4), bd4, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
   if (int rc = check_launch("ls_coarse_kernel")) return rc;
   const size_t smem_w = (size_t)LSP_WPB * 2 * W * sizeof(double);
   if (smem_w <= 200 * 1024) {          // warp per signal
