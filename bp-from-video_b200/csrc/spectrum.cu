@@ -493,7 +493,7 @@ __device__ double ls_eval_f64(const double* __restrict__ t, const double* __rest
   return 2.0 * (a * YC + b * YS) * (0.5 / YY);
 }
 
-// Coarse fp32 pass (LS_NF = 4 or 8, chosen per launch).  grid = (nsig, ceil(Fmax / (LS_NF * blockDim))), thread t of tile T owns the LS_NF
+// Coarse fp32 pass (LS_NF = 4..8, chosen per launch).  grid = (nsig, ceil(Fmax / (LS_NF * blockDim))), thread t of tile T owns the LS_NF
 // frequencies k = T*LS_NF*blockDim + t + m*blockDim, m = 0..LS_NF-1.  The grid is uniform, so consecutive
 // frequencies of a thread differ by D = blockDim*df and exp(i*2pi*(f+D)*t_j) = exp(i*2pi*f*t_j) * rot_j with
 // rot_j = exp(i*2pi*D*t_j) shared by the whole CTA: one sincos (2 MUFU + exact phase reduction) per sample
@@ -854,20 +854,32 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
   if (smem_c > 48 * 1024) {
     cudaFuncSetAttribute(ls_coarse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(ls_coarse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(ls_coarse_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(ls_coarse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
     cudaFuncSetAttribute(ls_coarse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
   }
   if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-  // frequencies per thread (4 or 8): the one with the smaller padded cost tiles * NF * threads * (instructions per pair)
-  auto plan = [&](int nf, int& bd, int& tiles) {
-    bd = ((Fmax + nf - 1) / nf + 31) / 32 * 32;          // threads per CTA: enough for Fmax in one tile, up to 128
+  // frequencies per thread NF in 4..8 and threads per CTA (multiple of 32, <= 128): the plan with the smallest padded cost
+  // tiles * NF * threads * (instructions per (sample, frequency) slot ~ 10 + 12 / NF: one sincos per sample and thread,
+  // 6 accumulations per slot, NF - 1 rotations)
+  int best_nf = 4, best_bd = 128, best_tiles = 1;
+  double best_cost = 1e300;
+  for (int nf = 4; nf <= 8; ++nf) {
+    int bd = ((Fmax + nf - 1) / nf + 31) / 32 * 32;          // enough threads for Fmax in one tile, up to 128
     if (bd > 128) bd = 128;
-    tiles = (Fmax + nf * bd - 1) / (nf * bd);
-    return (double)tiles * nf * bd * (nf == 8 ? 11.5 : 13.0);
-  };
-  int bd4, t4, bd8, t8;
-  const double c4 = plan(4, bd4, t4), c8 = plan(8, bd8, t8);
-  if (c8 < c4) ls_coarse_kernel<8><<<dim3((unsigned)nsig, t8), bd8, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
-  else ls_coarse_kernel<4><<<dim3((unsigned)nsig, t4), bd4, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd);
+    const int tiles = (Fmax + nf * bd - 1) / (nf * bd);
+    const double cost = (double)tiles * nf * bd * (10.0 + 12.0 / nf);
+    if (cost < best_cost) { best_cost = cost; best_nf = nf; best_bd = bd; best_tiles = tiles; }
+  }
+  const dim3 grid((unsigned)nsig, best_tiles);
+  switch (best_nf) {
+    case 4: ls_coarse_kernel<4><<<grid, best_bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd); break;
+    case 5: ls_coarse_kernel<5><<<grid, best_bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd); break;
+    case 6: ls_coarse_kernel<6><<<grid, best_bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd); break;
+    case 7: ls_coarse_kernel<7><<<grid, best_bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd); break;
+    default: ls_coarse_kernel<8><<<grid, best_bd, smem_c, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd); break;
+  }
   if (int rc = check_launch("ls_coarse_kernel")) return rc;
   const size_t smem_w = (size_t)LSP_WPB * 2 * W * sizeof(double);
   if (smem_w <= 200 * 1024) {          // warp per signal
