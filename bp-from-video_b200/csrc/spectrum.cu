@@ -575,9 +575,13 @@ __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict
     if (k >= F) break;
     const double dC = C[m] * w, dS = S[m] * w, dCC = CC[m] * w, dCS = CS[m] * w, dYC = YC[m] * w, dYS = YS[m] * w;
     const double cc0 = dCC - dC * dC, ss0 = (1.0 - dCC) - dS * dS, cs0 = dCS - dC * dS;
-    const double tau = 0.5 * atan2(2.0 * cs0, cc0 - ss0);
+    // cos / sin of tau = 0.5 * atan2(2 cs0, cc0 - ss0) by the half-angle formulas (tau in (-pi/2, pi/2]: cos >= 0, the
+    // sign of sin is the sign of cs0), each branch free of cancellation; no atan2 / sincos on the per-frequency path
+    const double s2 = 2.0 * cs0, c2 = cc0 - ss0, hyp = hypot(s2, c2);
     double st, ct;
-    sincos(tau, &st, &ct);
+    if (!(hyp > 0.0)) { ct = 1.0; st = 0.0; }                    // atan2(0, 0) = 0
+    else if (c2 >= 0.0) { ct = sqrt(0.5 * (1.0 + c2 / hyp)); st = 0.5 * (s2 / hyp) / ct; }
+    else { st = copysign(sqrt(0.5 * (1.0 - c2 / hyp)), s2); ct = 0.5 * (s2 / hyp) / st; }
     const double YCt = ct * dYC + st * dYS, YSt = ct * dYS - st * dYC;
     const double Ct = ct * dC + st * dS, St = ct * dS - st * dC;
     const double CCraw = ct * ct * dCC + 2.0 * ct * st * dCS + st * st * (1.0 - dCC);
