@@ -93,7 +93,7 @@ class BatchedSignalProcessor:
         need = max(_cabi.lib().bpv_window_workspace_bytes(p), _cabi.lib().bpv_spectrum_workspace_bytes(p, self._mb), 16)
         self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self._spec = self._xc = None
-        self.launches_per_step = 0
+        self.launches_per_step = self._extra_launches = 0
         # sg_bpm / sg_ptt histories and their running means on the device (0 = off)
         self.peak_max_samples = int(peak_max_samples)
         if self.peak_max_samples:
@@ -116,8 +116,10 @@ class BatchedSignalProcessor:
         with OpenCV's integer BT.601 conversion, i.e. as from the BGR frame cv2.VideoCapture would have produced."""
         S, T = frames.shape[:2]
         assert S == self.S and 1 <= T <= self.Tmax and boxes.shape == (S, T, self.R, 4)
+        self._extra_launches = 0
         if view is not None:
             boxes = ops.view_boxes(boxes.contiguous(), *view)
+            self._extra_launches = 1
         if resize_to is not None:
             # boxes live in the frame cv2.resize(frame, (dst_w, dst_h)) would produce (video_reader.py:95-96); pixels are
             # generated on the fly with OpenCV's integer bilinear arithmetic, the resized frame is never materialised
@@ -193,7 +195,12 @@ class BatchedSignalProcessor:
         if (self.transform == _cabi.PGRAM_WELCH and not self.store_arrays and 256 <= self.W <= 383
                 and os.environ.get('BPV_WELCH_TC', '') == '1'):
             n_spec = 2                  # welch_tc_kernel (tensor cores) + welch_warp_kernel for the windows it flags
-        self.launches_per_step = (1 if _count_roi else 0) + 1 + n_pre + n_spec + (1 if self.P else 0)
+        if self.transform == _cabi.DFT_RFFT and 16 <= self.W <= 2048:
+            env = os.environ.get('BPV_DFT_TC')
+            interp = any(m in (_cabi.INTERP_LINEAR, _cabi.INTERP_CUBIC) for m in self.methods)
+            if (env[:1] == '1') if env is not None else interp:
+                n_spec = 3              # dft_tc_kernel + dft_peak_kernel + spectrum_dense_kernel for the flagged windows
+        self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + 1 + n_pre + n_spec + (1 if self.P else 0)
         arrays = {}
         if self.store_arrays:
             arrays = dict(proc_x=px, proc_y=py, freqs=sp['freqs'], mags=sp['mags'], num_bins=sp['num_bins'],

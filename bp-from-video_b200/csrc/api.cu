@@ -1,5 +1,8 @@
 // libbpv: error plumbing + version.
 #include <stdarg.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 
 namespace bpv {
@@ -9,6 +12,26 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device): remember what each pair was raised
+// to, so that repeated launches skip the driver call and a host process that drives several GPUs (or several
+// threads) still configures every one of them.
+int ensure_dyn_smem(const void* kernel, size_t bytes, bool max_carveout) {
+  if (bytes <= 48 * 1024 && !max_carveout) return 0;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> raised;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = raised[{kernel, dev}];
+  if (bytes <= have) return 0;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && max_carveout) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B of dynamic shared memory): %s", bytes, cudaGetErrorString(e)); return (int)e; }
+  have = bytes;
+  return 0;
 }
 }  // namespace bpv
 

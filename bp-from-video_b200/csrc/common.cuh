@@ -9,6 +9,8 @@
 namespace bpv {
 
 void set_error(const char* fmt, ...);
+// Opt `kernel` into `bytes` of dynamic shared memory on the current device (api.cu); 0 or a CUDA error code.
+int ensure_dyn_smem(const void* kernel, size_t bytes, bool max_carveout = false);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -310,9 +310,8 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) welch_tc_kernel(const double* 
   // ---- epilogue: thread = signal row (warps 0..3 <-> TMEM lanes 0..127)
   if (tid < TC_M) {
     const int row = tid;
-    const long long sig = sig0 + row;
     const bool ok = s_ok[row] != 0;
-    const double fs = s_fs[row], mean = s_mean[row];
+    const double fs = s_fs[row];
     const float scale = ok ? (float)(1.0 / (fs * *s_sw)) : 0.f;
     // pass 1: fp32 maximum of the one-sided density
     float pmax = -INFINITY;
@@ -413,12 +412,7 @@ __global__ void __launch_bounds__(WTC_THREADS, 1) welch_tc_kernel(const double* 
 
 int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
                     double* peak_freq, double* peak_mag, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(welch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTC_SMEM);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)welch_tc_kernel, WTC_SMEM)) return rc;
   welch_tc_kernel<<<(unsigned)((nsig + TC_M - 1) / TC_M), WTC_THREADS, WTC_SMEM, st>>>(proc_x, proc_y, W, nsig, num_bins, peak_idx,
                                                                                       peak_freq, peak_mag);
   return check_launch("welch_tc_kernel");
@@ -440,7 +434,6 @@ int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long
 // ---------------------------------------------------------------------------------------------
 constexpr int DTC_THREADS = 512;
 constexpr int DTC_KB = 16;                               // samples per k block
-constexpr int DTC_MAXW = 2048;
 constexpr float DFT_TC_BAND = 1.0e-4f;                   // relative band below the fp32 maximum (3xTF32: 4e-6 of the maximum)
 constexpr int DTC_STAGE = 48 * 1024;                     // A hi | A lo [4][128][4] + B hi | B lo [4][256][4]
 constexpr int DTC_OFF_TW = 2 * DTC_STAGE;                // double2 [W]
@@ -674,17 +667,8 @@ __global__ void __launch_bounds__(128) dft_peak_kernel(const double* __restrict_
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
                   int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, cudaStream_t st) {
   const int smem = dtc_smem(W), smem_p = W * 16;
-  static int configured = 0, configured_p = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(dft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
-  if (smem_p > 48 * 1024 && smem_p > configured_p) {
-    cudaError_t e = cudaFuncSetAttribute(dft_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured_p = smem_p;
-  }
+  if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
+  if (int rc = ensure_dyn_smem((const void*)dft_peak_kernel, smem_p)) return rc;
   const int F = W / 2 + 1;
   dim3 grid((unsigned)((nsig + TC_M - 1) / TC_M), (unsigned)((F + 127) / 128));
   dft_tc_kernel<<<grid, DTC_THREADS, smem, st>>>(proc_y, W, nsig, max_bins, mags, num_bins);
@@ -700,12 +684,7 @@ extern "C" int bpv_dft256_tc(const float* z, int32_t rows, float* d, void* strea
   using namespace bpv;
   BPV_REQUIRE(z && d && rows >= 0, BPV_E_INVALID, "bpv_dft256_tc: bad arguments");
   if (rows == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dft256_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)dft256_tc_kernel, TC_SMEM)) return rc;
   dft256_tc_kernel<<<(rows + TC_M - 1) / TC_M, TC_M, TC_SMEM, (cudaStream_t)stream>>>(z, rows, d);
   return check_launch("bpv_dft256_tc");
 }

@@ -474,14 +474,9 @@ static void launch_staged(const RoiArgs& a, int stage_bytes, cudaStream_t st) {
   const int smem = STAGE == 1 ? THREADS * K * 16 : stage_bytes;
   auto k1 = roi_staged_kernel<THREADS, K, true, STAGE>;
   auto k0 = roi_staged_kernel<THREADS, K, false, STAGE>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_done = true;
-  }
+  // a failed opt-in is not fatal here: the launch below then fails and check_launch() reports it
+  (void)ensure_dyn_smem((const void*)k1, 200 * 1024, true);
+  (void)ensure_dyn_smem((const void*)k0, 200 * 1024, true);
   if (a.out_sums) k1<<<(unsigned)a.num_rois, THREADS, smem, st>>>(a, stage_bytes);
   else k0<<<(unsigned)a.num_rois, THREADS, smem, st>>>(a, stage_bytes);
 }
@@ -500,12 +495,8 @@ static void launch_rows(const RoiArgs& a, unsigned grid, cudaStream_t st) {
   size_t smem = 0;
   if (LDMODE == 2) {
     smem = 120 * 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(roi_rows_kernel<GROUP, 4, true, LDMODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(roi_rows_kernel<GROUP, 4, false, LDMODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_done = true;
-    }
+    (void)ensure_dyn_smem((const void*)roi_rows_kernel<GROUP, 4, true, LDMODE, 4>, smem);
+    (void)ensure_dyn_smem((const void*)roi_rows_kernel<GROUP, 4, false, LDMODE, 4>, smem);
   }
   if (a.out_sums) roi_rows_kernel<GROUP, 4, true, LDMODE, 4><<<grid, 256, smem, st>>>(a);
   else roi_rows_kernel<GROUP, 4, false, LDMODE, 4><<<grid, 256, smem, st>>>(a);
@@ -737,6 +728,7 @@ extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_b
               "bpv_roi_sample_nv12: pitch < W or frame stride < pitch * 3H/2");
   BPV_REQUIRE(mode == BPV_GREEN || mode == BPV_CHROM_GREEN, BPV_E_UNSUPPORTED,
               "bpv_roi_sample_nv12: unknown color channel %d (NotImplementedError, signal_processor.py:185)", mode);
+  BPV_REQUIRE(num_frames * (int64_t)R <= INT32_MAX, BPV_E_TOO_LARGE, "bpv_roi_sample_nv12: more than 2^31-1 ROIs in one call");
   if (num_frames == 0) return 0;
   const long long n = num_frames * R;
   cudaStream_t st = (cudaStream_t)stream;
@@ -759,15 +751,12 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
               "bpv_roi_sample_resized_u8: unknown color channel %d (NotImplementedError, signal_processor.py:185)", mode);
   BPV_REQUIRE((int64_t)(dst_h + dst_w) * (int64_t)sizeof(ResizeTap) <= 200 * 1024, BPV_E_TOO_LARGE,
               "bpv_roi_sample_resized_u8: target size too large for the tap tables");
+  BPV_REQUIRE(num_frames * (int64_t)R <= INT32_MAX, BPV_E_TOO_LARGE, "bpv_roi_sample_resized_u8: more than 2^31-1 ROIs in one call");
   if (num_frames == 0) return 0;
   const long long n = num_frames * R;
   const int smem = (dst_h + dst_w) * (int)sizeof(ResizeTap);        // worst case: a ROI spanning the whole resized frame
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(roi_resized_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(roi_resized_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<true>, smem)) return rc;
+  if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<false>, smem)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (out_sums) roi_resized_kernel<true><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, dst_w,
                                                                       R, mode, n, boxes, (unsigned long long*)out_sums, out_value);
@@ -788,6 +777,8 @@ extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* fr
   BPV_REQUIRE(H > 0 && W > 0 && R > 0 && num_frames >= 0, BPV_E_INVALID, "bpv_roi_sample_u8: bad H/W/R/num_frames");
   BPV_REQUIRE((int64_t)H * W * 3 < (1ll << 31), BPV_E_TOO_LARGE, "bpv_roi_sample_u8: frame larger than 2 GiB");
   BPV_REQUIRE(row_stride_bytes >= 3ll * W, BPV_E_INVALID, "bpv_roi_sample_u8: row_stride_bytes < 3*W");
+  BPV_REQUIRE(frame_stride_bytes >= 0, BPV_E_INVALID, "bpv_roi_sample_u8: negative frame_stride_bytes");   // 0 = one frame, many box sets
+  BPV_REQUIRE(num_frames * (int64_t)R <= INT32_MAX, BPV_E_TOO_LARGE, "bpv_roi_sample_u8: more than 2^31-1 ROIs in one call");
   BPV_REQUIRE(mode == BPV_GREEN || mode == BPV_CHROM_GREEN, BPV_E_UNSUPPORTED,
               "bpv_roi_sample_u8: unknown color channel %d (NotImplementedError, signal_processor.py:185)", mode);
   if (num_frames == 0) return 0;

@@ -41,7 +41,7 @@ __device__ SigInfo gather_signal(const double* __restrict__ px, const double* __
   for (int k = tid; k < W; k += blockDim.x) { xs[k] = px[k]; ys[k] = py[k]; }
   __syncthreads();
   if (tid < 32) {
-    int n = 0, m = 0, kfirst = 0x7fffffff, klast = -1;
+    int n = 0, m = 0, kfirst = 0x7fffffff;
     double xfirst = nan_f64(), xlast = nan_f64();
     const unsigned lt = (1u << lane) - 1u;
     for (int k0 = 0; k0 < W; k0 += 32) {
@@ -52,7 +52,7 @@ __device__ SigInfo gather_signal(const double* __restrict__ px, const double* __
       const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
       if (bx) {
         if (kfirst == 0x7fffffff) { kfirst = k0 + __ffs(bx) - 1; xfirst = __shfl_sync(0xffffffffu, x, __ffs(bx) - 1); }
-        klast = k0 + 31 - __clz(bx); xlast = __shfl_sync(0xffffffffu, x, 31 - __clz(bx));
+        xlast = __shfl_sync(0xffffffffu, x, 31 - __clz(bx));
       }
       __syncwarp();
       if (fy) { const int idx = n + __popc(by & lt); ys[idx] = y; xs[idx] = x; }
@@ -796,10 +796,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
     BPV_REQUIRE(!spec_mag || max_bins >= need, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, need);
     if (p->transform == BPV_PGRAM_WELCH && W <= 512) {   // warp per signal (x staging needs W <= 512 doubles)
       const size_t smw = (size_t)(512 + WELCH_WPB * welch_warp_doubles(W)) * sizeof(double);
-      if (smw > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(welch_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      }
+      if (int rc = ensure_dyn_smem((const void*)welch_warp_kernel, smw)) return rc;
       // BPV_WELCH_TC=1: peak-only calls on one-segment windows run the 256-point DFT on the tensor cores (dft_tc.cu:
       // tcgen05 candidates + float64 decision, same peaks bit for bit); the warp kernel then only takes the windows that
       // kernel flagged (warm-up, n < 256).  Opt-in: measured 82 + 8 us against 76 us for the float64 FFT kernel per
@@ -817,10 +814,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
     }
     const size_t smem = (size_t)(4 * W + W / 2 + 2 + 256) * sizeof(double);
     BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window %d too large for the dense spectrum kernel", W);
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(spectrum_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    }
+    if (int rc = ensure_dyn_smem((const void*)spectrum_dense_kernel, smem)) return rc;
     // DFT_RFFT as one dense contraction on the tensor cores (dft_tc.cu) when the windows of the launch share n = W: by
     // default for pipelines that resample (INTERP_*: valid = block, so every warmed-up window is full), or forced /
     // disabled with BPV_DFT_TC=1 / 0.  Windows with a non-finite sample are flagged and taken by the float64 kernel.
@@ -856,14 +850,9 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   const size_t smem_c = (size_t)W * (2 * sizeof(double) + sizeof(float4) + sizeof(float2));
   const size_t smem_p = (size_t)W * 2 * sizeof(double) + (size_t)max_bins * (sizeof(double) + sizeof(int));
   BPV_REQUIRE(smem_c <= 200 * 1024 && smem_p <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_spectrum: window/grid too large for shared memory");
-  if (smem_c > 48 * 1024) {
-    cudaFuncSetAttribute(ls_coarse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
-    cudaFuncSetAttribute(ls_coarse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
-    cudaFuncSetAttribute(ls_coarse_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
-    cudaFuncSetAttribute(ls_coarse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
-    cudaFuncSetAttribute(ls_coarse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
-  }
-  if (smem_p > 48 * 1024) cudaFuncSetAttribute(ls_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+  for (const void* k : {(const void*)ls_coarse_kernel<4>, (const void*)ls_coarse_kernel<5>, (const void*)ls_coarse_kernel<6>,
+                        (const void*)ls_coarse_kernel<7>, (const void*)ls_coarse_kernel<8>})
+    if (int rc = ensure_dyn_smem(k, smem_c)) return rc;
   // frequencies per thread NF in 4..8 and threads per CTA (multiple of 32, <= 128): the plan with the smallest padded cost
   // tiles * NF * threads * (instructions per (sample, frequency) slot ~ 10 + 12 / NF: one sincos per sample and thread,
   // 6 accumulations per slot, NF - 1 rotations)
@@ -887,15 +876,12 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   if (int rc = check_launch("ls_coarse_kernel")) return rc;
   const size_t smem_w = (size_t)LSP_WPB * 2 * W * sizeof(double);
   if (smem_w <= 200 * 1024) {          // warp per signal
-    static size_t configured_w = 0;
-    if (smem_w > 48 * 1024 && smem_w > configured_w) {
-      cudaFuncSetAttribute(ls_peak_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-      configured_w = smem_w;
-    }
+    if (int rc = ensure_dyn_smem((const void*)ls_peak_warp_kernel, smem_w)) return rc;
     ls_peak_warp_kernel<<<(unsigned)((nsig + LSP_WPB - 1) / LSP_WPB), 32 * LSP_WPB, smem_w, st>>>(proc_x, proc_y, *p, max_bins, nsig, spec_f,
                                                                                                  psd, num_bins, peak_idx, peak_freq, peak_mag);
     return check_launch("ls_peak_warp_kernel");
   }
+  if (int rc = ensure_dyn_smem((const void*)ls_peak_kernel, smem_p)) return rc;
   ls_peak_kernel<<<(unsigned)nsig, 128, smem_p, st>>>(proc_x, proc_y, *p, max_bins, spec_f, psd, num_bins, peak_idx, peak_freq, peak_mag);
   return check_launch("ls_peak_kernel");
 }

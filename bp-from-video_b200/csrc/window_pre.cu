@@ -636,12 +636,7 @@ extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y,
     if (warps > best || (warps == best && c < wpb)) { best = warps; wpb = c; }
   }
   const size_t smem = (size_t)wpb * L.total;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)window_preprocess_kernel, smem)) return rc;
   const long long nsig = J * p->R;
   window_preprocess_kernel<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, *p, L, sos_ws, taps_ws,
                                                                                      proc_x, proc_y, status);

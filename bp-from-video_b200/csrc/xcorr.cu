@@ -363,12 +363,7 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
     if (wpb > 4) wpb = 4;
     if (wpb >= 1) {
       const size_t smw = (size_t)wpb * Lw.total;
-      static size_t configured = 0;
-      if (smw > 48 * 1024 && smw > configured) {
-        cudaError_t e = cudaFuncSetAttribute(xcorr_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = smw;
-      }
+      if (int rc = ensure_dyn_smem((const void*)xcorr_warp_kernel, smw)) return rc;
       xcorr_warp_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smw, (cudaStream_t)stream>>>(
           proc_x, proc_y, *p, Lw, n, corr_lag, corr_val, num_lags, lag_idx, lag_sec, lag_corr);
       return check_launch("bpv_window_xcorr");
@@ -377,10 +372,7 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   const int Kw = (W + 7) / 8 * 8;
   const size_t smem = (size_t)(3 * W) * sizeof(double) + (size_t)(2 * W + Kw + 8 * ((Kw + 3 * W + 16) / 8 + 1)) * sizeof(float);
   BPV_REQUIRE(smem <= 200 * 1024, BPV_E_TOO_LARGE, "bpv_window_xcorr: window %d too large for shared memory", W);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(xcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  }
+  if (int rc = ensure_dyn_smem((const void*)xcorr_kernel, smem)) return rc;
   xcorr_kernel<<<(unsigned)n, 128, smem, (cudaStream_t)stream>>>(proc_x, proc_y, *p, corr_lag, corr_val, num_lags, lag_idx, lag_sec, lag_corr);
   return check_launch("bpv_window_xcorr");
 }
