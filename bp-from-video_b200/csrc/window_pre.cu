@@ -42,7 +42,7 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   PreLayout L;
   L.buf_len = butter ? W + 2 * pad : (interp ? W : 0);
   if (fir) {   // FIR stages only the operands that reach the cropped output: Kp + n + T + tile slack (fir_filtfilt)
-    const int need = W + 2 * 128 + 32;
+    const int need = W + 2 * 128 + 48;   // 8 * LD <= W + 302 (LD rounded up to 2 mod 4), 10 * LDB <= W + 287
     if (need > L.buf_len) L.buf_len = need;
   }
   int o = 0;
@@ -396,8 +396,17 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   const int KpB = (T + FIR_RTB - 1) / FIR_RTB * FIR_RTB;
   double* b = w.coef;          // [max(Kp, KpB)] zero padded
   double* zi = w.coef + 136;   // [T-1]
-  for (int i = w.lane; i < 136; i += 32) b[i] = i < T ? taps_g[i] : 0.0;
-  for (int i = w.lane; i < T - 1; i += 32) zi[i] = taps_g[128 + i];   // lfilter_zi, from the design kernel
+  {   // all nine global loads of the lane in flight before the first store (taps 0..135 zero padded | lfilter_zi from the design kernel)
+    double tb[5], tz[4];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) { const int i = w.lane + 32 * u; tb[u] = i < T ? taps_g[i] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = w.lane + 32 * u; tz[u] = i < T - 1 ? taps_g[128 + i] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) { const int i = w.lane + 32 * u; if (i < 136) b[i] = tb[u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = w.lane + 32 * u; if (i < T - 1) zi[i] = tz[u]; }
+  }
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
   const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);   // forward outputs needed
@@ -405,21 +414,24 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   // Only the operands those outputs can touch are staged: ext[fa-Kp .. fb+7] and G[ba-KpB .. bb+9]
   // (negative logical indices are the zero history of lfilter).  storage index = logical index - base.
   const int xbase = fa - Kp, gbase = ba - KpB;
-  const int LD = (Kp + n + T + 15) / FIR_RT + 1;
+  int LD = (Kp + n + T + 15) / FIR_RT + 1;
+  LD += (6 - (LD & 3)) & 3;   // LD = 2 (mod 4): the 8 rows of XT start 4 banks apart, the extension below stores without conflicts
   const int LDB = (KpB + n + T + 2 * FIR_RTB) / FIR_RTB + 1;
   double* XT = w.buf0;   // ext, de-interleaved by FIR_RT
   double* GT = w.buf1;   // reversed forward output G[g] = F[L-1-g], de-interleaved by FIR_RTB
   const double y_first = w.yv[0], y_last = w.yv[n - 1];
+  // odd extension (scipy.signal._arraytools.odd_ext), branch free so that the unrolled iterations overlap their loads:
+  // head 2*y[0] - y[p-i], body y[i-p], tail 2*y[n-1] - y[2n-2+p-i], zero outside [0, L)
+#pragma unroll 3
   for (int jj = w.lane; jj < FIR_RT * LD; jj += 32) {
     const int i = jj + xbase;
-    double v = 0.0;
-    if (i >= 0 && i < L) {                       // odd extension (scipy.signal._arraytools.odd_ext)
-      if (i < p) v = 2.0 * y_first - w.yv[p - i];
-      else if (i < p + n) v = w.yv[i - p];
-      else v = 2.0 * y_last - w.yv[n - 2 - (i - p - n)];
-    }
-    XT[xt_index<FIR_RT>(jj, LD)] = v;
+    const bool inside = i >= 0 && i < L, head = i < p, tail = i >= p + n;
+    const int src = head ? p - i : (tail ? 2 * n - 2 + p - i : i - p);
+    const double y = w.yv[inside ? src : 0];
+    const double v = head ? 2.0 * y_first - y : (tail ? 2.0 * y_last - y : y);
+    XT[xt_index<FIR_RT>(jj, LD)] = inside ? v : 0.0;
   }
+#pragma unroll 4
   for (int jj = w.lane; jj < FIR_RTB * LDB; jj += 32) GT[jj] = 0.0;
   __syncwarp();
   const double x0 = p >= 1 ? 2.0 * y_first - w.yv[p] : y_first;       // ext[0]
@@ -497,6 +509,15 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   const int W = p.window;
   bool has_interp = false;
   for (int i = 0; i < p.num_methods; ++i) has_interp |= (p.methods[i] == BPV_INTERP_LINEAR || p.methods[i] == BPV_INTERP_CUBIC);
+
+  // the job's filter coefficients are first needed after the gather and the detrend: start pulling their 2 KB (taps | zi,
+  // 16 lines) resp. 768 B (sos) towards the SM now, so that the filter stage does not open with a DRAM round trip
+  for (int i = 0; i < p.num_methods; ++i) {
+    if (p.methods[i] == BPV_FILTER_FIR && w.lane < 16)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(taps_ws + job * 256 + w.lane * 16));
+    if (p.methods[i] == BPV_FILTER_BUTTER && w.lane * 16 < p.butter_order * 6)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(sos_ws + job * (p.butter_order * 6) + w.lane * 16));
+  }
 
   // ---- gather + compaction (Signal.reset_mask: v = isfinite(x), w = isfinite(y); signal_data.py:43-45)
   int n = 0, m = 0;
