@@ -243,9 +243,19 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
     int lo = 0x7fffffff, hi = -1, cnt = 0;
     const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
     const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
-    for (int k = sub; k < p.window; k += FIRLS_LPD) {
-      int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
-      if (k >= kmin && isfinite(rt[slot])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+    for (int k0 = sub; k0 < p.window; k0 += FIRLS_LPD * 8) {     // 8 independent loads in flight per lane
+      double tv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * FIRLS_LPD;
+        int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
+        tv[u] = (k < p.window && k >= kmin) ? rt[slot] : nan_f64();
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * FIRLS_LPD;
+        if (isfinite(tv[u])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+      }
     }
     for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) {
       const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
