@@ -37,7 +37,7 @@ WORKLOADS = {
                     transform='PGRAM_WELCH', fps=30.0, kw={}, desc='reduced c2 for quick checks (not a bench line)'),
 }
 METRIC, UNIT = 'roi_sampled_frames_per_s', 'frames/s'
-ROI_NCU_TRAFFIC_BYTES = 336.0e6   # dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch (profiles/r1m_c2_summary.md)
+ROI_NCU_TRAFFIC_BYTES = 336.0e6   # dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch (profiles/r1w_c2_summary.md)
 
 
 def peaks():
@@ -358,7 +358,7 @@ def run_gpu(args, wl):
                      'peak_source': peak_src,
                      'note': 'achieved = algorithmic bytes (sum of 3*w*h over the ROIs of a launch + boxes + outputs) / mean '
                              'CUDA-event time of the F1 launches inside the timed region; traffic = dram__bytes_read+write of '
-                             'one launch from ncu --set full (profiles/r1m_c2_summary.md, same boxes); ncu launch list: 61 us per launch'},
+                             'one launch from ncu --set full (profiles/r1w_c2_summary.md, same boxes); ncu launch list: 61 us per launch'},
         'roofline_by_time': {'kernel': dom, 'bound': 'fp64 / issue (reported against HBM for reference)',
                              'achieved': kernels[dom]['gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': kernels[dom]['frac_hbm'],
                              'note': 'dominant kernel family of the step by CUDA-event time'},
