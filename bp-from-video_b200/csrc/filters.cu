@@ -47,7 +47,8 @@ __global__ void butter_from_fs_kernel(const double* __restrict__ fs, int n, int 
 // reductions, the reciprocal, warp syncs), not by the FMAs: with a whole warp per filter it issued 22 k warp
 // instructions per design.  Here a group of FIRLS_LPD = 8 lanes owns a filter (element i lives on lane i % 8,
 // register i / 8), so one warp instruction advances four designs, the reductions are 3 shuffle levels, and the
-// band-edge sinc tables are evaluated once with sinpi (5 per element instead of 8 sin).
+// band-edge sinc tables are built once per design (five sines per element, advanced by rotation along the lane's
+// arithmetic progression of elements).
 constexpr int FIRLS_LPD = 8;                        // lanes per design
 constexpr int FIRLS_EPL = 128 / FIRLS_LPD;          // elements per lane
 constexpr int FIRLS_DPW = 32 / FIRLS_LPD;           // designs per warp
