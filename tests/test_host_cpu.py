@@ -207,3 +207,56 @@ def test_reference_modules_import_on_top_of_the_drop_in():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'bp-from-video_b200') + ':' + REF)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+def test_cabi_rejects_bad_arguments_before_touching_the_gpu():
+    """Argument validation of the C ABI (include/bpv.h error codes): every case below returns before the first CUDA call,
+    so it runs without a GPU.  -1 = BPV_E_INVALID, -2 = BPV_E_UNSUPPORTED (the reference's NotImplementedError,
+    signal_processor.py:185/238/262), -3 = BPV_E_TOO_LARGE; bpv_last_error() names the entry point."""
+    import ctypes as C
+    from bpv import _cabi, ops
+    lib = _cabi.lib()
+    buf = (C.c_uint8 * 4096)()
+    a = C.cast(buf, C.c_void_p)        # a non-NULL address that is never dereferenced
+    # F1: NULL frames, NULL boxes, bad sizes, short row stride, unknown channel, too many ROIs, empty batch
+    assert lib.bpv_roi_sample_u8(None, None, 0, 24, 8, 8, 1, a, 1, 0, None, a, 0, None) == -1
+    assert b'bpv_roi_sample_u8' in lib.bpv_last_error()
+    assert lib.bpv_roi_sample_u8(a, None, 192, 24, 8, 8, 1, None, 1, 0, None, a, 0, None) == -1
+    assert lib.bpv_roi_sample_u8(a, None, 192, 24, 0, 8, 1, a, 1, 0, None, a, 0, None) == -1
+    assert lib.bpv_roi_sample_u8(a, None, 192, 23, 8, 8, 1, a, 1, 0, None, a, 0, None) == -1
+    assert lib.bpv_roi_sample_u8(a, None, 192, 24, 8, 8, 1, a, 1, 7, None, a, 0, None) == -2
+    assert b'NotImplementedError' in lib.bpv_last_error()
+    assert lib.bpv_roi_sample_u8(a, None, 192, 24, 8, 8, 2 ** 31, a, 2, 0, None, a, 0, None) == -3
+    assert lib.bpv_roi_sample_u8(a, None, 192, 24, 8, 8, 0, a, 1, 0, None, a, 0, None) == 0          # empty batch: nothing to do
+    # NV12 wants even sizes and pitch >= W; the fused resize wants positive target sizes
+    assert lib.bpv_roi_sample_nv12(a, 96, 8, 7, 8, 1, a, 1, 0, None, a, None) == -1
+    assert lib.bpv_roi_sample_nv12(a, 96, 6, 8, 8, 1, a, 1, 0, None, a, None) == -1
+    assert lib.bpv_roi_sample_nv12(a, 96, 8, 8, 8, 0, a, 1, 0, None, a, None) == 0
+    assert lib.bpv_roi_sample_resized_u8(a, 192, 24, 8, 8, 0, 4, 1, a, 1, 0, None, a, None) == -1
+    assert lib.bpv_roi_sample_resized_u8(a, 192, 24, 8, 8, 4, 4, 1, a, 1, 9, None, a, None) == -2
+    # window pipeline: NULL params, filter limits, unknown method / transform, window > cap, missing workspace
+    assert lib.bpv_window_workspace_bytes(None) == -1
+    assert lib.bpv_window_preprocess(a, a, None, None, 0, a, a, a, None) == -1
+    good = dict(butter_order=16, butter_min_bw=0.1, fir_taps=127, fir_df=0.3, min_freq=0.8, max_freq=4.0, ls_num_freqs=0)
+
+    def params(methods, transform=_cabi.PGRAM_LS, W=32, cap=33, **kw):
+        return ops.make_params(1, 2, cap, W, W - 1, 1, 1, methods, transform, **{**good, **kw})
+    pre = lambda p, ws=None, nbytes=0: lib.bpv_window_preprocess(a, a, C.byref(p), ws, nbytes, a, a, a, None)
+    assert pre(params([], butter_order=17)) == -3
+    assert pre(params([], fir_taps=128)) == -3                      # even / > 127 taps
+    assert pre(params([], W=40, cap=33)) == -1                      # window longer than the ring
+    p = params([_cabi.DIFF_1]); p.methods[0] = 42
+    assert pre(p) == -2 and b'NotImplementedError' in lib.bpv_last_error()
+    assert pre(params([_cabi.FILTER_FIR])) == -1                    # filter design needs the caller's workspace
+    assert b'workspace' in lib.bpv_last_error()
+    need = lib.bpv_window_workspace_bytes(C.byref(params([_cabi.FILTER_FIR])))
+    assert need == 1 * (16 * 6 + 256) * 8
+    assert pre(params([_cabi.FILTER_FIR]), a, need - 1) == -1
+    p = params([], transform=9)
+    assert lib.bpv_window_spectrum(a, a, C.byref(p), 64, None, 0, None, None, a, a, a, a, None) == -2
+    assert lib.bpv_window_spectrum(None, a, C.byref(params([])), 64, None, 0, None, None, a, a, a, a, None) == -1
+    assert lib.bpv_window_xcorr(None, a, C.byref(params([])), None, None, None, a, a, a, None) == -1
+    assert lib.bpv_window_xcorr(a, a, C.byref(params([])), a, None, None, a, a, a, None) == -1      # corr_lag without corr_val
+    assert lib.bpv_butter_sos_design(None, 4, C.byref(params([])), a, None) == -1
+    assert lib.bpv_firls_design(a, 0, C.byref(params([])), a, None) == 0                              # nothing to design
+    assert lib.bpv_dft256_tc(None, 1, a, None) == -1
