@@ -73,3 +73,19 @@ def test_resize_restatement_matches_opencv():
                                ((90, 160), (90, 160)), ((216, 384), (54, 96))]:
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         assert np.array_equal(orc.resize_linear_u8(src, dw, dh), cv2.resize(src, (dw, dh))), ((sh, sw), (dh, dw))
+
+
+def test_resize_and_nv12_restatements_fuzzed_against_opencv():
+    """Seeded fuzz of the two ingest restatements against cv2 over random geometries (down / up / mixed scaling, 1-pixel
+    targets, 2-pixel sources; even NV12 sizes): every output byte equal."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(99)
+    for _ in range(200):
+        sh, sw = int(rng.integers(2, 120)), int(rng.integers(2, 160))
+        dh, dw = int(rng.integers(1, 200)), int(rng.integers(1, 260))
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(orc.resize_linear_u8(src, dw, dh), cv2.resize(src, (dw, dh))), ((sh, sw), (dh, dw))
+    for _ in range(40):
+        H, W = 2 * int(rng.integers(1, 60)), 2 * int(rng.integers(1, 80))
+        nv = rng.integers(0, 256, (H * 3 // 2, W), dtype=np.uint8)
+        assert np.array_equal(orc.nv12_to_bgr(nv, H, W), cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12)), (H, W)
