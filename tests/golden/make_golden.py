@@ -89,12 +89,12 @@ def sig_arrays(group):
 
 
 sys.path.insert(0, ROOT)
-from tests.helpers import CASES, IMG_H as H, IMG_W as W  # noqa: E402  (single source of the case table)
+from tests.helpers import CASES, LIVE_CASES, IMG_H as H, IMG_W as W  # noqa: E402  (single source of the case tables)
 
 
 
-def run_case(sp, name, seed):
-    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = CASES[name]
+def run_case(sp, name, seed, table=CASES):
+    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = table[name]
     rng = np.random.default_rng(seed)
     ts = synth.timestamps(rng, n, fps, irregular=irregular, drop=0.05 if irregular else 0.0, origin=3.0)
     det = make_detections(rng, n, H, W, p_none)
@@ -144,6 +144,11 @@ def roi_case(sp, seed=7):
 def main():
     warnings.simplefilter('ignore')
     sp = load_reference()
+    if len(sys.argv) == 3 and sys.argv[1] == '--live':     # the non-committed differential cases, into a scratch directory
+        for k, name in enumerate(LIVE_CASES):
+            np.savez_compressed(os.path.join(sys.argv[2], f'{name}.npz'), **run_case(sp, name, 500 + k, LIVE_CASES))
+        print('live ok')
+        return
     for k, name in enumerate(CASES):
         out = run_case(sp, name, seed=100 + k)
         np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)

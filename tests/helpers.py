@@ -26,6 +26,17 @@ CASES = {
     'long_window_c2':    ('CHROM_GREEN', ['DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_WELCH', 300, 306, 30, False, 0.01, 1, {}),
     'long_window_c1':    ('GREEN', ['FILTER_BUTTER'], 'PGRAM_LS', 300, 306, 30, False, 0.01, 1, dict(min_freq=0.7)),
 }
+# cases that are NOT committed as fixtures: tests/test_oracle_golden.py::test_live_differential_vs_reference runs the
+# reference on them in a subprocess (build container only) and demands exact equality with the oracle, so the pin does
+# not rest on the ten frozen files alone
+LIVE_CASES = {
+    'live_diff1_butter4_welch': ('GREEN', ['DIFF_1', 'FILTER_BUTTER'], 'PGRAM_WELCH', 44, 64, 30, True, 0.04, 2, dict(butter_order=4)),
+    'live_cubic_lin_fir31_ls':  ('CHROM_GREEN', ['INTERP_CUBIC', 'DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_LS', 52, 70, 60, True, 0.04, 1,
+                                 dict(fir_taps=31, min_freq=0.7)),
+    'live_const_dft':           ('CHROM_GREEN', ['DETREND_CONST'], 'DFT_RFFT', 36, 50, 24, False, 0.10, 3, {}),
+    'live_lin_diff2_butter_ls': ('GREEN', ['INTERP_LINEAR', 'DIFF_2', 'FILTER_BUTTER'], 'PGRAM_LS', 40, 58, 15, True, 0.02, 1,
+                                 dict(butter_order=8, max_freq=3.0)),
+}
 IMG_H, IMG_W = 60, 80
 REL = [(-0.00, -0.10, 0.20, 0.05), (-0.10, -0.10, 0.10, 0.10)]  # roi.py:26,28
 LMK = [[151], [0, 9]]                                            # roi.py:19,21-22

@@ -11,8 +11,25 @@ from tests import helpers as h
 
 @pytest.mark.parametrize('name', list(h.CASES))
 def test_process_matches_reference(name):
-    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = h.CASES[name]
-    g = h.load_case(name)
+    _replay(h.CASES[name], h.load_case(name), name)
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference'), reason='reference not mounted (GPU box)')
+def test_live_differential_vs_reference(tmp_path):
+    """Beyond the frozen fixtures: run the UNMODIFIED reference now, in a subprocess, on cases that are not committed
+    (other method chains, filter orders, tap counts, frame rates, ROI smoothing lengths) and demand exact equality."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(h.GOLDEN, 'make_golden.py'), '--live', str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'live ok' in r.stdout, r.stderr[-2000:]
+    for name, case in h.LIVE_CASES.items():
+        g = np.load(os.path.join(str(tmp_path), f'{name}.npz'))
+        _replay(case, {k: g[k] for k in g.files}, name)
+
+
+def _replay(case, g, name):
+    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = case
     frames = h.case_frames(g)
     st = orc.OracleStream(2, roi_ms, window, 50, h.CHANNEL[channel], [h.METHOD[m] for m in methods],
                           h.TRANSFORM[transform], **kw)
