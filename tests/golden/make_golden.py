@@ -89,7 +89,7 @@ def sig_arrays(group):
 
 
 sys.path.insert(0, ROOT)
-from tests.helpers import CASES, LIVE_CASES, IMG_H as H, IMG_W as W  # noqa: E402  (single source of the case tables)
+from tests.helpers import CASES, LIVE_CASES, SEEDS, IMG_H as H, IMG_W as W  # noqa: E402  (single source of the case tables)
 
 
 
@@ -150,7 +150,7 @@ def main():
         print('live ok')
         return
     for k, name in enumerate(CASES):
-        out = run_case(sp, name, seed=100 + k)
+        out = run_case(sp, name, seed=SEEDS[name])
         np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
         print(name, 'ok', sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) // 1024, 'KiB')
     np.savez_compressed(os.path.join(HERE, 'roi_sample.npz'), **roi_case(sp))

@@ -26,16 +26,26 @@ CASES = {
     'long_window_c2':    ('CHROM_GREEN', ['DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_WELCH', 300, 306, 30, False, 0.01, 1, {}),
     'long_window_c1':    ('GREEN', ['FILTER_BUTTER'], 'PGRAM_LS', 300, 306, 30, False, 0.01, 1, dict(min_freq=0.7)),
 }
+# added after the first ten (generated with their own seeds, SEEDS below): other method chains, filter orders, tap counts,
+# frame rates and ROI smoothing lengths
+CASES.update({
+    'diff1_butter4_welch':  ('GREEN', ['DIFF_1', 'FILTER_BUTTER'], 'PGRAM_WELCH', 44, 64, 30, True, 0.04, 2, dict(butter_order=4)),
+    'cubic_lin_fir31_ls':   ('CHROM_GREEN', ['INTERP_CUBIC', 'DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_LS', 52, 70, 60, True, 0.04, 1,
+                             dict(fir_taps=31, min_freq=0.7)),
+    'const_dft_smooth3':    ('CHROM_GREEN', ['DETREND_CONST'], 'DFT_RFFT', 36, 50, 24, False, 0.10, 3, {}),
+    'lin_diff2_butter8_ls': ('GREEN', ['INTERP_LINEAR', 'DIFF_2', 'FILTER_BUTTER'], 'PGRAM_LS', 40, 58, 15, True, 0.02, 1,
+                             dict(butter_order=8, max_freq=3.0)),
+})
+SEEDS = {name: 100 + k for k, name in enumerate(list(CASES)[:10])}
+SEEDS.update(diff1_butter4_welch=500, cubic_lin_fir31_ls=501, const_dft_smooth3=502, lin_diff2_butter8_ls=503)
 # cases that are NOT committed as fixtures: tests/test_oracle_golden.py::test_live_differential_vs_reference runs the
 # reference on them in a subprocess (build container only) and demands exact equality with the oracle, so the pin does
-# not rest on the ten frozen files alone
+# not rest on the frozen files alone
 LIVE_CASES = {
-    'live_diff1_butter4_welch': ('GREEN', ['DIFF_1', 'FILTER_BUTTER'], 'PGRAM_WELCH', 44, 64, 30, True, 0.04, 2, dict(butter_order=4)),
-    'live_cubic_lin_fir31_ls':  ('CHROM_GREEN', ['INTERP_CUBIC', 'DETREND_LINEAR', 'FILTER_FIR'], 'PGRAM_LS', 52, 70, 60, True, 0.04, 1,
-                                 dict(fir_taps=31, min_freq=0.7)),
-    'live_const_dft':           ('CHROM_GREEN', ['DETREND_CONST'], 'DFT_RFFT', 36, 50, 24, False, 0.10, 3, {}),
-    'live_lin_diff2_butter_ls': ('GREEN', ['INTERP_LINEAR', 'DIFF_2', 'FILTER_BUTTER'], 'PGRAM_LS', 40, 58, 15, True, 0.02, 1,
-                                 dict(butter_order=8, max_freq=3.0)),
+    'live_diff2_butter2_dft':       ('GREEN', ['DIFF_2', 'FILTER_BUTTER'], 'DFT_RFFT', 38, 54, 30, True, 0.03, 1, dict(butter_order=2)),
+    'live_cubic_const_fir63_welch': ('CHROM_GREEN', ['INTERP_CUBIC', 'DETREND_CONST', 'FILTER_FIR'], 'PGRAM_WELCH', 48, 66, 50, True, 0.03, 2,
+                                     dict(fir_taps=63)),
+    'live_lin_detrend_ls_lowfs':    ('GREEN', ['INTERP_LINEAR', 'DETREND_LINEAR'], 'PGRAM_LS', 32, 48, 10, True, 0.05, 1, {}),
 }
 IMG_H, IMG_W = 60, 80
 REL = [(-0.00, -0.10, 0.20, 0.05), (-0.10, -0.10, 0.10, 0.10)]  # roi.py:26,28
