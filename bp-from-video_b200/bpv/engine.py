@@ -13,6 +13,14 @@ frame of the step.  All state lives in HBM: ring_t f64 [S, cap], ring_y f64 [S, 
 
 ROI boxes are inputs (calc_rois / detection are upstream of the path).  torch is used for
 device allocations and the stream handle only; every computation is a libbpv kernel.
+
+Lifetime of results: the tensors of a StepResult are views of `result_buffers` rotating buffer sets owned by the
+engine (no allocation per step).  With the default of 2 a result stays valid while the NEXT step runs and is
+overwritten by the one after; hold results longer by cloning them or by raising `result_buffers`.
+
+Overlap (`overlap`, bit mask; default from the environment variable BPV_OVERLAP, else OVERLAP_DEFAULT):
+  1  the filter design of the step (it needs only the timestamps) runs on a side stream beside F1
+  2  F4 (cross-correlation) runs on a side stream beside F3 (spectrum): both only read the processed windows
 """
 from __future__ import annotations
 
@@ -25,6 +33,9 @@ import torch
 from . import _cabi, ops
 
 EVERY_FRAME, LAST = 'every_frame', 'last'
+OVERLAP_DESIGN, OVERLAP_XCORR = 1, 2
+OVERLAP_DEFAULT = OVERLAP_XCORR
+STATE_VERSION = 1
 
 
 @dataclass
@@ -50,9 +61,14 @@ class StepResult:
     def ptt_ms(self):                     # signal_processor.py:312  t * 1000
         return self.lag_sec * 1000
 
-    def packed(self) -> torch.Tensor:
-        """[J, 2R + 2P] float64 record (bpm, ptt_ms, peak_idx, lag_idx) — what the multi-GPU gather moves."""
-        return ops.pack_records(self.peak_freq, self.lag_sec, self.peak_idx, self.lag_idx)
+    def packed(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[J, 2R + 2P] float64 record (bpm, ptt_ms, peak_idx, lag_idx): full-precision host read-back."""
+        return ops.pack_records(self.peak_freq, self.lag_sec, self.peak_idx, self.lag_idx, out=out)
+
+    def packed32(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """[J, 2R + 2P] int32 words (bpm f32, ptt_ms f32, peak_idx i32, lag_idx i32): the 24-byte record of SURVEY.md
+        8(e) that the multi-GPU gather moves (`ops.unpack_records32` splits it)."""
+        return ops.pack_records32(self.peak_freq, self.lag_sec, self.peak_idx, self.lag_idx, out=out)
 
 
 class BatchedSignalProcessor:
@@ -61,11 +77,17 @@ class BatchedSignalProcessor:
                  spectrum_transform: int = _cabi.PGRAM_LS, butter_order: int = 16, butter_min_bw: float = 0.1,
                  fir_taps: int = 127, fir_df: float = 0.3, min_freq: float = 0.8, max_freq: float = 4.0,
                  ls_num_freqs: int | None = None, windows: str = EVERY_FRAME, store_arrays: bool = False,
-                 device: str | torch.device = 'cuda', roi_pixels_hint: int = 0, peak_max_samples: int = 0):
+                 device: str | torch.device = 'cuda', roi_pixels_hint: int = 0, peak_max_samples: int = 0,
+                 result_buffers: int = 2, overlap: int | None = None):
         _cabi.lib()  # fail loudly if the CUDA library is missing: there is no CPU fallback
         if not torch.cuda.is_available():
             raise _cabi.BpvError('BatchedSignalProcessor needs a CUDA device (no CPU fallback)')
-        assert windows in (EVERY_FRAME, LAST)
+        if windows not in (EVERY_FRAME, LAST):
+            raise ValueError(f"windows must be '{EVERY_FRAME}' or '{LAST}', not {windows!r}")
+        if int(num_streams) < 1 or int(num_rois) < 1 or int(signal_max_samples) < 1 or int(max_frames_per_step) < 1:
+            raise ValueError('num_streams, num_rois, signal_max_samples and max_frames_per_step must be positive')
+        if int(result_buffers) < 1:
+            raise ValueError('result_buffers must be >= 1')
         self.S, self.R, self.P = int(num_streams), int(num_rois), math.comb(int(num_rois), 2)
         self.W = int(signal_max_samples)
         self.Tmax = int(max_frames_per_step)
@@ -78,73 +100,135 @@ class BatchedSignalProcessor:
         self.windows, self.store_arrays = windows, bool(store_arrays)
         self.roi_pixels_hint = int(roi_pixels_hint)
         self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _cabi.BpvError('BatchedSignalProcessor needs a CUDA device (no CPU fallback)')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        if overlap is None:
+            env = os.environ.get('BPV_OVERLAP')
+            overlap = int(env) if env not in (None, '') else OVERLAP_DEFAULT
+        self.overlap = int(overlap)
         dev, f64 = self.device, torch.float64
         self.ring_t = torch.full((self.S, self.cap), float('nan'), dtype=f64, device=dev)
         self.ring_y = torch.full((self.S, self.R, self.cap), float('nan'), dtype=f64, device=dev)
         self.count = 0  # samples pushed per stream so far (global index of the next sample)
         Jmax = self.S * (self.Tmax if windows == EVERY_FRAME else 1)
         self._Jmax = Jmax
-        self._samples = torch.empty((self.S, self.Tmax, self.R), dtype=f64, device=dev)
-        self._proc_x = torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev)
-        self._proc_y = torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev)
-        self._status = torch.empty((Jmax, self.R), dtype=torch.int32, device=dev)
+        self._nbuf = int(result_buffers)
+        self._turn = 0
+        self._samples = [torch.empty((self.S, self.Tmax, self.R), dtype=f64, device=dev) for _ in range(self._nbuf)]
+        # the processed windows are results only when the arrays are stored; otherwise scratch between F2 and F3 / F4
+        nproc = self._nbuf if self.store_arrays else 1
+        self._proc = [(torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev),
+                       torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev)) for _ in range(nproc)]
+        self._status = [torch.empty((Jmax, self.R), dtype=torch.int32, device=dev) for _ in range(self._nbuf)]
+        self._spec = [None] * self._nbuf
+        self._xc = [None] * self._nbuf
         p = self._params(0, 1, self.Tmax if windows == EVERY_FRAME else 1)
         self._mb = ops.max_bins(p)
-        need = max(_cabi.lib().bpv_window_workspace_bytes(p), _cabi.lib().bpv_spectrum_workspace_bytes(p, self._mb), 16)
-        self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        self._spec = self._xc = None
+        need = max(_cabi.lib().bpv_window_workspace_bytes(p), 16)
+        self._ws = torch.empty(need, dtype=torch.uint8, device=dev)                 # per-job filter designs
+        need = max(_cabi.lib().bpv_spectrum_workspace_bytes(p, self._mb), 16)
+        self._ws_spec = torch.empty(need, dtype=torch.uint8, device=dev)
         self.launches_per_step = self._extra_launches = 0
+        self._has_filter = any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
+        self._side = None
+        self._ev = None
         # sg_bpm / sg_ptt histories and their running means on the device (0 = off)
         self.peak_max_samples = int(peak_max_samples)
+        self._mean_count = 0
+        self._bpm_ring = self._ptt_ring = None
         if self.peak_max_samples:
             self._bpm_ring = torch.full((self.S, self.R, self.peak_max_samples), float('nan'), dtype=f64, device=dev)
             self._ptt_ring = torch.full((self.S, max(self.P, 1), self.peak_max_samples), float('nan'), dtype=f64, device=dev)
-            self._mean_count = 0
+        self._roi_hist = None
+        self._roi_count = 0
 
     # ------------------------------------------------------------------------------------------
     def _params(self, head0: int, head_step: int, jobs: int) -> _cabi.WindowParams:
         return ops.make_params(self.S, self.R, self.cap, self.W, head0, head_step, jobs, self.methods, self.transform, **self.kw)
 
+    def _streams(self):
+        """Side stream + events of the overlapped schedule (created on first use, on the engine's device)."""
+        if self._side is None:
+            with torch.cuda.device(self.device):
+                self._side = torch.cuda.Stream(device=self.device)
+                self._ev = {k: torch.cuda.Event() for k in ('ts', 'design', 'pre', 'xc')}
+        return self._side, self._ev
+
+    def _check_step(self, S, T, boxes=None):
+        if S != self.S or not 1 <= T <= self.Tmax:
+            raise ValueError(f'step: expected {self.S} streams and 1..{self.Tmax} frames per stream, got {S} x {T}')
+        if boxes is not None and tuple(boxes.shape) != (S, T, self.R, 4):
+            raise ValueError(f'step: boxes must be int32 [{S}, {T}, {self.R}, 4], got {tuple(boxes.shape)}')
+
     def step(self, frames: torch.Tensor, boxes: torch.Tensor, timestamps: torch.Tensor, view=None, nv12_size=None,
-             resize_to=None) -> StepResult:
+             resize_to=None, masks: torch.Tensor | None = None, mask_category=0) -> StepResult:
         """frames uint8 [S, T, H, W, 3] (HBM, or pinned host memory: the ROI kernel then reads the ROI rows
         straight over PCIe), boxes int32 [S, T, R, 4] (device), timestamps float64 [S, T] (device).
         view = (view_w, view_h, left, flip_horizontally): the boxes are expressed in the reference VideoReader's
         cropped / mirrored view of the decoded frames (video_reader.py:97-103) and are mapped back onto `frames`
         on the device; nothing is copied.
         nv12_size = (H, W): frames are NV12 decoder buffers uint8 [S, T, 3H/2, pitch]; the ROI is sampled from the planes
-        with OpenCV's integer BT.601 conversion, i.e. as from the BGR frame cv2.VideoCapture would have produced."""
+        with OpenCV's integer BT.601 conversion, i.e. as from the BGR frame cv2.VideoCapture would have produced.
+        masks uint8 [S, T, H, W] + mask_category (one int, or one per ROI): only ROI pixels whose segmentation category
+        matches contribute (category masks as InferenceResults.person_segmenter, inference_runner.py:154-166)."""
         S, T = frames.shape[:2]
-        assert S == self.S and 1 <= T <= self.Tmax and boxes.shape == (S, T, self.R, 4)
+        self._check_step(S, T, boxes)
         self._extra_launches = 0
-        if view is not None:
-            boxes = ops.view_boxes(boxes.contiguous(), *view)
-            self._extra_launches = 1
-        if resize_to is not None:
-            # boxes live in the frame cv2.resize(frame, (dst_w, dst_h)) would produce (video_reader.py:95-96); pixels are
-            # generated on the fly with OpenCV's integer bilinear arithmetic, the resized frame is never materialised
-            dst_h, dst_w = resize_to
-            val, _ = ops.roi_sample_resized(frames.view(S * T, *frames.shape[2:]), dst_h, dst_w,
-                                            boxes.reshape(S * T, self.R, 4).contiguous(), self.color_channel)
-            return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
-        if nv12_size is not None:
-            H, W = nv12_size
-            val, _ = ops.roi_sample_nv12(frames.view(S * T, *frames.shape[2:]), H, W, boxes.reshape(S * T, self.R, 4).contiguous(),
-                                         self.color_channel)
-            return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
-        samples = self._samples[:, :T]
-        if T != self.Tmax:
-            samples = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)
-        ops.roi_sample(frames.view(S * T, *frames.shape[2:]), boxes.view(S * T, self.R, 4), self.color_channel,
-                       roi_pixels_hint=self.roi_pixels_hint, out_value=samples.view(S * T, self.R))
-        return self.step_signals(samples, timestamps, _count_roi=True)
+        with torch.cuda.device(self.device):
+            if view is not None:
+                boxes = ops.view_boxes(boxes.contiguous(), *view)
+                self._extra_launches = 1
+            if resize_to is not None:
+                # boxes live in the frame cv2.resize(frame, (dst_w, dst_h)) would produce (video_reader.py:95-96); pixels
+                # are generated on the fly with OpenCV's integer bilinear arithmetic, the resized frame is never materialised
+                dst_h, dst_w = resize_to
+                val, _ = ops.roi_sample_resized(frames.view(S * T, *frames.shape[2:]), dst_h, dst_w,
+                                                boxes.reshape(S * T, self.R, 4).contiguous(), self.color_channel)
+                return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
+            if nv12_size is not None:
+                H, W = nv12_size
+                val, _ = ops.roi_sample_nv12(frames.view(S * T, *frames.shape[2:]), H, W,
+                                             boxes.reshape(S * T, self.R, 4).contiguous(), self.color_channel)
+                return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
+            if masks is not None:
+                val, _ = ops.roi_sample_masked(frames.view(S * T, *frames.shape[2:]), masks.view(S * T, *masks.shape[2:]),
+                                               mask_category, boxes.reshape(S * T, self.R, 4).contiguous(),
+                                               self.color_channel)
+                return self.step_signals(val.view(S, T, self.R), timestamps, _count_roi=True)
+            samples = self._samples[self._turn][:, :T]
+            if T != self.Tmax:
+                samples = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)
+            design_ahead = bool(self.overlap & OVERLAP_DESIGN) and self._has_filter
+            if design_ahead:
+                self._design_ahead(timestamps, T)
+            ops.roi_sample(frames.view(S * T, *frames.shape[2:]), boxes.view(S * T, self.R, 4), self.color_channel,
+                           roi_pixels_hint=self.roi_pixels_hint, out_value=samples.view(S * T, self.R))
+            return self.step_signals(samples, timestamps, _count_roi=True, _designed=design_ahead)
+
+    def _design_ahead(self, timestamps: torch.Tensor, T: int) -> None:
+        """Push the step's timestamps and start the filter design of its window jobs on the side stream: make_filter
+        depends on nothing else (signal_processor.py:158-173), so it runs beside F1 instead of between F1 and F2."""
+        side, ev = self._streams()
+        main = torch.cuda.current_stream(self.device)
+        ops.ring_push(self.ring_t, self.ring_y, self.count, timestamps.contiguous(), None)
+        ev['ts'].record(main)
+        jobs = T if self.windows == EVERY_FRAME else 1
+        head0 = self.count if self.windows == EVERY_FRAME else self.count + T - 1
+        p = self._params(head0, 1, jobs)
+        side.wait_event(ev['ts'])
+        with torch.cuda.stream(side):
+            ops.window_design(self.ring_t, p, self._ws)
+            ev['design'].record(side)
 
     # ------------------------------------------------------------------------------------------
     # SURVEY.md §8(f) row 1: calc_rois + ROI smoothing on the device for batched landmark tensors
     def set_roi_configs(self, relative_bboxes, num_points, roi_max_samples: int = 1):
         """relative_bboxes [R][4] (left, top, right, bottom) and the number of anchor landmarks per ROI, as in
         roi.ROIConfig (roi.py:8-13); roi_max_samples = length of the smoothing history (signal_processor.py:47)."""
-        assert len(relative_bboxes) == self.R and len(num_points) == self.R
+        if len(relative_bboxes) != self.R or len(num_points) != self.R:
+            raise ValueError(f'set_roi_configs: expected {self.R} ROI configs')
         self._rel = torch.tensor(relative_bboxes, dtype=torch.float64, device=self.device).contiguous()
         self._npts = torch.tensor(num_points, dtype=torch.int32, device=self.device)
         self._roi_hist = torch.full((self.S, self.R, int(roi_max_samples), 6), float('nan'), dtype=torch.float64, device=self.device)
@@ -154,6 +238,8 @@ class BatchedSignalProcessor:
         """One step from detector outputs instead of boxes: present u8 [S,T,R], bbox i32 [S,T,R,4] (largest detection
         of the ROI's model), points i32 [S,T,R,K,2] (the landmarks the ROI config selects).  Returns (StepResult, boxes
         [, locations, smoothed])."""
+        if self._roi_hist is None:
+            raise ValueError('step_detections: call set_roi_configs first')
         out = ops.calc_rois(present, bbox, points, self._npts, self._rel, self._roi_hist, self._roi_count, want_locations)
         self._roi_count += present.shape[1]
         boxes = out[0] if want_locations else out
@@ -165,31 +251,58 @@ class BatchedSignalProcessor:
         overlap the ROI sampling of the next batch (e.g. zero-copy from pinned host memory, PCIe bound) with the
         window pipeline of the current one: run this on a side stream, then `step_signals` on the main stream."""
         S, T = frames.shape[:2]
-        assert S == self.S and boxes.shape == (S, T, self.R, 4)
+        if S != self.S or tuple(boxes.shape) != (S, T, self.R, 4):
+            raise ValueError('roi_samples: frames [S, T, H, W, 3] / boxes [S, T, R, 4] do not match the engine')
         if out is None:
             out = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)
         ops.roi_sample(frames.view(S * T, *frames.shape[2:]), boxes.view(S * T, self.R, 4), self.color_channel,
                        roi_pixels_hint=self.roi_pixels_hint, out_value=out.view(S * T, self.R))
         return out
 
-    def step_signals(self, samples: torch.Tensor, timestamps: torch.Tensor, _count_roi: bool = False) -> StepResult:
+    def step_signals(self, samples: torch.Tensor, timestamps: torch.Tensor, _count_roi: bool = False,
+                     _designed: bool = False) -> StepResult:
         """Signals-only entry: samples float64 [S, T, R] (already ROI-sampled), timestamps float64 [S, T]."""
         S, T, R = samples.shape
-        assert S == self.S and R == self.R and 1 <= T <= self.Tmax and timestamps.shape == (S, T)
-        ops.ring_push(self.ring_t, self.ring_y, self.count, timestamps.contiguous(), samples.contiguous())
+        self._check_step(S, T)
+        if R != self.R or tuple(timestamps.shape) != (S, T):
+            raise ValueError(f'step_signals: samples must be [S, T, {self.R}] and timestamps [S, T]')
+        with torch.cuda.device(self.device):
+            return self._step_signals(samples, timestamps, S, T, _count_roi, _designed)
+
+    def _step_signals(self, samples, timestamps, S, T, _count_roi, _designed) -> StepResult:
+        main = torch.cuda.current_stream(self.device)
+        turn = self._turn
+        self._turn = (turn + 1) % self._nbuf
+        ops.ring_push(self.ring_t, self.ring_y, self.count, None if _designed else timestamps.contiguous(), samples.contiguous())
         g0 = self.count
         self.count += T
         jobs = T if self.windows == EVERY_FRAME else 1
         head0 = g0 if self.windows == EVERY_FRAME else g0 + T - 1
         p = self._params(head0, 1, jobs)
         J = S * jobs
-        px, py, st = self._proc_x[:J], self._proc_y[:J], self._status[:J]
-        ops.window_preprocess(self.ring_t, self.ring_y, p, px, py, st, workspace=self._ws)
-        sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws,
-                                 out=None if self._spec is None or self._spec['peak_idx'].shape[0] != J else self._spec)
-        xc = ops.window_xcorr(px, py, p, store=self.store_arrays,
-                              out=None if self._xc is None or self._xc['lag_idx'].shape[0] != J else self._xc)
-        self._spec, self._xc = sp, xc
+        pxb, pyb = self._proc[turn % len(self._proc)]
+        px, py, st = pxb[:J], pyb[:J], self._status[turn][:J]
+        if _designed:
+            main.wait_event(self._ev['design'])
+            ops.window_filter(self.ring_t, self.ring_y, p, self._ws, px, py, st)
+        else:
+            ops.window_preprocess(self.ring_t, self.ring_y, p, px, py, st, workspace=self._ws)
+        spo, xco = self._spec[turn], self._xc[turn]
+        spo = None if spo is None or spo['peak_idx'].shape[0] != J else spo
+        xco = None if xco is None or xco['lag_idx'].shape[0] != J else xco
+        if (self.overlap & OVERLAP_XCORR) and self.P:
+            side, ev = self._streams()
+            ev['pre'].record(main)
+            side.wait_event(ev['pre'])
+            with torch.cuda.stream(side):
+                xc = ops.window_xcorr(px, py, p, store=self.store_arrays, out=xco)
+                ev['xc'].record(side)
+            sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
+            main.wait_event(ev['xc'])
+        else:
+            sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
+            xc = ops.window_xcorr(px, py, p, store=self.store_arrays, out=xco)
+        self._spec[turn], self._xc[turn] = sp, xc
         n_pre = 1 + sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
         n_spec = 2 if self.transform == _cabi.PGRAM_LS else 1
         if (self.transform == _cabi.PGRAM_WELCH and not self.store_arrays and 256 <= self.W <= 383
@@ -200,7 +313,8 @@ class BatchedSignalProcessor:
             interp = any(m in (_cabi.INTERP_LINEAR, _cabi.INTERP_CUBIC) for m in self.methods)
             if (env[:1] == '1') if env is not None else interp:
                 n_spec = 3              # dft_tc_kernel + dft_peak_kernel + spectrum_dense_kernel for the flagged windows
-        self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + 1 + n_pre + n_spec + (1 if self.P else 0)
+        n_push = 2 if _designed else 1
+        self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P else 0)
         arrays = {}
         if self.store_arrays:
             arrays = dict(proc_x=px, proc_y=py, freqs=sp['freqs'], mags=sp['mags'], num_bins=sp['num_bins'],
@@ -217,7 +331,50 @@ class BatchedSignalProcessor:
         return StepResult(jobs, samples, sp['peak_freq'], sp['peak_idx'], sp['peak_mag'], xc['lag_sec'], xc['lag_idx'],
                           xc['lag_corr'], st, arrays, means)
 
+    # ------------------------------------------------------------------------------------------
+    # snapshot / resume of the per-stream state (the reference's deepcopy(store), :313, is the
+    # only "checkpoint" it has; long-running batched streams need the device rings and histories)
+    def _signature(self) -> dict:
+        return dict(S=self.S, R=self.R, W=self.W, cap=self.cap, peak_max_samples=self.peak_max_samples,
+                    roi_max_samples=0 if self._roi_hist is None else int(self._roi_hist.shape[2]))
+
+    def state_dict(self) -> dict:
+        """Everything a run needs to continue bit-for-bit: raw-sample rings and their count, the bpm / ptt histories of
+        the running means, the ROI smoothing history.  Tensors are copied to the host."""
+        torch.cuda.synchronize(self.device)
+        cpu = lambda t: None if t is None else t.detach().to('cpu', copy=True)
+        return dict(version=STATE_VERSION, signature=self._signature(), count=int(self.count),
+                    ring_t=cpu(self.ring_t), ring_y=cpu(self.ring_y),
+                    mean_count=int(self._mean_count), bpm_ring=cpu(self._bpm_ring), ptt_ring=cpu(self._ptt_ring),
+                    roi_count=int(self._roi_count), roi_hist=cpu(self._roi_hist))
+
+    def load_state_dict(self, state: dict) -> None:
+        if state.get('version') != STATE_VERSION:
+            raise ValueError(f"load_state_dict: unsupported state version {state.get('version')!r}")
+        if state['signature'] != self._signature():
+            raise ValueError(f"load_state_dict: state of a different engine geometry {state['signature']} != {self._signature()}")
+
+        def put(dst, src, name):
+            if (dst is None) != (src is None):
+                raise ValueError(f'load_state_dict: {name} present on one side only')
+            if dst is not None:
+                if tuple(dst.shape) != tuple(src.shape) or dst.dtype != src.dtype:
+                    raise ValueError(f'load_state_dict: {name} has shape {tuple(src.shape)}, expected {tuple(dst.shape)}')
+                dst.copy_(src)
+        put(self.ring_t, state['ring_t'], 'ring_t')
+        put(self.ring_y, state['ring_y'], 'ring_y')
+        put(self._bpm_ring, state['bpm_ring'], 'bpm_ring')
+        put(self._ptt_ring, state['ptt_ring'], 'ptt_ring')
+        put(self._roi_hist, state['roi_hist'], 'roi_hist')
+        self.count, self._mean_count, self._roi_count = int(state['count']), int(state['mean_count']), int(state['roi_count'])
+
     def reset(self):
-        self.ring_t.fill_(float('nan'))
-        self.ring_y.fill_(float('nan'))
+        """Back to the state of a freshly constructed engine: empty rings AND empty bpm / ptt / ROI histories."""
+        nan = float('nan')
+        self.ring_t.fill_(nan)
+        self.ring_y.fill_(nan)
         self.count = 0
+        for t in (self._bpm_ring, self._ptt_ring, self._roi_hist):
+            if t is not None:
+                t.fill_(nan)
+        self._mean_count = self._roi_count = 0

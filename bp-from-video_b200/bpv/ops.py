@@ -13,6 +13,20 @@ from . import _cabi
 from ._cabi import WindowParams, check, lib, ptr, stream_handle
 
 
+def _run(dev: torch.device, name: str, *args) -> None:
+    """Call libbpv entry point `name` with `args` + the current stream of `dev`, with `dev` as the CUDA device of the
+    calling thread: kernels are enqueued on the GPU that owns the tensors, whatever the caller's current device is."""
+    fn = getattr(lib(), name)
+    if dev.type != 'cuda':
+        raise _cabi.BpvError(f'{name}: tensors must live on a CUDA device (no CPU fallback)')
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            check(fn(*args, stream_handle(idx)), name)
+    else:
+        check(fn(*args, stream_handle(idx)), name)
+
+
 def _dev_accessible(t: torch.Tensor) -> bool:
     return t.is_cuda or t.is_pinned()
 
@@ -33,9 +47,8 @@ def roi_sample(frames: torch.Tensor, boxes: torch.Tensor, mode: int, *, want_sum
         out_value = torch.empty((N, R), dtype=torch.float64, device=dev)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=dev) if want_sums else None
     fstride = frames.stride(0) if N > 1 else H * frames.stride(1)
-    check(lib().bpv_roi_sample_u8(ptr(frames), None, fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode),
-                                  ptr(sums), ptr(out_value), int(roi_pixels_hint), stream_handle()),
-          'bpv_roi_sample_u8')
+    _run(boxes.device, 'bpv_roi_sample_u8', ptr(frames), None, fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode),
+                                  ptr(sums), ptr(out_value), int(roi_pixels_hint))
     return out_value, sums
 
 
@@ -47,9 +60,8 @@ def roi_sample_ptrs(frame_ptrs: torch.Tensor, H: int, W: int, row_stride: int, b
     R = boxes.shape[1]
     out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
-    check(lib().bpv_roi_sample_u8(None, ptr(frame_ptrs), 0, row_stride, H, W, N, ptr(boxes), R, int(mode),
-                                  ptr(sums), ptr(out_value), int(roi_pixels_hint), stream_handle()),
-          'bpv_roi_sample_u8')
+    _run(boxes.device, 'bpv_roi_sample_u8', None, ptr(frame_ptrs), 0, row_stride, H, W, N, ptr(boxes), R, int(mode),
+                                  ptr(sums), ptr(out_value), int(roi_pixels_hint))
     return out_value, sums
 
 
@@ -63,8 +75,8 @@ def calc_rois(present, bbox, points, num_points, rel_bbox, hist, g0: int, want_l
     boxes = torch.empty((S, T, R, 4), dtype=torch.int32, device=dev)
     loc = torch.empty((S, T, R, 6), dtype=torch.float64, device=dev) if want_locations else None
     smo = torch.empty((S, T, R, 6), dtype=torch.float64, device=dev) if want_locations else None
-    check(lib().bpv_calc_rois(ptr(present), ptr(bbox), ptr(points), ptr(num_points), ptr(rel_bbox), S, T, R, K, H, int(g0),
-                              ptr(hist), ptr(loc), ptr(smo), ptr(boxes), stream_handle()), 'bpv_calc_rois')
+    _run(present.device, 'bpv_calc_rois', ptr(present), ptr(bbox), ptr(points), ptr(num_points), ptr(rel_bbox), S, T, R, K, H, int(g0),
+                              ptr(hist), ptr(loc), ptr(smo), ptr(boxes))
     return (boxes, loc, smo) if want_locations else boxes
 
 
@@ -76,19 +88,22 @@ def running_mean(ring, g0: int, values, scale: float):
     assert values.shape == (S, T, C_) and values.is_contiguous()
     mean = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
     mean_int = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
-    check(lib().bpv_running_mean(ptr(ring), S, C_, H, int(g0), T, ptr(values), float(scale), ptr(mean), ptr(mean_int),
-                                 stream_handle()), 'bpv_running_mean')
+    _run(ring.device, 'bpv_running_mean', ptr(ring), S, C_, H, int(g0), T, ptr(values), float(scale), ptr(mean), ptr(mean_int))
     return mean, mean_int
 
 
-def ring_push(ring_t: torch.Tensor, ring_y: torch.Tensor, g0: int, ts: torch.Tensor, values: torch.Tensor):
+def ring_push(ring_t: torch.Tensor, ring_y: torch.Tensor, g0: int, ts: torch.Tensor | None, values: torch.Tensor | None):
     """Append T samples per stream (signal_data.py:31-35, 94-98).  ring_t f64 [S,cap], ring_y f64 [S,R,cap],
-    ts f64 [S,T], values f64 [S,T,R]."""
+    ts f64 [S,T], values f64 [S,T,R]; either of ts / values may be None (timestamps pushed ahead of the samples)."""
     S, R, cap = ring_y.shape
-    T = ts.shape[1]
-    assert ts.shape == (S, T) and values.shape == (S, T, R) and ts.is_contiguous() and values.is_contiguous()
-    check(lib().bpv_ring_push(ptr(ring_t), ptr(ring_y), S, R, cap, int(g0), T, ptr(ts), ptr(values), stream_handle()),
-          'bpv_ring_push')
+    if ts is None and values is None:
+        raise ValueError('ring_push: nothing to push')
+    T = ts.shape[1] if ts is not None else values.shape[1]
+    if ts is not None and not (ts.shape == (S, T) and ts.is_contiguous()):
+        raise ValueError('ring_push: ts must be a contiguous [S, T] tensor')
+    if values is not None and not (values.shape == (S, T, R) and values.is_contiguous()):
+        raise ValueError('ring_push: values must be a contiguous [S, T, R] tensor')
+    _run(ring_y.device, 'bpv_ring_push', ptr(ring_t), ptr(ring_y), S, R, cap, int(g0), T, ptr(ts), ptr(values))
 
 
 def make_params(S, R, cap, window, head0, head_step, jobs_per_stream, methods, transform, *, butter_order=16,
@@ -107,8 +122,7 @@ def make_params(S, R, cap, window, head0, head_step, jobs_per_stream, methods, t
     return p
 
 
-def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None, status=None, workspace=None):
-    """F2 (signal_processor.py:196-245).  Returns proc_x, proc_y f64 [J,R,window], status i32 [J,R]."""
+def _pre_buffers(ring_y, p, proc_x, proc_y, status, workspace):
     J = p.S * p.jobs_per_stream
     dev = ring_y.device
     proc_x = torch.empty((J, p.R, p.window), dtype=torch.float64, device=dev) if proc_x is None else proc_x
@@ -117,9 +131,38 @@ def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None,
     need = lib().bpv_window_workspace_bytes(C.byref(p))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    check(lib().bpv_window_preprocess(ptr(ring_t), ptr(ring_y), C.byref(p), ptr(workspace), workspace.numel(),
-                                      ptr(proc_x), ptr(proc_y), ptr(status), stream_handle()), 'bpv_window_preprocess')
+    return proc_x, proc_y, status, workspace
+
+
+def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None, status=None, workspace=None):
+    """F2 (signal_processor.py:196-245).  Returns proc_x, proc_y f64 [J,R,window], status i32 [J,R]."""
+    proc_x, proc_y, status, workspace = _pre_buffers(ring_y, p, proc_x, proc_y, status, workspace)
+    _run(ring_y.device, 'bpv_window_preprocess', ptr(ring_t), ptr(ring_y), C.byref(p), ptr(workspace), workspace.numel(),
+                                      ptr(proc_x), ptr(proc_y), ptr(status))
     return proc_x, proc_y, status
+
+
+def window_design(ring_t, p: WindowParams, workspace):
+    """make_filter of every window job into `workspace` (signal_processor.py:158-173): needs only the timestamps, so
+    it can run on another stream beside the ROI sampling of the same frames."""
+    _run(ring_t.device, 'bpv_window_design', ptr(ring_t), C.byref(p), ptr(workspace), workspace.numel())
+
+
+def window_filter(ring_t, ring_y, p: WindowParams, workspace, proc_x=None, proc_y=None, status=None):
+    """F2 given the designs `window_design` left in `workspace`."""
+    proc_x, proc_y, status, workspace = _pre_buffers(ring_y, p, proc_x, proc_y, status, workspace)
+    _run(ring_y.device, 'bpv_window_filter', ptr(ring_t), ptr(ring_y), C.byref(p), ptr(workspace), workspace.numel(),
+                                  ptr(proc_x), ptr(proc_y), ptr(status))
+    return proc_x, proc_y, status
+
+
+def probe_fma(dtype: str, iters: int, blocks: int, sink: torch.Tensor) -> int:
+    """Enqueue the FMA throughput probe (bench.py); returns the number of FMAs it executes."""
+    with torch.cuda.device(sink.device):
+        n = lib().bpv_probe_fma(1 if dtype == 'f64' else 0, int(iters), int(blocks), ptr(sink), stream_handle(sink.device.index))
+    if n < 0:
+        check(int(-n), 'bpv_probe_fma')
+    return int(n)
 
 
 def max_bins(p: WindowParams) -> int:
@@ -155,10 +198,9 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
     need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if not store else 0
     if need and (workspace is None or workspace.numel() < need):
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    check(lib().bpv_window_spectrum(ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
+    _run(proc_y.device, 'bpv_window_spectrum', ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
                                     ptr(o['freqs']), ptr(o['mags']),
-                                    ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']),
-                                    stream_handle()), 'bpv_window_spectrum')
+                                    ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']))
     return o
 
 
@@ -185,21 +227,20 @@ def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
     if 'lag_corr' not in o:
         o['lag_corr'] = torch.empty((J, P), dtype=torch.float64, device=dev)
     if P > 0:
-        check(lib().bpv_window_xcorr(ptr(proc_x), ptr(proc_y), C.byref(p), ptr(o['lags']), ptr(o['corr']),
-                                     ptr(o['num_lags']), ptr(o['lag_idx']), ptr(o['lag_sec']), ptr(o['lag_corr']),
-                                     stream_handle()), 'bpv_window_xcorr')
+        _run(proc_y.device, 'bpv_window_xcorr', ptr(proc_x), ptr(proc_y), C.byref(p), ptr(o['lags']), ptr(o['corr']),
+                                     ptr(o['num_lags']), ptr(o['lag_idx']), ptr(o['lag_sec']), ptr(o['lag_corr']))
     return o
 
 
 def butter_sos_design(fs: torch.Tensor, p: WindowParams):
     out = torch.empty((fs.numel(), p.butter_order, 6), dtype=torch.float64, device=fs.device)
-    check(lib().bpv_butter_sos_design(ptr(fs), fs.numel(), C.byref(p), ptr(out), stream_handle()), 'bpv_butter_sos_design')
+    _run(fs.device, 'bpv_butter_sos_design', ptr(fs), fs.numel(), C.byref(p), ptr(out))
     return out
 
 
 def firls_design(fs: torch.Tensor, p: WindowParams):
     out = torch.empty((fs.numel(), p.fir_taps), dtype=torch.float64, device=fs.device)
-    check(lib().bpv_firls_design(ptr(fs), fs.numel(), C.byref(p), ptr(out), stream_handle()), 'bpv_firls_design')
+    _run(fs.device, 'bpv_firls_design', ptr(fs), fs.numel(), C.byref(p), ptr(out))
     return out
 
 
@@ -208,8 +249,8 @@ def view_boxes(boxes: torch.Tensor, view_w: int, view_h: int, left: int = 0, fli
     horizontal flip; video_reader.py:97-103) onto the decoded frame.  No pixel is copied."""
     assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[-1] == 4
     out = torch.empty_like(boxes) if out is None else out
-    check(lib().bpv_view_boxes(ptr(boxes), boxes.numel() // 4, int(view_w), int(view_h), int(left), int(bool(flip_horizontally)),
-                               ptr(out), stream_handle()), 'bpv_view_boxes')
+    _run(boxes.device, 'bpv_view_boxes', ptr(boxes), boxes.numel() // 4, int(view_w), int(view_h), int(left), int(bool(flip_horizontally)),
+                               ptr(out))
     return out
 
 
@@ -219,9 +260,27 @@ def pack_records(peak_freq, lag_sec, peak_idx, lag_idx, out=None):
     P = lag_sec.shape[1]
     if out is None:
         out = torch.empty((J, 2 * R + 2 * P), dtype=torch.float64, device=peak_freq.device)
-    check(lib().bpv_pack_records(ptr(peak_freq), ptr(lag_sec) if P else None, ptr(peak_idx), ptr(lag_idx) if P else None,
-                                 J, R, P, ptr(out), stream_handle()), 'bpv_pack_records')
+    _run(peak_freq.device, 'bpv_pack_records', ptr(peak_freq), ptr(lag_sec) if P else None, ptr(peak_idx), ptr(lag_idx) if P else None,
+                                 J, R, P, ptr(out))
     return out
+
+
+def pack_records32(peak_freq, lag_sec, peak_idx, lag_idx, out=None):
+    """[J, 2R + 2P] int32 words: (bpm f32, ptt_ms f32, peak_idx i32, lag_idx i32) — the 24-byte record of SURVEY.md 8(e).
+    `unpack_records32` splits it again."""
+    J, R = peak_freq.shape
+    P = lag_sec.shape[1]
+    if out is None:
+        out = torch.empty((J, 2 * R + 2 * P), dtype=torch.int32, device=peak_freq.device)
+    _run(peak_freq.device, 'bpv_pack_records32', ptr(peak_freq), ptr(lag_sec) if P else None, ptr(peak_idx), ptr(lag_idx) if P else None,
+         J, R, P, ptr(out))
+    return out
+
+
+def unpack_records32(rec: torch.Tensor, R: int, P: int):
+    """(bpm f32 [J,R], ptt_ms f32 [J,P], peak_idx i32 [J,R], lag_idx i32 [J,P]) views of a packed int32 record tensor."""
+    f = rec.view(torch.float32)
+    return f[:, :R], f[:, R:R + P], rec[:, R + P:2 * R + P], rec[:, 2 * R + P:]
 
 
 def dft256_tc(z: torch.Tensor) -> torch.Tensor:
@@ -229,7 +288,7 @@ def dft256_tc(z: torch.Tensor) -> torch.Tensor:
     [:, :129] = Re X[0..128] and [:, 129:] = -Im X[1..127]."""
     assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2 and z.shape[1] == 256
     d = torch.empty_like(z)
-    check(lib().bpv_dft256_tc(ptr(z), z.shape[0], ptr(d), stream_handle()), 'bpv_dft256_tc')
+    _run(z.device, 'bpv_dft256_tc', ptr(z), z.shape[0], ptr(d))
     return d
 
 
@@ -244,8 +303,8 @@ def roi_sample_nv12(frames: torch.Tensor, H: int, W: int, boxes: torch.Tensor, m
     out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
     fstride = frames.stride(0) if N > 1 else frames.shape[1] * frames.stride(1)
-    check(lib().bpv_roi_sample_nv12(ptr(frames), fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode), ptr(sums),
-                                    ptr(out_value), stream_handle()), 'bpv_roi_sample_nv12')
+    _run(boxes.device, 'bpv_roi_sample_nv12', ptr(frames), fstride, frames.stride(1), H, W, N, ptr(boxes), R, int(mode), ptr(sums),
+                                    ptr(out_value))
     return out_value, sums
 
 
@@ -261,6 +320,38 @@ def roi_sample_resized(frames: torch.Tensor, dst_h: int, dst_w: int, boxes: torc
     out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
     fstride = frames.stride(0) if N > 1 else H * frames.stride(1)
-    check(lib().bpv_roi_sample_resized_u8(ptr(frames), fstride, frames.stride(1), H, W, int(dst_h), int(dst_w), N, ptr(boxes), R,
-                                          int(mode), ptr(sums), ptr(out_value), stream_handle()), 'bpv_roi_sample_resized_u8')
+    _run(boxes.device, 'bpv_roi_sample_resized_u8', ptr(frames), fstride, frames.stride(1), H, W, int(dst_h), int(dst_w), N, ptr(boxes), R,
+                                          int(mode), ptr(sums), ptr(out_value))
+    return out_value, sums
+
+
+def roi_sample_masked(frames: torch.Tensor, masks: torch.Tensor, categories, boxes: torch.Tensor, mode: int, *,
+                      want_sums: bool = False):
+    """F1 through a segmentation mask: frames uint8 [N, H, W, 3], masks uint8 [N, H, W] per-pixel
+    categories (the person segmenter's category_mask, inference_runner.py:154-166), categories = one int for all ROIs or
+    an int32 [R] tensor / sequence; boxes int32 [N, R, 4].  Only pixels whose category matches contribute; returns
+    (value f64 [N, R], sums (sumB, sumG, sumR, N_selected) | None)."""
+    if not (frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and _dev_accessible(frames)):
+        raise ValueError('roi_sample_masked: frames must be uint8 [N, H, W, 3] in CUDA or pinned host memory')
+    if not (frames.stride(3) == 1 and frames.stride(2) == 3):
+        raise ValueError('roi_sample_masked: pixels must be packed BGR')
+    N, H, W, _ = frames.shape
+    if not (masks.dtype == torch.uint8 and tuple(masks.shape) == (N, H, W) and masks.stride(2) == 1 and _dev_accessible(masks)):
+        raise ValueError('roi_sample_masked: masks must be uint8 [N, H, W] with contiguous rows')
+    if not (boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4):
+        raise ValueError('roi_sample_masked: boxes must be a contiguous CUDA int32 [N, R, 4] tensor')
+    R = boxes.shape[1]
+    dev = boxes.device
+    if isinstance(categories, int):
+        categories = [categories] * R
+    if not torch.is_tensor(categories):
+        categories = torch.tensor(list(categories), dtype=torch.int32, device=dev)
+    if not (categories.dtype == torch.int32 and categories.numel() == R and categories.device == dev):
+        raise ValueError(f'roi_sample_masked: categories must be {R} int32 values on {dev}')
+    out_value = torch.empty((N, R), dtype=torch.float64, device=dev)
+    sums = torch.empty((N, R, 4), dtype=torch.int64, device=dev) if want_sums else None
+    fstride = frames.stride(0) if N > 1 else H * frames.stride(1)
+    mstride = masks.stride(0) if N > 1 else H * masks.stride(1)
+    _run(dev, 'bpv_roi_sample_masked_u8', ptr(frames), fstride, frames.stride(1), ptr(masks), mstride, masks.stride(1), H, W, N,
+         ptr(boxes), R, ptr(categories.contiguous()), int(mode), ptr(sums), ptr(out_value))
     return out_value, sums

@@ -79,3 +79,48 @@ def raw_signals(rng, ts, R=2, f_pulse=None, dc=120.0, ac=0.5, noise=0.15, delay_
     if p_nan > 0:
         y[rng.uniform(size=y.shape) < p_nan] = np.nan
     return y
+
+
+def detections(rng, n, H, W, jitter=2, p_none=0.01):
+    """Detector outputs per frame, in the form the reference's calc_rois consumes (signal_processor.py:133-155;
+    inference_runner.py:125-132): face bbox [n,4] + its landmark 151 [n,2], hand bbox [n,4] + its landmarks 0 and 9
+    [n,2,2], present [n,2].  Geometry as roi_boxes: face bbox 0.25W x 0.4H around (0.45W, 0.3H), hand bbox 0.2W x 0.33H
+    around (0.7W, 0.75H), anchors jittered by +-jitter px, p_none missing detections."""
+    out = {}
+    for name, (cx, cy), (bw, bh) in (('face', (0.45 * W, 0.30 * H), (0.25 * W, 0.40 * H)),
+                                     ('hand', (0.70 * W, 0.75 * H), (0.20 * W, 0.33 * H))):
+        ax = np.rint(cx + rng.integers(-jitter, jitter + 1, n)).astype(np.int64)
+        ay = np.rint(cy + rng.integers(-jitter, jitter + 1, n)).astype(np.int64)
+        out[name + '_bbox'] = np.stack([np.rint(ax - bw / 2), np.rint(ay - bh / 2), np.rint(ax - bw / 2) + np.rint(bw),
+                                        np.rint(ay - bh / 2) + np.rint(bh)], axis=1).astype(np.int64)
+        out[name + '_pt'] = np.stack([ax, ay], axis=1)
+    out['present'] = rng.uniform(size=(n, 2)) >= p_none
+    return out
+
+
+class _ModelOut:
+    def __init__(self, detections):
+        self.detections = detections
+
+
+class ModelResults:
+    """Stand-in for inference_runner.InferenceResults: the two attributes calc_rois reads (signal_processor.py:136-139)."""
+
+    def __init__(self, det, i):
+        face, hand = [], []
+        if det['present'][i, 0]:
+            pts = np.zeros((478, 2), np.int64)
+            pts[151] = det['face_pt'][i]
+            face = [(tuple(int(v) for v in det['face_bbox'][i]), pts)]
+        if det['present'][i, 1]:
+            pts = np.zeros((21, 2), np.int64)
+            pts[0] = pts[9] = det['hand_pt'][i]
+            hand = [(tuple(int(v) for v in det['hand_bbox'][i]), pts)]
+        self.face_landmarker, self.hand_landmarker = _ModelOut(face), _ModelOut(hand)
+
+
+class FrameData:
+    """Stand-in for video_reader.FrameData: the two attributes process() reads (signal_processor.py:304-307)."""
+
+    def __init__(self, frame, timestamp):
+        self.frame, self.timestamp = frame, timestamp

@@ -51,3 +51,35 @@ extern "C" int bpv_get_l2_fetch_granularity(void) {
   if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) return -1;
   return (int)v;
 }
+
+
+// ---- FMA throughput probe (bench.py: measured FP64 / FP32 peaks for the roofline of the filter / spectrum families) ----
+namespace bpv {
+template <typename T>
+__global__ void __launch_bounds__(256) probe_fma_kernel(long long iters, T* sink) {
+  T a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (T)(threadIdx.x + i) * (T)1e-3;
+  const T m = (T)0.999999, c = (T)1e-7;
+  for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+    }
+  }
+  T sres = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sres += a[i];
+  if (!(sres == sres)) *sink = sres;      // never true: keeps the chain alive
+}
+}  // namespace bpv
+
+extern "C" int64_t bpv_probe_fma(int32_t dtype, int64_t iters, int32_t blocks, void* sink, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(sink && iters > 0 && blocks > 0 && (dtype == 0 || dtype == 1), BPV_E_INVALID, "bpv_probe_fma: bad arguments");
+  if (dtype == 1) probe_fma_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, (double*)sink);
+  else probe_fma_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, (float*)sink);
+  if (int rc = check_launch("bpv_probe_fma")) return -(int64_t)rc;
+  return (int64_t)blocks * 256 * iters * 32;
+}

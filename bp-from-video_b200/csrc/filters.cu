@@ -78,7 +78,8 @@ __device__ __forceinline__ double group_sum_d(double v) {
 //   x'[i]      = x[i] + (y[k] - ex) * rev(f')[i]
 // so one pass over the elements updates both vectors with a single reversed read of the old f from shared memory.
 __device__ void firls_design_group(double fs, bool live, int taps, double min_freq, double max_freq, double df,
-                                   double* __restrict__ out, double* __restrict__ zi_out, double* smem) {
+                                   double* __restrict__ out, double* __restrict__ zi_out, double* __restrict__ ac_out,
+                                   double* smem) {
   const int M = (taps - 1) / 2, n = taps;
   double* r = smem + FIRLS_PAD;                 // [128] first column of T: q[0 .. taps-1]; r[-PAD .. -1] = 0
   double* fA = r + 128 + FIRLS_PAD;             // forward vector, ping (fA[-PAD .. -1] = 0)
@@ -223,6 +224,35 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
       run += hs[i];
     }
   }
+  if (ac_out) {
+    // Autocorrelation of the taps, ac[d] = sum_i h[i] h[i+d] (d = 0 .. 127; 0 beyond taps-1): filtfilt's forward and
+    // backward passes merged into ONE symmetric filter h * rev(h) of 2*taps-1 coefficients ac[|k|], which the
+    // preprocessing kernel applies wherever the padding keeps the initial-condition terms out of the cropped output
+    // (window_pre.cu fir_merged).  Lane `sub` owns the 16 consecutive lags [16 sub, 16 sub + 16) as a register-tiled
+    // sliding dot product; hs[] is zero beyond the taps (r's pad in front of fA), so no bounds are tested.
+    constexpr int E = FIRLS_EPL;
+    const int d0 = E * sub;
+    double acc[E], wv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { acc[e] = 0.0; wv[e] = hs[d0 + e]; }
+    const int nblk = (128 - d0) / E;                 // h[i + d] == 0 for i >= 128 - d0
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+      const double* hc = hs + blk * E;
+      const double* hn = hs + blk * E + d0 + E;
+#pragma unroll
+      for (int ii = 0; ii < E; ++ii) {
+        const double ck = hc[ii];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = fma(ck, wv[(e + ii) % E], acc[e]);
+        wv[ii] = hn[ii];                             // h[i + d0 + E] replaces h[i + d0]
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) ac_out[d0 + e] = ok ? acc[e] : nan_f64();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const double* __restrict__ fs, int n, int taps, double min_freq,
@@ -231,7 +261,7 @@ __global__ void __launch_bounds__(FIRLS_THREADS) firls_from_fs_kernel(const doub
   const int d = threadIdx.x / FIRLS_LPD, job = blockIdx.x * FIRLS_DPB + d;
   const bool live = job < n;
   firls_design_group(live ? fs[job] : 30.0, live, taps, min_freq, max_freq, df, out + (long long)(live ? job : 0) * taps, nullptr,
-                     smem + firls_smem_offset(d));
+                     nullptr, smem + firls_smem_offset(d));
 }
 
 // ---- per-job design from the ring timestamps (used by the window pipeline) ----------------------
@@ -284,8 +314,8 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
     fs = nan_f64();
     if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
   }
-  double* o = out + (long long)(live ? job : 0) * 256;
-  firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, smem + firls_smem_offset(d));
+  double* o = out + (long long)(live ? job : 0) * FIR_WS_STRIDE;      // taps [128] | lfilter_zi [128] | autocorrelation [128]
+  firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, o + 256, smem + firls_smem_offset(d));
 }
 
 constexpr size_t FIRLS_SMEM = (size_t)(firls_smem_offset(FIRLS_DPB - 1) + FIRLS_WS) * sizeof(double);

@@ -7,6 +7,7 @@ namespace bpv {
 
 constexpr int MAX_SOS = 16;     // butter_order <= 16 -> <= 16 second-order sections
 constexpr int MAX_TAPS = 127;   // fir_taps <= 127 (odd)
+constexpr int FIR_WS_STRIDE = 384;   // doubles of filter workspace per window job: taps [128] | lfilter_zi [128] | tap autocorrelation [128]
 
 // status codes written to the per-signal status array
 constexpr int ST_OK = 0, ST_GUARD = 1, ST_CUBIC_X = 2, ST_BAD_BANDS = 3;

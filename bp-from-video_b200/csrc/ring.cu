@@ -15,15 +15,15 @@ __global__ void ring_push_kernel(double* __restrict__ ring_t, double* __restrict
   const int t = (int)(st % T);
   const long long s = st / T;
   const int slot = (int)((g0 + t) % cap);
-  if (c == R) ring_t[s * cap + slot] = ts[s * T + t];
-  else ring_y[(s * R + c) * cap + slot] = values[(s * T + t) * R + c];
+  if (c == R) { if (ts) ring_t[s * cap + slot] = ts[s * T + t]; }
+  else if (values) ring_y[(s * R + c) * cap + slot] = values[(s * T + t) * R + c];
 }
 }  // namespace bpv
 
 extern "C" int bpv_ring_push(double* ring_t, double* ring_y, int32_t S, int32_t R, int32_t cap,
                              int64_t g0, int32_t T, const double* ts, const double* values, void* stream) {
   using namespace bpv;
-  BPV_REQUIRE(ring_t && ring_y && ts && values, BPV_E_INVALID, "bpv_ring_push: NULL pointer");
+  BPV_REQUIRE(ring_t && ring_y && (ts || values), BPV_E_INVALID, "bpv_ring_push: NULL pointer");
   BPV_REQUIRE(S > 0 && R > 0 && cap > 0 && T > 0 && T <= cap && g0 >= 0, BPV_E_INVALID, "bpv_ring_push: bad sizes");
   const long long total = (long long)S * T * (R + 1);
   ring_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ring_t, ring_y, S, R, cap, g0, T, ts, values);
@@ -126,4 +126,37 @@ extern "C" int bpv_pack_records(const double* peak_freq, const double* lag_sec, 
   const long long n = J * (2 * R + 2 * P);
   pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(peak_freq, lag_sec, peak_idx, lag_idx, J, R, P, out);
   return check_launch("bpv_pack_records");
+}
+
+
+// Compact form of the same record, SURVEY.md 8(e): 4-byte words (bpm f32 [R], ptt_ms f32 [P], peak_idx i32 [R],
+// lag_idx i32 [P]) = 24 B per window job at R = 2 — what the per-step NCCL gather moves.  bpm / ptt are rounded from
+// the float64 result once, here; the bins travel exactly.
+namespace bpv {
+__global__ void pack_records32_kernel(const double* __restrict__ peak_freq, const double* __restrict__ lag_sec,
+                                      const int32_t* __restrict__ peak_idx, const int32_t* __restrict__ lag_idx,
+                                      long long J, int R, int P, int32_t* __restrict__ out) {
+  const int C = 2 * R + 2 * P;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= J * C) return;
+  const long long j = i / C;
+  const int c = (int)(i % C);
+  int32_t v;
+  if (c < R) v = __float_as_int((float)(peak_freq[j * R + c] * 60));
+  else if (c < R + P) v = __float_as_int((float)(lag_sec[j * P + (c - R)] * 1000));
+  else if (c < 2 * R + P) v = peak_idx[j * R + (c - R - P)];
+  else v = lag_idx[j * P + (c - 2 * R - P)];
+  out[i] = v;
+}
+}  // namespace bpv
+
+extern "C" int bpv_pack_records32(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx,
+                                  const int32_t* lag_idx, int64_t J, int32_t R, int32_t P, int32_t* out, void* stream) {
+  using namespace bpv;
+  BPV_REQUIRE(peak_freq && peak_idx && out && (P == 0 || (lag_sec && lag_idx)), BPV_E_INVALID, "bpv_pack_records32: NULL pointer");
+  BPV_REQUIRE(J >= 0 && R > 0 && P >= 0, BPV_E_INVALID, "bpv_pack_records32: bad sizes");
+  if (J == 0) return 0;
+  const long long n = J * (2 * R + 2 * P);
+  pack_records32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(peak_freq, lag_sec, peak_idx, lag_idx, J, R, P, out);
+  return check_launch("bpv_pack_records32");
 }

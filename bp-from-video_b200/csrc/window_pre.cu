@@ -23,8 +23,23 @@ int check_filter_params(const bpv_window_params* p, const char* who);
 
 struct PreLayout {        // per-warp shared-memory plan, in bytes
   int yv, xv, posv, posb, buf0, buf1, coef, total;
-  int buf_len;            // doubles in buf0 / buf1
+  int buf_len;            // doubles in buf0
+  // FIR sub-plan inside buf0 (doubles): merged path  XT [0, fir_c) | c [fir_c, fir_c + Kmax)
+  //                                     two-pass path XT [0, fir_gt) | GT [fir_gt, fir_b) | b [fir_b, +136) | zi [+136, +264)
+  int fir_c, fir_gt, fir_b;
 };
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+// two-pass FIR (windows shorter than the filter): leading dimensions of the de-interleaved operand buffers
+__host__ __device__ inline int fir_ld_fwd(int n, int T) {
+  int LD = (round_up(T, 8) + n + T + 15) / 8 + 1;
+  LD += (6 - (LD & 3)) & 3;   // LD = 2 (mod 4): the 8 rows of XT start 4 banks apart, the extension stores without conflicts
+  return LD;
+}
+__host__ __device__ inline int fir_ld_bwd(int n, int T) { return (round_up(T, 10) + n + T + 20) / 10 + 1; }
+// merged FIR: 2T-1 taps padded to a multiple of the tile, outputs m = 0 .. n-1 at storage index m + K
+__host__ __device__ inline int fir_merged_k(int T, int RT) { return round_up(2 * T - 1, RT); }
+__host__ __device__ inline int fir_merged_ld(int n, int T, int RT) { return (fir_merged_k(T, RT) / RT + (n + RT - 1) / RT) | 1; }
 
 __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   bool interp = false, cubic = false, butter = false, fir = false;
@@ -41,16 +56,27 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
   if (pad > W - 1) pad = W - 1 > 0 ? W - 1 : 0;
   PreLayout L;
   L.buf_len = butter ? W + 2 * pad : (interp ? W : 0);
-  if (fir) {   // FIR stages only the operands that reach the cropped output: Kp + n + T + tile slack (fir_filtfilt)
-    const int need = W + 2 * 128 + 48;   // 8 * LD <= W + 302 (LD rounded up to 2 mod 4), 10 * LDB <= W + 287
+  L.fir_c = L.fir_gt = L.fir_b = 0;
+  if (fir) {
+    const int T = p.fir_taps, nf = W < T - 1 ? W : T - 1;          // the two-pass path only sees windows of n < T samples
+    L.fir_gt = 8 * fir_ld_fwd(nf, T);
+    L.fir_b = L.fir_gt + 10 * fir_ld_bwd(nf, T);
+    int need = L.fir_b + 136 + 128;
+    if (W >= T) {
+      const int x8 = 8 * fir_merged_ld(W, T, 8), x10 = 10 * fir_merged_ld(W, T, 10);
+      L.fir_c = x8 > x10 ? x8 : x10;
+      const int k8 = fir_merged_k(T, 8), k10 = fir_merged_k(T, 10);
+      const int m = L.fir_c + (k8 > k10 ? k8 : k10);
+      if (m > need) need = m;
+    }
     if (need > L.buf_len) L.buf_len = need;
   }
   int o = 0;
   L.yv = o; o += W * 8;
   L.xv = o; o += interp ? W * 8 : 0;
-  L.buf0 = o; o += (butter || fir || interp) ? L.buf_len * 8 : 0;
-  L.buf1 = o; o += (fir || cubic) ? L.buf_len * 8 : 0;
-  L.coef = o; o += (butter || fir) ? 272 * 8 : 0;      // FIR: taps [130 padded] | lfilter_zi at +136
+  L.buf0 = o; o += L.buf_len * 8;
+  L.buf1 = o; o += cubic ? W * 8 : 0;                  // knot slopes of the spline
+  L.coef = o; o += butter ? 128 * 8 : 0;               // sos [16][6] | sosfilt_zi [16][2]
   L.posv = o; o += ((W * 2 + 7) / 8) * 8;
   L.posb = o; o += interp ? ((W * 2 + 7) / 8) * 8 : 0;
   L.total = o;
@@ -68,6 +94,7 @@ struct Warp {
   int n, m;            // valid (finite y) / block (finite x) counts
   double xfirst, xlast;
   bool grid;           // x[block] has been replaced by the uniform grid (after an INTERP_*)
+  int fir_c, fir_gt, fir_b;   // FIR sub-plan inside buf0 (PreLayout)
 };
 
 __device__ void diff1(Warp& w) {  // np.diff(y, n=1, prepend=y[0])  (signal_processor.py:203)
@@ -394,8 +421,8 @@ constexpr int FIR_RTB = 10;   // backward pass: n outputs (300) = ONE round of 3
 __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) {
   const int Kp = (T + FIR_RT - 1) / FIR_RT * FIR_RT;
   const int KpB = (T + FIR_RTB - 1) / FIR_RTB * FIR_RTB;
-  double* b = w.coef;          // [max(Kp, KpB)] zero padded
-  double* zi = w.coef + 136;   // [T-1]
+  double* b = w.buf0 + w.fir_b;   // [max(Kp, KpB)] zero padded
+  double* zi = b + 136;           // [T-1]
   {   // all nine global loads of the lane in flight before the first store (taps 0..135 zero padded | lfilter_zi from the design kernel)
     double tb[5], tz[4];
 #pragma unroll
@@ -417,8 +444,8 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   int LD = (Kp + n + T + 15) / FIR_RT + 1;
   LD += (6 - (LD & 3)) & 3;   // LD = 2 (mod 4): the 8 rows of XT start 4 banks apart, the extension below stores without conflicts
   const int LDB = (KpB + n + T + 2 * FIR_RTB) / FIR_RTB + 1;
-  double* XT = w.buf0;   // ext, de-interleaved by FIR_RT
-  double* GT = w.buf1;   // reversed forward output G[g] = F[L-1-g], de-interleaved by FIR_RTB
+  double* XT = w.buf0;              // ext, de-interleaved by FIR_RT
+  double* GT = w.buf0 + w.fir_gt;   // reversed forward output G[g] = F[L-1-g], de-interleaved by FIR_RTB
   const double y_first = w.yv[0], y_last = w.yv[n - 1];
   // odd extension (scipy.signal._arraytools.odd_ext), branch free so that the unrolled iterations overlap their loads:
   // head 2*y[0] - y[p-i], body y[i-p], tail 2*y[n-1] - y[2n-2+p-i], zero outside [0, L)
@@ -473,14 +500,82 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
   __syncwarp();
 }
 
+// filtfilt with both passes merged: wherever the padding is at least T-1 samples (n >= T), neither pass's initial
+// condition reaches the cropped output and forward . backward collapses into ONE symmetric FIR of 2T-1 taps,
+//   out[m] = sum_{d=-(T-1)}^{T-1} ac[|d|] ext[p + m + d],        ac[d] = sum_i b[i] b[i+d]   (from the design kernel)
+// (F[f] = sum_k b[k] ext[f-k] for f >= p >= T-1 has no zi term and no zero history; B[i] for i in [p, p+n-1] likewise.)
+// 253 x n multiply-adds instead of 127 x (2n + 126), one staged operand buffer instead of two, no intermediate signal;
+// agrees with the two-pass form to rounding (1e-15 relative).  RT consecutive outputs per lane (corr_tile.cuh): RT = 10
+// makes a 300-sample window ONE round of 30 lanes, RT = 8 a 250-sample window one round of 32.
+template <int RT>
+__device__ void fir_merged(Warp& w, const double* __restrict__ ac_g, int T) {
+  const int M = T - 1;
+  const int K = fir_merged_k(T, RT);
+  const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;      // signal_processor.py:233-234
+  const int L = n + 2 * p;
+  const int tiles = (n + RT - 1) / RT;
+  const int LD = (K / RT + tiles) | 1;
+  double* XT = w.buf0;              // X[j] = ext[j + xbase], de-interleaved by RT; output m sits at j = m + K
+  double* c = w.buf0 + w.fir_c;     // c[k] = ac[|k - M|], k = 0 .. 2M; zero up to K
+  for (int k = w.lane; k < K; k += 32) {
+    const int d = k < M ? M - k : k - M;
+    c[k] = k <= 2 * M ? ac_g[d] : 0.0;
+  }
+  const int xbase = p + M - K;
+  const double y_first = w.yv[0], y_last = w.yv[n - 1];
+  // odd extension (scipy.signal._arraytools.odd_ext): head 2*y[0] - y[p-i], body y[i-p], tail 2*y[n-1] - y[2n-2+p-i];
+  // indices outside [0, L) only meet the zero taps k > 2M
+  const int total = RT * (K / RT + tiles);
+#pragma unroll 3
+  for (int jj = w.lane; jj < total; jj += 32) {
+    const int i = jj + xbase;
+    const bool inside = i >= 0 && i < L, hd = i < p, tl = i >= p + n;
+    const int src = hd ? p - i : (tl ? 2 * n - 2 + p - i : i - p);
+    const double y = w.yv[inside ? src : 0];
+    const double v = hd ? 2.0 * y_first - y : (tl ? 2.0 * y_last - y : y);
+    XT[xt_index<RT>(jj, LD)] = inside ? v : 0.0;
+  }
+  __syncwarp();
+  for (int t = w.lane; t < tiles; t += 32) {
+    double acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    corr_tile<RT, double>(acc, c, K, XT, LD, K + RT * t);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int m = RT * t + r;
+      if (m < n) w.yv[m] = acc[r];          // yv is not an operand of the tiles: no hazard with the other lanes
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void fir_apply(Warp& w, const double* __restrict__ tg, int T) {
+  const int n = w.n;
+  if (n >= T) {
+    // the cheaper tiling for this window length: rounds x RT x padded taps
+    const int c8 = ((n + 7) / 8 + 31) / 32 * 8 * fir_merged_k(T, 8);
+    const int c10 = ((n + 9) / 10 + 31) / 32 * 10 * fir_merged_k(T, 10);
+    if (c10 < c8) fir_merged<10>(w, tg + 256, T);
+    else fir_merged<8>(w, tg + 256, T);
+  } else {
+    fir_filtfilt(w, tg, T);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __restrict__ ring_t,
-                                                                const double* __restrict__ ring_y,
-                                                                const bpv_window_params p, const PreLayout L,
-                                                                const double* __restrict__ sos_ws,
-                                                                const double* __restrict__ taps_ws,
-                                                                double* __restrict__ proc_x, double* __restrict__ proc_y,
-                                                                int32_t* __restrict__ status) {
+// FEAT = which of the heavy stages this instantiation contains (register budget and code size follow the method list):
+// bit 0 INTERP_*, bit 1 FILTER_BUTTER, bit 2 FILTER_FIR.  diff / detrend are always present.
+constexpr int F_INTERP = 1, F_BUTTER = 2, F_FIR = 4;
+
+template <int FEAT, int MINB>
+__global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const double* __restrict__ ring_t,
+                                                                      const double* __restrict__ ring_y,
+                                                                      const bpv_window_params p, const PreLayout L,
+                                                                      const double* __restrict__ sos_ws,
+                                                                      const double* __restrict__ taps_ws,
+                                                                      double* __restrict__ proc_x, double* __restrict__ proc_y,
+                                                                      int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long sig = (long long)blockIdx.x * wpb + wib;       // job * R + r
@@ -497,6 +592,7 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   w.posv = reinterpret_cast<unsigned short*>(sm + L.posv);
   w.posb = reinterpret_cast<unsigned short*>(sm + L.posb);
   w.grid = false;
+  w.fir_c = L.fir_c; w.fir_gt = L.fir_gt; w.fir_b = L.fir_b;
 
   const long long job = sig / p.R;
   const int r = (int)(sig % p.R);
@@ -507,15 +603,15 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   double* ox = proc_x + sig * p.window;
   double* oy = proc_y + sig * p.window;
   const int W = p.window;
-  bool has_interp = false;
-  for (int i = 0; i < p.num_methods; ++i) has_interp |= (p.methods[i] == BPV_INTERP_LINEAR || p.methods[i] == BPV_INTERP_CUBIC);
+  constexpr bool has_interp = (FEAT & F_INTERP) != 0;
 
-  // the job's filter coefficients are first needed after the gather and the detrend: start pulling their 2 KB (taps | zi,
-  // 16 lines) resp. 768 B (sos) towards the SM now, so that the filter stage does not open with a DRAM round trip
+  // the job's filter coefficients are first needed after the gather and the detrend: start pulling them (taps | zi |
+  // autocorrelation: 24 lines, resp. 768 B of sos) towards the SM now, so that the filter stage does not open with a
+  // DRAM round trip
   for (int i = 0; i < p.num_methods; ++i) {
-    if (p.methods[i] == BPV_FILTER_FIR && w.lane < 16)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(taps_ws + job * 256 + w.lane * 16));
-    if (p.methods[i] == BPV_FILTER_BUTTER && w.lane * 16 < p.butter_order * 6)
+    if ((FEAT & F_FIR) && p.methods[i] == BPV_FILTER_FIR && w.lane < 24)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(taps_ws + job * FIR_WS_STRIDE + w.lane * 16));
+    if ((FEAT & F_BUTTER) && p.methods[i] == BPV_FILTER_BUTTER && w.lane * 16 < p.butter_order * 6)
       asm volatile("prefetch.global.L1 [%0];" ::"l"(sos_ws + job * (p.butter_order * 6) + w.lane * 16));
   }
 
@@ -574,22 +670,24 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
     switch (p.methods[mi]) {
       case BPV_DIFF_1: diff1(w); break;
       case BPV_DIFF_2: diff2(w); break;
-      case BPV_INTERP_LINEAR: interp_linear(w); break;
-      case BPV_INTERP_CUBIC: if (!interp_cubic(w)) st = ST_CUBIC_X; break;
+      case BPV_INTERP_LINEAR: if (FEAT & F_INTERP) interp_linear(w); break;
+      case BPV_INTERP_CUBIC: if (FEAT & F_INTERP) { if (!interp_cubic(w)) st = ST_CUBIC_X; } break;
       case BPV_DETREND_CONST: detrend_const(w); break;
       case BPV_DETREND_LINEAR: detrend_linear(w); break;
-      case BPV_FILTER_BUTTER: {
-        const double* sg = sos_ws + (long long)jobi * p.butter_order * 6;
-        if (!isfinite(sg[0])) { st = ST_BAD_BANDS; break; }
-        sos_filtfilt(w, sg, p.butter_order);
+      case BPV_FILTER_BUTTER:
+        if (FEAT & F_BUTTER) {
+          const double* sg = sos_ws + (long long)jobi * p.butter_order * 6;
+          if (!isfinite(sg[0])) { st = ST_BAD_BANDS; break; }
+          sos_filtfilt(w, sg, p.butter_order);
+        }
         break;
-      }
-      case BPV_FILTER_FIR: {
-        const double* tg = taps_ws + (long long)jobi * 256;
-        if (!isfinite(tg[0])) { st = ST_BAD_BANDS; break; }
-        fir_filtfilt(w, tg, p.fir_taps);
+      case BPV_FILTER_FIR:
+        if (FEAT & F_FIR) {
+          const double* tg = taps_ws + (long long)jobi * FIR_WS_STRIDE;
+          if (!isfinite(tg[0])) { st = ST_BAD_BANDS; break; }
+          fir_apply(w, tg, p.fir_taps);
+        }
         break;
-      }
       default: break;
     }
   }
@@ -606,60 +704,106 @@ __global__ void __launch_bounds__(128) window_preprocess_kernel(const double* __
   if (w.lane == 0) status[sig] = st;
 }
 
+template <int FEAT, int MINB>
+static int launch_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params& p, const PreLayout& L,
+                             const double* sos_ws, const double* taps_ws, double* proc_x, double* proc_y, int32_t* status,
+                             cudaStream_t st) {
+  const int max_smem = 200 * 1024;
+  BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
+              p.window, L.total);
+  // warps (signals) per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
+  const int reg_warps = 4 * MINB;                                // what the register budget of this instantiation allows
+  int wpb = 1, best = 0;
+  for (int c = 1; c <= 4; ++c) {
+    const int per_block = c * L.total + 1024;                    // + per-CTA reservation
+    if (per_block > max_smem) break;
+    int blocks = (227 * 1024) / per_block;
+    if (blocks > 32) blocks = 32;
+    int warps = blocks * c;
+    if (warps > reg_warps) warps = reg_warps;
+    if (warps > best || (warps == best && c < wpb)) { best = warps; wpb = c; }
+  }
+  const size_t smem = (size_t)wpb * L.total;
+  auto kern = window_preprocess_kernel<FEAT, MINB>;
+  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+  const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
+  kern<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, p, L, sos_ws, taps_ws, proc_x, proc_y, status);
+  return check_launch("bpv_window_preprocess");
+}
+
+static int parse_methods(const bpv_window_params* p, const char* who, bool& butter, bool& fir, bool& interp) {
+  butter = fir = interp = false;
+  BPV_REQUIRE(p->num_methods >= 0 && p->num_methods <= BPV_MAX_METHODS, BPV_E_INVALID, "%s: bad sizes", who);
+  for (int i = 0; i < p->num_methods; ++i) {
+    const int m = p->methods[i];
+    BPV_REQUIRE(m >= BPV_DIFF_1 && m <= BPV_FILTER_FIR, BPV_E_UNSUPPORTED,
+                "%s: unknown processing method %d (NotImplementedError, signal_processor.py:238)", who, m);
+    butter |= m == BPV_FILTER_BUTTER;
+    fir |= m == BPV_FILTER_FIR;
+    interp |= m == BPV_INTERP_LINEAR || m == BPV_INTERP_CUBIC;
+  }
+  return 0;
+}
+
 }  // namespace bpv
 
 extern "C" int64_t bpv_window_workspace_bytes(const bpv_window_params* p) {
   if (!p) return -1;
   const int64_t J = (int64_t)p->S * p->jobs_per_stream;
-  return J * (int64_t)(bpv::MAX_SOS * 6 + 256) * 8;   // per job: sos[16][6] | taps[128] | zi[128]
+  return J * (int64_t)(bpv::MAX_SOS * 6 + bpv::FIR_WS_STRIDE) * 8;   // per job: sos[16][6] | taps[128] | zi[128] | autocorrelation[128]
+}
+
+extern "C" int bpv_window_design(const double* ring_t, const bpv_window_params* p, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  using namespace bpv;
+  if (int rc = check_filter_params(p, "bpv_window_design")) return rc;
+  BPV_REQUIRE(ring_t, BPV_E_INVALID, "bpv_window_design: NULL pointer");
+  BPV_REQUIRE(p->S > 0 && p->window > 0 && p->window <= p->cap && p->jobs_per_stream > 0, BPV_E_INVALID, "bpv_window_design: bad sizes");
+  bool butter, fir, interp;
+  if (int rc = parse_methods(p, "bpv_window_design", butter, fir, interp)) return rc;
+  if (!butter && !fir) return 0;
+  BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
+              "bpv_window_design: workspace too small (see bpv_window_workspace_bytes)");
+  const long long J = (long long)p->S * p->jobs_per_stream;
+  double* sos_ws = (double*)workspace;
+  double* taps_ws = sos_ws + J * MAX_SOS * 6;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (butter) if (int rc = launch_job_butter(ring_t, *p, sos_ws, st)) return rc;
+  if (fir) if (int rc = launch_job_firls(ring_t, *p, taps_ws, st)) return rc;
+  return 0;
+}
+
+extern "C" int bpv_window_filter(const double* ring_t, const double* ring_y, const bpv_window_params* p,
+                                 const void* workspace, int64_t workspace_bytes,
+                                 double* proc_x, double* proc_y, int32_t* status, void* stream) {
+  using namespace bpv;
+  if (int rc = check_filter_params(p, "bpv_window_preprocess")) return rc;
+  BPV_REQUIRE(ring_t && ring_y && proc_x && proc_y && status, BPV_E_INVALID, "bpv_window_preprocess: NULL pointer");
+  BPV_REQUIRE(p->S > 0 && p->R > 0 && p->window > 0 && p->window <= p->cap && p->jobs_per_stream > 0, BPV_E_INVALID,
+              "bpv_window_preprocess: bad sizes");
+  BPV_REQUIRE(p->window <= 65535, BPV_E_TOO_LARGE, "bpv_window_preprocess: window > 65535");
+  bool butter, fir, interp;
+  if (int rc = parse_methods(p, "bpv_window_preprocess", butter, fir, interp)) return rc;
+  const long long J = (long long)p->S * p->jobs_per_stream;
+  const double* sos_ws = (const double*)workspace;
+  const double* taps_ws = sos_ws ? sos_ws + J * MAX_SOS * 6 : nullptr;
+  if (butter || fir)
+    BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
+                "bpv_window_preprocess: workspace too small (see bpv_window_workspace_bytes)");
+  const PreLayout L = pre_layout(*p);
+  cudaStream_t st = (cudaStream_t)stream;
+#define BPV_PRE(feat, minb) return launch_preprocess<feat, minb>(ring_t, ring_y, *p, L, sos_ws, taps_ws, proc_x, proc_y, status, st)
+  if (!interp && !butter && !fir) BPV_PRE(0, 6);
+  if (!interp && !butter) BPV_PRE(F_FIR, 5);
+  if (!interp && !fir) BPV_PRE(F_BUTTER, 5);
+  if (!fir) BPV_PRE(F_INTERP | F_BUTTER, 4);
+  BPV_PRE(F_INTERP | F_BUTTER | F_FIR, 4);
+#undef BPV_PRE
 }
 
 extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
                                      void* workspace, int64_t workspace_bytes,
                                      double* proc_x, double* proc_y, int32_t* status, void* stream) {
-  using namespace bpv;
-  if (int rc = check_filter_params(p, "bpv_window_preprocess")) return rc;
-  BPV_REQUIRE(ring_t && ring_y && proc_x && proc_y && status, BPV_E_INVALID, "bpv_window_preprocess: NULL pointer");
-  BPV_REQUIRE(p->S > 0 && p->R > 0 && p->window > 0 && p->window <= p->cap && p->jobs_per_stream > 0 &&
-              p->num_methods >= 0 && p->num_methods <= BPV_MAX_METHODS, BPV_E_INVALID, "bpv_window_preprocess: bad sizes");
-  BPV_REQUIRE(p->window <= 65535, BPV_E_TOO_LARGE, "bpv_window_preprocess: window > 65535");
-  bool butter = false, fir = false;
-  for (int i = 0; i < p->num_methods; ++i) {
-    const int m = p->methods[i];
-    BPV_REQUIRE(m >= BPV_DIFF_1 && m <= BPV_FILTER_FIR, BPV_E_UNSUPPORTED,
-                "bpv_window_preprocess: unknown processing method %d (NotImplementedError, signal_processor.py:238)", m);
-    butter |= m == BPV_FILTER_BUTTER;
-    fir |= m == BPV_FILTER_FIR;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long J = (long long)p->S * p->jobs_per_stream;
-  double* sos_ws = (double*)workspace;
-  double* taps_ws = sos_ws ? sos_ws + J * MAX_SOS * 6 : nullptr;
-  if (butter || fir) {
-    BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
-                "bpv_window_preprocess: workspace too small (see bpv_window_workspace_bytes)");
-    if (butter) if (int rc = launch_job_butter(ring_t, *p, sos_ws, st)) return rc;
-    if (fir) if (int rc = launch_job_firls(ring_t, *p, taps_ws, st)) return rc;
-  }
-  const PreLayout L = pre_layout(*p);
-  const int max_smem = 200 * 1024;
-  BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
-              p->window, L.total);
-  // warps (signals) per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
-  int wpb = 1, best = 0;
-  for (int c = 1; c <= 4; ++c) {
-    const int per_block = c * L.total + 1024;                  // + per-CTA reservation
-    if (per_block > max_smem) break;
-    int blocks = (227 * 1024) / per_block;
-    if (blocks > 32) blocks = 32;
-    int warps = blocks * c;
-    if (warps > 16) warps = 16;                                // register file: ~126 regs/thread -> 16 warps
-    if (warps > best || (warps == best && c < wpb)) { best = warps; wpb = c; }
-  }
-  const size_t smem = (size_t)wpb * L.total;
-  if (int rc = ensure_dyn_smem((const void*)window_preprocess_kernel, smem)) return rc;
-  const long long nsig = J * p->R;
-  window_preprocess_kernel<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, *p, L, sos_ws, taps_ws,
-                                                                                     proc_x, proc_y, status);
-  return check_launch("bpv_window_preprocess");
+  if (int rc = bpv_window_design(ring_t, p, workspace, workspace_bytes, stream)) return rc;
+  return bpv_window_filter(ring_t, ring_y, p, workspace, workspace_bytes, proc_x, proc_y, status, stream);
 }

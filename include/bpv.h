@@ -105,6 +105,17 @@ int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_stride_bytes,
                               const int32_t* boxes, int32_t R, int32_t mode,
                               uint64_t* out_sums, double* out_value, void* stream);
 
+/* F1 through a segmentation mask.  masks uint8 [num_frames] of H x W per-pixel categories — the
+ * category_mask the reference's person segmenter returns for every frame (inference_runner.py:154-166; used there only for
+ * drawing, drawer.py:95-99).  A ROI is sampled only over the pixels whose category equals categories[r] (int32 [R], device
+ * memory; e.g. 3 = face skin, 2 = body skin): sums = (sumB, sumG, sumR, N) over those pixels, value = the float64
+ * np.mean(channel(frame[y0:y1, x0:x1])[mask[y0:y1, x0:x1] == category]) gives; no selected pixel -> NaN.  Other arguments
+ * as bpv_roi_sample_u8. */
+int bpv_roi_sample_masked_u8(const uint8_t* frames, int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                             const uint8_t* masks, int64_t mask_frame_stride_bytes, int64_t mask_row_stride_bytes,
+                             int32_t H, int32_t W, int64_t num_frames, const int32_t* boxes, int32_t R,
+                             const int32_t* categories, int32_t mode, uint64_t* out_sums, double* out_value, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ROI geometry for batched landmark tensors — replaces SignalProcessor.calc_rois and the ROI smoothing
  *     sg_roi.add_samples + get_means(as_int=True) (signal_processor.py:133-155, 304-305; signal_data.py:60-63).
@@ -137,7 +148,8 @@ int bpv_view_boxes(const int32_t* boxes, int64_t num_boxes, int32_t view_w, int3
  *
  * ring_t float64 [S, cap], ring_y float64 [S, R, cap]: sample with global index g (0-based count
  * since the stream started) lives at slot g % cap.  Pushes T samples per stream with global
- * indices g0 .. g0+T-1.  ts float64 [S, T]; values float64 [S, T, R] (F1's out_value).
+ * indices g0 .. g0+T-1.  ts float64 [S, T]; values float64 [S, T, R] (F1's out_value).  Either of ts / values may be
+ * NULL: the timestamps of a batch can be pushed ahead of its samples (they are all bpv_window_design needs).
  */
 int bpv_ring_push(double* ring_t, double* ring_y, int32_t S, int32_t R, int32_t cap,
                   int64_t g0, int32_t T, const double* ts, const double* values, void* stream);
@@ -186,6 +198,17 @@ int64_t bpv_window_workspace_bytes(const bpv_window_params* p);
 int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
                           void* workspace, int64_t workspace_bytes,
                           double* proc_x, double* proc_y, int32_t* status, void* stream);
+/* The two halves of bpv_window_preprocess, for callers that overlap them:
+ * bpv_window_design — make_filter for every window job (signal_processor.py:158-173, called per frame and signal at
+ *   :226, :232): needs only the timestamps (ring_t), so it can run on another stream as soon as they are pushed, beside
+ *   the ROI sampling of the same frames.  Fills `workspace` (per job: Butterworth sos | FIR taps | lfilter_zi | tap
+ *   autocorrelation).
+ * bpv_window_filter — process_signal given the designs in `workspace` (same stream, or after an event on the design). */
+int bpv_window_design(const double* ring_t, const bpv_window_params* p, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+int bpv_window_filter(const double* ring_t, const double* ring_y, const bpv_window_params* p,
+                      const void* workspace, int64_t workspace_bytes,
+                      double* proc_x, double* proc_y, int32_t* status, void* stream);
 
 /* F3 + F4(a) spectrum and HR peak — replaces transform_signal(s) + SignalGroup.get_peaks on
  *     sg_spec (signal_processor.py:248-277, 310; signal_data.py:65-70 with the range reset of
@@ -225,6 +248,10 @@ int bpv_firls_design(const double* fs, int32_t n, const bpv_window_params* p, do
  */
 int bpv_pack_records(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx, const int32_t* lag_idx,
                      int64_t J, int32_t R, int32_t P, double* out, void* stream);
+/* Compact record, SURVEY.md 8(e): out int32 [J, 2R + 2P] 4-byte words = (bpm f32 [R], ptt_ms f32 [P], peak_idx i32 [R],
+ * lag_idx i32 [P]) — 24 B per window job at R = 2; the payload of the per-step multi-GPU gather. */
+int bpv_pack_records32(const double* peak_freq, const double* lag_sec, const int32_t* peak_idx, const int32_t* lag_idx,
+                       int64_t J, int32_t R, int32_t P, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core building block of the spectra: 256-point DFT of `rows` real segments as one dense contraction on the
@@ -233,6 +260,13 @@ int bpv_pack_records(const double* peak_freq, const double* lag_sec, const int32
  * z float32 [rows, 256]; d float32 [rows, 256]: d[:, 0..128] = Re X[0..128], d[:, 129..255] = -Im X[1..127].
  */
 int bpv_dft256_tc(const float* z, int32_t rows, float* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement aid (bench.py roofline of the FP64 / FP32 bound families; not part of the reference path): a grid of
+ * `blocks` x 256 threads, each running `iters` rounds of 8 independent dependent-chain fused multiply-adds in
+ * float64 (dtype 1) or float32 (dtype 0).  Returns the number of FMAs enqueued (2 flop each) or a negative error;
+ * sink = >= 8 bytes of device memory (written only if a result is non-finite, so the loop is not optimised away). */
+int64_t bpv_probe_fma(int32_t dtype, int64_t iters, int32_t blocks, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -173,6 +173,31 @@ def roi_sample(frame, sroi, channel=GREEN):
             return np.mean(px)
 
 
+def roi_sample_masked(frame, mask, category, sroi, channel=GREEN):
+    """SURVEY.md 8(f) row 4 — ROI sampling through a segmentation mask.  The reference never samples through its
+    person-segmenter category mask (inference_runner.py:154-166 produces it, drawer.py:95-99 only draws with it), so this
+    function DEFINES the extension in the reference's own idiom: sample_signal (signal_processor.py:176-189) restricted
+    to the ROI pixels whose category equals `category`:  np.mean(channel(roi)[mask_roi == category]).
+    Returns (value, (sumB, sumG, sumR, N_selected))."""
+    if np.isnan(sroi).any():
+        return np.nan, (0, 0, 0, 0)
+    _, _, x0, y0, x1, y1 = sroi
+    roi_bgr = frame[y0:y1, x0:x1, :]
+    sel = mask[y0:y1, x0:x1] == category
+    if channel == GREEN:
+        px = roi_bgr[..., 1]
+    elif channel == CHROM_GREEN:
+        px = roi_bgr[..., 1] / 2 - roi_bgr[..., 0] / 4 - roi_bgr[..., 2] / 4 + 0.5
+    else:
+        raise NotImplementedError
+    picked = roi_bgr[sel].astype(np.uint64)                      # [N_selected, 3]
+    sums = (int(picked[:, 0].sum()), int(picked[:, 1].sum()), int(picked[:, 2].sum()), int(sel.sum()))
+    import warnings
+    with np.errstate(all='ignore'), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return np.mean(px[sel]), sums
+
+
 def value_from_sums(sB, sG, sR, n, channel):
     """the float64 the reference's np.mean produces, from exact integer sums."""
     if n == 0:
