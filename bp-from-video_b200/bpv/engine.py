@@ -78,7 +78,7 @@ class BatchedSignalProcessor:
                  fir_taps: int = 127, fir_df: float = 0.3, min_freq: float = 0.8, max_freq: float = 4.0,
                  ls_num_freqs: int | None = None, windows: str = EVERY_FRAME, store_arrays: bool = False,
                  device: str | torch.device = 'cuda', roi_pixels_hint: int = 0, peak_max_samples: int = 0,
-                 result_buffers: int = 2, overlap: int | None = None):
+                 result_buffers: int = 2, overlap: int | None = None, design_cache: bool | None = None):
         _cabi.lib()  # fail loudly if the CUDA library is missing: there is no CPU fallback
         if not torch.cuda.is_available():
             raise _cabi.BpvError('BatchedSignalProcessor needs a CUDA device (no CPU fallback)')
@@ -132,6 +132,12 @@ class BatchedSignalProcessor:
         self._ws_spec = torch.empty(need, dtype=torch.uint8, device=dev)
         self.launches_per_step = self._extra_launches = 0
         self._has_filter = any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
+        # design cache (include/bpv.h bpv_window_design): make_filter is a pure function of fs, so sampling rates that were
+        # designed before — constant-fps streams: every window of every stream on that clock — are looked up, not redesigned
+        if design_cache is None:
+            design_cache = os.environ.get('BPV_DESIGN_CACHE', '1') != '0'
+        self._dcache = ops.new_design_cache(dev) if design_cache else None
+        self._dcache_sig = None
         self._side = None
         self._ev = None
         # sg_bpm / sg_ptt histories and their running means on the device (0 = off)
@@ -200,7 +206,7 @@ class BatchedSignalProcessor:
             samples = self._samples[self._turn][:, :T]
             if T != self.Tmax:
                 samples = torch.empty((S, T, self.R), dtype=torch.float64, device=self.device)
-            design_ahead = bool(self.overlap & OVERLAP_DESIGN) and self._has_filter
+            design_ahead = bool(self.overlap & OVERLAP_DESIGN) and any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
             if design_ahead:
                 self._design_ahead(timestamps, T)
             ops.roi_sample(frames.view(S * T, *frames.shape[2:]), boxes.view(S * T, self.R, 4), self.color_channel,
@@ -219,8 +225,20 @@ class BatchedSignalProcessor:
         p = self._params(head0, 1, jobs)
         side.wait_event(ev['ts'])
         with torch.cuda.stream(side):
-            ops.window_design(self.ring_t, p, self._ws)
+            ops.window_design(self.ring_t, p, self._ws, self._cache())
             ev['design'].record(side)
+
+    def _cache(self):
+        """The design cache, emptied whenever the filter parameters it was filled under have changed (the drop-in
+        SignalProcessor lets callers edit them between frames)."""
+        if self._dcache is None:
+            return None
+        sig = tuple(sorted(self.kw.items()))
+        if sig != self._dcache_sig:
+            if self._dcache_sig is not None:
+                self._dcache.zero_()
+            self._dcache_sig = sig
+        return self._dcache
 
     # ------------------------------------------------------------------------------------------
     # SURVEY.md §8(f) row 1: calc_rois + ROI smoothing on the device for batched landmark tensors
@@ -282,11 +300,12 @@ class BatchedSignalProcessor:
         J = S * jobs
         pxb, pyb = self._proc[turn % len(self._proc)]
         px, py, st = pxb[:J], pyb[:J], self._status[turn][:J]
+        has_filter = any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
         if _designed:
             main.wait_event(self._ev['design'])
-            ops.window_filter(self.ring_t, self.ring_y, p, self._ws, px, py, st)
-        else:
-            ops.window_preprocess(self.ring_t, self.ring_y, p, px, py, st, workspace=self._ws)
+        elif has_filter:
+            ops.window_design(self.ring_t, p, self._ws, self._cache())
+        ops.window_filter(self.ring_t, self.ring_y, p, self._ws, px, py, st, cache=self._dcache if has_filter else None)
         spo, xco = self._spec[turn], self._xc[turn]
         spo = None if spo is None or spo['peak_idx'].shape[0] != J else spo
         xco = None if xco is None or xco['lag_idx'].shape[0] != J else xco
@@ -303,7 +322,8 @@ class BatchedSignalProcessor:
             sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
             xc = ops.window_xcorr(px, py, p, store=self.store_arrays, out=xco)
         self._spec[turn], self._xc[turn] = sp, xc
-        n_pre = 1 + sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
+        n_design = sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
+        n_pre = 1 + n_design + (1 if n_design and self._dcache is not None else 0)     # filter + designs (+ cache probe)
         n_spec = 2 if self.transform == _cabi.PGRAM_LS else 1
         if (self.transform == _cabi.PGRAM_WELCH and not self.store_arrays and 256 <= self.W <= 383
                 and os.environ.get('BPV_WELCH_TC', '') == '1'):

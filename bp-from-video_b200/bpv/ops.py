@@ -142,17 +142,25 @@ def window_preprocess(ring_t, ring_y, p: WindowParams, proc_x=None, proc_y=None,
     return proc_x, proc_y, status
 
 
-def window_design(ring_t, p: WindowParams, workspace):
+def new_design_cache(device) -> torch.Tensor:
+    """A zero-initialised design cache (include/bpv.h bpv_window_design): keep it across steps, zero it when the filter
+    parameters change."""
+    return torch.zeros(lib().bpv_design_cache_bytes(), dtype=torch.uint8, device=device)
+
+
+def window_design(ring_t, p: WindowParams, workspace, cache=None):
     """make_filter of every window job into `workspace` (signal_processor.py:158-173): needs only the timestamps, so
-    it can run on another stream beside the ROI sampling of the same frames."""
-    _run(ring_t.device, 'bpv_window_design', ptr(ring_t), C.byref(p), ptr(workspace), workspace.numel())
+    it can run on another stream beside the ROI sampling of the same frames.  cache = new_design_cache(...) tensor:
+    sampling rates that were designed before are looked up instead."""
+    _run(ring_t.device, 'bpv_window_design', ptr(ring_t), C.byref(p), ptr(workspace), workspace.numel(),
+         ptr(cache), 0 if cache is None else cache.numel())
 
 
-def window_filter(ring_t, ring_y, p: WindowParams, workspace, proc_x=None, proc_y=None, status=None):
-    """F2 given the designs `window_design` left in `workspace`."""
+def window_filter(ring_t, ring_y, p: WindowParams, workspace, proc_x=None, proc_y=None, status=None, cache=None):
+    """F2 given the designs `window_design` left in `workspace` (and `cache`, when one was used)."""
     proc_x, proc_y, status, workspace = _pre_buffers(ring_y, p, proc_x, proc_y, status, workspace)
     _run(ring_y.device, 'bpv_window_filter', ptr(ring_t), ptr(ring_y), C.byref(p), ptr(workspace), workspace.numel(),
-                                  ptr(proc_x), ptr(proc_y), ptr(status))
+         ptr(cache), 0 if cache is None else cache.numel(), ptr(proc_x), ptr(proc_y), ptr(status))
     return proc_x, proc_y, status
 
 
@@ -182,9 +190,9 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
     o = out or {}
     if store:
         if 'freqs' not in o:
-            o['freqs'] = torch.empty((J, p.R, mb), dtype=torch.float32, device=dev)
+            o['freqs'] = torch.full((J, p.R, mb), float('nan'), dtype=torch.float32, device=dev)
         if 'mags' not in o:
-            o['mags'] = torch.empty((J, p.R, mb), dtype=torch.float32, device=dev)
+            o['mags'] = torch.full((J, p.R, mb), float('nan'), dtype=torch.float32, device=dev)
     else:
         o['freqs'] = o['mags'] = None
     if 'num_bins' not in o:
@@ -213,9 +221,9 @@ def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
     o = out or {}
     if store:
         if 'lags' not in o:
-            o['lags'] = torch.empty((J, P, L), dtype=torch.float32, device=dev)
+            o['lags'] = torch.full((J, P, L), float('nan'), dtype=torch.float32, device=dev)
         if 'corr' not in o:
-            o['corr'] = torch.empty((J, P, L), dtype=torch.float32, device=dev)
+            o['corr'] = torch.full((J, P, L), float('nan'), dtype=torch.float32, device=dev)
     else:
         o['lags'] = o['corr'] = None
     if 'num_lags' not in o:

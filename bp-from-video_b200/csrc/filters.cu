@@ -274,7 +274,39 @@ __global__ void job_butter_kernel(const double* __restrict__ ring_t, bpv_window_
   double sos[MAX_SOS * 6];
   if (isfinite(fs)) butter_bandpass_sos(fs, p.butter_order, p.min_freq, p.max_freq, p.butter_min_bw, sos);
   else for (int k = 0; k < p.butter_order * 6; ++k) sos[k] = nan_f64();
-  for (int k = 0; k < p.butter_order * 6; ++k) sos_out[(long long)job * p.butter_order * 6 + k] = sos[k];
+  for (int k = 0; k < p.butter_order * 6; ++k) sos_out[(long long)job * (MAX_SOS * 6) + k] = sos[k];   // slot stride 16 x 6 whatever the order
+}
+
+// fs of a job's window, cooperative over a group of FIRLS_LPD lanes (first / last finite timestamp and their count); every
+// lane of the group returns the same value.  Same arithmetic as job_fs.
+__device__ __forceinline__ double group_job_fs(const double* __restrict__ ring_t, const bpv_window_params& p, int job, int sub) {
+  const int s = job / p.jobs_per_stream, j = job % p.jobs_per_stream;
+  const double* rt = ring_t + (long long)s * p.cap;
+  const long long g0 = p.head0 + (long long)j * p.head_step - p.window + 1;
+  int lo = 0x7fffffff, hi = -1, cnt = 0;
+  const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
+  const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
+  for (int k0 = sub; k0 < p.window; k0 += FIRLS_LPD * 8) {     // 8 independent loads in flight per lane
+    double tv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * FIRLS_LPD;
+      int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
+      tv[u] = (k < p.window && k >= kmin) ? rt[slot] : nan_f64();
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * FIRLS_LPD;
+      if (isfinite(tv[u])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
+    }
+  }
+  for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) {
+    const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = lo < l2 ? lo : l2; hi = hi > h2 ? hi : h2; cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  double fs = nan_f64();
+  if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
+  return fs;
 }
 
 __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* __restrict__ ring_t, bpv_window_params p,
@@ -283,39 +315,114 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
   const int d = threadIdx.x / FIRLS_LPD, sub = threadIdx.x & (FIRLS_LPD - 1);
   const int job = blockIdx.x * FIRLS_DPB + d;
   const bool live = job < p.S * p.jobs_per_stream;
-  double fs;
-  {
-    const int jc = live ? job : 0;                   // padding groups shadow job 0 (warp-uniform control flow), write nothing
-    const int s = jc / p.jobs_per_stream, j = jc % p.jobs_per_stream;
-    // fs of the job's window, group cooperative (first / last finite timestamp and their count)
-    const double* rt = ring_t + (long long)s * p.cap;
-    const long long g0 = p.head0 + (long long)j * p.head_step - p.window + 1;
-    int lo = 0x7fffffff, hi = -1, cnt = 0;
-    const int kmin = g0 < 0 ? (int)(-g0 < p.window ? -g0 : p.window) : 0;
-    const int slot0 = (int)(((g0 % p.cap) + p.cap) % p.cap);
-    for (int k0 = sub; k0 < p.window; k0 += FIRLS_LPD * 8) {     // 8 independent loads in flight per lane
-      double tv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + u * FIRLS_LPD;
-        int slot = slot0 + k; if (slot >= p.cap) slot -= p.cap;
-        tv[u] = (k < p.window && k >= kmin) ? rt[slot] : nan_f64();
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + u * FIRLS_LPD;
-        if (isfinite(tv[u])) { lo = lo < k ? lo : k; hi = k; ++cnt; }
-      }
-    }
-    for (int o = FIRLS_LPD / 2; o > 0; o >>= 1) {
-      const int l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-      lo = lo < l2 ? lo : l2; hi = hi > h2 ? hi : h2; cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    fs = nan_f64();
-    if (cnt >= 2) fs = 1.0 / ((rt[(slot0 + hi) % p.cap] - rt[(slot0 + lo) % p.cap]) / (double)(cnt - 1));
-  }
+  // padding groups shadow job 0 (warp-uniform control flow), write nothing
+  const double fs = group_job_fs(ring_t, p, live ? job : 0, sub);
   double* o = out + (long long)(live ? job : 0) * FIR_WS_STRIDE;      // taps [128] | lfilter_zi [128] | autocorrelation [128]
   firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, o + 256, smem + firls_smem_offset(d));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Design cache.  make_filter is a pure function of the window's sampling rate (the band edges, order and tap count are
+// fixed per processor), yet the reference calls it for every signal of every frame (signal_processor.py:226, 232).  A
+// stream with a constant frame period — every video file, and the synthetic c2 workload — yields the same fs, bit for
+// bit, window after window, and streams that share a clock share it too.  The cache is an open-addressing table in
+// device memory keyed by the 64 bits of fs, persistent across launches:
+//   probe   (one 8-lane group per window job) computes fs, looks it up and, on a miss, claims a slot with one
+//           atomicCAS and appends (destination, fs) to the launch's miss list; a full neighbourhood (DC_PROBES slots)
+//           or a non-finite fs falls back to the job's own workspace slot;
+//   design  kernels run the Levinson / Butterworth design for the entries of the miss list only (CTAs beyond it exit);
+//   filter  (window_pre.cu) reads each job's coefficients through ref[job]: a cache slot, or its own workspace slot.
+// Hits return the very bits a fresh design would produce (the design kernels are deterministic in fs), so cached and
+// uncached runs are identical.  Jittered timestamps give all-distinct fs: the table fills, later jobs use their own
+// slots, and a launch that missed more than half the table clears the keys so stale rates do not squat in it.
+// The table is only valid for one set of filter parameters: the owner zeroes it when they change.
+// Layout of the cache buffer: hdr [16 B: miss counter] | keys u64 [DC_SLOTS] | vals double [DC_SLOTS][DC_STRIDE].
+// ---------------------------------------------------------------------------------------------
+struct DesignMiss { int32_t target; int32_t pad; double fs; };     // target >= 0: cache slot; < 0: own slot of job -(target + 1)
+
+__device__ __forceinline__ unsigned dc_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33;
+  return (unsigned)k & (DC_SLOTS - 1);
+}
+
+__global__ void __launch_bounds__(256) design_probe_kernel(const double* __restrict__ ring_t, const bpv_window_params p,
+                                                           unsigned char* __restrict__ cache, int32_t* __restrict__ ref,
+                                                           DesignMiss* __restrict__ miss) {
+  const int J = p.S * p.jobs_per_stream;
+  const int job = (blockIdx.x * blockDim.x + threadIdx.x) / FIRLS_LPD, sub = threadIdx.x & (FIRLS_LPD - 1);
+  const bool live = job < J;
+  const double fs = group_job_fs(ring_t, p, live ? job : 0, sub);
+  if (!live || sub != 0) return;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(cache);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(cache + DC_HDR_BYTES);
+  int slot = -1;
+  bool fresh = false;
+  if (isfinite(fs) && fs > 0.0) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(fs);
+    unsigned h = dc_hash(key);
+    for (int probe = 0; probe < DC_PROBES; ++probe) {
+      unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(keys + h);
+      if (k == 0ULL) {
+        k = atomicCAS(keys + h, 0ULL, key);
+        if (k == 0ULL) { slot = (int)h; fresh = true; break; }
+      }
+      if (k == key) { slot = (int)h; break; }
+      h = (h + 1) & (DC_SLOTS - 1);
+    }
+  }
+  ref[job] = slot;
+  if (slot < 0 || fresh) {
+    const unsigned e = atomicAdd(counter, 1u);
+    miss[e].target = slot >= 0 ? slot : -(job + 1);
+    miss[e].fs = fs;
+  }
+}
+
+__device__ __forceinline__ double* dc_dest(int target, unsigned char* cache, double* ws_sos, double* ws_fir, bool fir) {
+  if (target >= 0) {
+    double* v = reinterpret_cast<double*>(cache + DC_HDR_BYTES + DC_SLOTS * 8) + (long long)target * DC_STRIDE;
+    return fir ? v + MAX_SOS * 6 : v;
+  }
+  const long long job = -(long long)target - 1;
+  return fir ? ws_fir + job * FIR_WS_STRIDE : ws_sos + job * (MAX_SOS * 6);
+}
+
+__device__ __forceinline__ void dc_maybe_clear(unsigned char* cache, unsigned nmiss) {
+  // a launch that missed more than half the table: its rates do not repeat — empty the table for whatever comes next.
+  // Nothing reads the keys between this launch's probe and the next one's; the values designed now stay where ref[] says.
+  if (blockIdx.x == 0 && nmiss > DC_SLOTS / 2) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(cache + DC_HDR_BYTES);
+    for (int i = threadIdx.x; i < DC_SLOTS; i += blockDim.x) keys[i] = 0ULL;
+  }
+}
+
+__global__ void __launch_bounds__(FIRLS_THREADS) miss_firls_kernel(const bpv_window_params p, unsigned char* __restrict__ cache,
+                                                                   const DesignMiss* __restrict__ miss, double* __restrict__ ws_sos,
+                                                                   double* __restrict__ ws_fir) {
+  extern __shared__ double smem[];
+  const unsigned nmiss = *reinterpret_cast<const unsigned int*>(cache);
+  dc_maybe_clear(cache, nmiss);
+  if (blockIdx.x * FIRLS_DPB >= nmiss) return;
+  const int d = threadIdx.x / FIRLS_LPD;
+  const unsigned e = blockIdx.x * FIRLS_DPB + d;
+  const bool live = e < nmiss;
+  const DesignMiss m = miss[live ? e : 0];
+  double* o = dc_dest(m.target, cache, ws_sos, ws_fir, true);
+  firls_design_group(m.fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, o + 256, smem + firls_smem_offset(d));
+}
+
+__global__ void miss_butter_kernel(const bpv_window_params p, unsigned char* __restrict__ cache, const DesignMiss* __restrict__ miss,
+                                   double* __restrict__ ws_sos, double* __restrict__ ws_fir) {
+  const unsigned nmiss = *reinterpret_cast<const unsigned int*>(cache);
+  dc_maybe_clear(cache, nmiss);
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nmiss) return;
+  const DesignMiss m = miss[e];
+  double sos[MAX_SOS * 6];
+  if (isfinite(m.fs)) butter_bandpass_sos(m.fs, p.butter_order, p.min_freq, p.max_freq, p.butter_min_bw, sos);
+  else for (int k = 0; k < p.butter_order * 6; ++k) sos[k] = nan_f64();
+  double* o = dc_dest(m.target, cache, ws_sos, ws_fir, false);
+  for (int k = 0; k < p.butter_order * 6; ++k) o[k] = sos[k];
 }
 
 constexpr size_t FIRLS_SMEM = (size_t)(firls_smem_offset(FIRLS_DPB - 1) + FIRLS_WS) * sizeof(double);
@@ -330,6 +437,27 @@ int launch_job_firls(const double* ring_t, const bpv_window_params& p, double* t
   const int J = p.S * p.jobs_per_stream;
   job_firls_kernel<<<(J + FIRLS_DPB - 1) / FIRLS_DPB, FIRLS_THREADS, FIRLS_SMEM, st>>>(ring_t, p, taps_out);
   return check_launch("job_firls_kernel");
+}
+
+// Cached design of every window job: probe + design of the misses.  ref int32 [J] and the miss list live in the caller's
+// workspace (window_pre.cu lays it out); `cache` is the persistent table (zero-initialised by its owner).
+int launch_design_cached(const double* ring_t, const bpv_window_params& p, bool butter, bool fir, unsigned char* cache,
+                         int32_t* ref, void* miss, double* ws_sos, double* ws_fir, cudaStream_t st) {
+  const int J = p.S * p.jobs_per_stream;
+  cudaError_t e = cudaMemsetAsync(cache, 0, 4, st);                       // the launch's miss counter
+  if (e != cudaSuccess) { set_error("bpv_window_design: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  const long long threads = (long long)J * FIRLS_LPD;
+  design_probe_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ring_t, p, cache, ref, (DesignMiss*)miss);
+  if (int rc = check_launch("design_probe_kernel")) return rc;
+  if (butter) {
+    miss_butter_kernel<<<(J + 63) / 64, 64, 0, st>>>(p, cache, (const DesignMiss*)miss, ws_sos, ws_fir);
+    if (int rc = check_launch("miss_butter_kernel")) return rc;
+  }
+  if (fir) {
+    miss_firls_kernel<<<(J + FIRLS_DPB - 1) / FIRLS_DPB, FIRLS_THREADS, FIRLS_SMEM, st>>>(p, cache, (const DesignMiss*)miss, ws_sos, ws_fir);
+    if (int rc = check_launch("miss_firls_kernel")) return rc;
+  }
+  return 0;
 }
 
 int check_filter_params(const bpv_window_params* p, const char* who) {

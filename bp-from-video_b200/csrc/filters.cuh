@@ -7,6 +7,10 @@ namespace bpv {
 
 constexpr int MAX_SOS = 16;     // butter_order <= 16 -> <= 16 second-order sections
 constexpr int MAX_TAPS = 127;   // fir_taps <= 127 (odd)
+// design cache (filters.cu): DC_SLOTS entries of [sos 16x6 | taps | zi | autocorrelation], keyed by the bits of fs
+constexpr int DC_SLOTS = 256, DC_PROBES = 8, DC_HDR_BYTES = 16;
+constexpr int DC_STRIDE = MAX_SOS * 6 + 384;
+constexpr long long DC_BYTES = DC_HDR_BYTES + (long long)DC_SLOTS * 8 + (long long)DC_SLOTS * DC_STRIDE * 8;
 constexpr int FIR_WS_STRIDE = 384;   // doubles of filter workspace per window job: taps [128] | lfilter_zi [128] | tap autocorrelation [128]
 
 // status codes written to the per-signal status array

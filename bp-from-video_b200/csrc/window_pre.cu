@@ -12,6 +12,7 @@
 //               lane to lane by __shfl_up (one sample enters per step), forward then backward
 //   FIR filtfilt register-tiled sliding dot product (corr_tile.cuh), 8 consecutive outputs per lane; only
 //               the part of the padded signal that reaches the cropped output is staged and computed
+#include <stdlib.h>
 #include "filters.cuh"
 #include "corr_tile.cuh"
 
@@ -20,6 +21,28 @@ namespace bpv {
 int launch_job_butter(const double* ring_t, const bpv_window_params& p, double* sos_out, cudaStream_t st);
 int launch_job_firls(const double* ring_t, const bpv_window_params& p, double* taps_out, cudaStream_t st);
 int check_filter_params(const bpv_window_params* p, const char* who);
+int launch_design_cached(const double* ring_t, const bpv_window_params& p, bool butter, bool fir, unsigned char* cache,
+                         int32_t* ref, void* miss, double* ws_sos, double* ws_fir, cudaStream_t st);
+
+// Where a window job's filter coefficients live: in the design cache (ref[job] = slot) or in the job's own workspace slot.
+struct DesignRef {
+  const double* sos_ws;            // [J][16*6]
+  const double* taps_ws;           // [J][FIR_WS_STRIDE]
+  const int32_t* ref;              // [J] cache slot or -1; NULL = no cache in use
+  const unsigned char* cache;
+  __device__ __forceinline__ const double* slot(long long job) const {
+    const int sl = ref ? ref[job] : -1;
+    return sl >= 0 ? reinterpret_cast<const double*>(cache + DC_HDR_BYTES + DC_SLOTS * 8) + (long long)sl * DC_STRIDE : nullptr;
+  }
+  __device__ __forceinline__ const double* sos(long long job) const {
+    const double* v = slot(job);
+    return v ? v : sos_ws + job * (MAX_SOS * 6);
+  }
+  __device__ __forceinline__ const double* fir(long long job) const {
+    const double* v = slot(job);
+    return v ? v + MAX_SOS * 6 : taps_ws + job * FIR_WS_STRIDE;
+  }
+};
 
 struct PreLayout {        // per-warp shared-memory plan, in bytes
   int yv, xv, posv, posb, buf0, buf1, coef, total;
@@ -408,6 +431,121 @@ __device__ void sos_filtfilt(Warp& w, const double* __restrict__ sos_g, int N) {
   __syncwarp();
 }
 
+// sosfiltfilt for TWO signals per warp: the cascade has at most 16 sections, so the single-signal version above leaves
+// half of every warp idle for its 2 x (L + N - 1) serial steps — the longest phase of every Butterworth configuration.
+// Here lanes 0-15 run the cascade of signal A and lanes 16-31 that of signal B (their own coefficients: the two signals
+// need not belong to the same window job), shuffles are 16 wide, and the arithmetic per lane is exactly that of
+// sos_filtfilt, so the results are bit-identical.  The halves may differ in length; the loop without liveness tests runs
+// while both are in steady state, the predicated loop finishes the longer one.  la / lb = false parks a half.
+__device__ void sos_filtfilt_dual(Warp& wa, Warp& wb, bool la, bool lb, const double* __restrict__ ga,
+                                  const double* __restrict__ gb, int N) {
+  const int lane = wa.lane, hf = lane >> 4, s = lane & 15;
+  const bool live = hf ? lb : la;
+  double* yv = hf ? wb.yv : wa.yv;
+  double* ext = hf ? wb.buf0 : wa.buf0;
+  double* sos = hf ? wb.coef : wa.coef;      // [N*6]
+  double* zi = sos + 6 * MAX_SOS;            // [N*2]
+  const double* sg = hf ? gb : ga;
+  const int n = live ? (hf ? wb.n : wa.n) : 0;
+  if (live) for (int i = s; i < N * 6; i += 16) sos[i] = sg[i];
+  __syncwarp();
+  int nb0 = 0, na0 = 0;
+  if (live) {
+    if (s == 0) {
+      // sosfilt_zi: zi[s] = scale * lfilter_zi(b, a); scale *= sum(b)/sum(a)   (:4520-4541)
+      double scale = 1.0;
+      for (int k = 0; k < N; ++k) {
+        const double* c = sos + 6 * k;
+        const double B0 = c[1] - c[4] * c[0], B1 = c[2] - c[5] * c[0];
+        const double z0 = (B0 + B1) / (1.0 + c[4] + c[5]);
+        zi[2 * k] = scale * z0;
+        zi[2 * k + 1] = scale * (B1 - c[5] * z0);
+        scale *= (c[0] + c[1] + c[2]) / (1.0 + c[4] + c[5]);
+      }
+    }
+    for (int k = 0; k < N; ++k) { nb0 += sos[6 * k + 2] == 0.0; na0 += sos[6 * k + 5] == 0.0; }
+  }
+  __syncwarp();
+  const int dpl = 3 * (2 * N + 1 - (nb0 < na0 ? nb0 : na0));      // padlen as signal_processor.py:227-228
+  const int p = n <= dpl ? n - 1 : dpl;
+  const int L = live ? n + 2 * p : 0;
+  if (live) {
+    const double y0 = yv[0], yl = yv[n - 1];
+    for (int i = s; i < L; i += 16) {                             // odd extension
+      double v;
+      if (i < p) v = 2.0 * y0 - yv[p - i];
+      else if (i < p + n) v = yv[i - p];
+      else v = 2.0 * yl - yv[n - 2 - (i - p - n)];
+      ext[i] = v;
+    }
+  }
+  __syncwarp();
+  const int La = __shfl_sync(0xffffffffu, L, 0), Lb = __shfl_sync(0xffffffffu, L, 16);
+  const int Lmax = La > Lb ? La : Lb;
+  const int Lfast = (La > 0 && Lb > 0) ? (La < Lb ? La : Lb) : Lmax;
+  const bool sec = live && s < N;
+  const double b0 = sec ? sos[6 * s] : 0, b1 = sec ? sos[6 * s + 1] : 0, b2 = sec ? sos[6 * s + 2] : 0;
+  const double a1 = sec ? sos[6 * s + 4] : 0, a2 = sec ? sos[6 * s + 5] : 0;
+  const double zi0 = sec ? zi[2 * s] : 0, zi1 = sec ? zi[2 * s + 1] : 0;
+  const double na1 = -a1, na2 = -a2;
+  const bool first = live && s == 0, last = live && s == N - 1;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double x0 = L > 0 ? (pass == 0 ? ext[0] : ext[L - 1]) : 0.0;
+    double z0 = zi0 * x0, z1 = zi1 * x0;
+    double prev_out = 0.0;
+    const int dir = pass == 0 ? 1 : -1, base = pass == 0 ? 0 : L - 1;   // position of sample i of this half: base + dir*i
+    double nxt = L > 0 ? ext[base] : 0.0;
+    __syncwarp();
+    const int t_fill = N - 1 < Lmax ? N - 1 : Lmax;
+    int t = 0;
+    for (; t < t_fill; ++t) {                                     // fill: lanes s <= t are live
+      const double from_prev = __shfl_up_sync(0xffffffffu, prev_out, 1, 16);
+      const double xc = s == 0 ? nxt : from_prev;
+      if (first && t + 1 < L) nxt = ext[base + dir * (t + 1)];
+      if (sec && t >= s && t - s < L) {
+        const double xn = fma(b0, xc, z0);
+        z0 = fma(b1, xc, fma(na1, xn, z1));
+        z1 = fma(b2, xc, na2 * xn);
+        prev_out = xn;
+        if (s == N - 1) ext[base + dir * (t - s)] = xn;           // only when N == 1
+      }
+    }
+    if (Lfast > 0) {
+      // steady state of BOTH halves: every section is live, lane N-1 of a half emits its sample t - (N-1)
+      const double* in = ext + (L > 0 ? base + dir * (t + 1) : 0);
+      double* out = ext + (L > 0 ? base + dir * (t - (N - 1)) : 0);
+      for (; t < Lfast - 1; ++t) {
+        const double from_prev = __shfl_up_sync(0xffffffffu, prev_out, 1, 16);
+        const double xc = s == 0 ? nxt : from_prev;
+        if (first) nxt = *in;
+        in += dir;
+        const double xn = fma(b0, xc, z0);
+        z0 = fma(b1, xc, fma(na1, xn, z1));
+        z1 = fma(b2, xc, na2 * xn);
+        prev_out = xn;
+        if (last) *out = xn;
+        out += dir;
+      }
+    }
+    for (; t < Lmax + N - 1; ++t) {                               // the longer half, and the drain of both
+      const double from_prev = __shfl_up_sync(0xffffffffu, prev_out, 1, 16);
+      const double xc = s == 0 ? nxt : from_prev;
+      if (first && t + 1 < L) nxt = ext[base + dir * (t + 1)];
+      const int i = t - s;
+      if (sec && i >= 0 && i < L) {
+        const double xn = fma(b0, xc, z0);
+        z0 = fma(b1, xc, fma(na1, xn, z1));
+        z1 = fma(b2, xc, na2 * xn);
+        prev_out = xn;
+        if (s == N - 1) ext[base + dir * i] = xn;
+      }
+    }
+    __syncwarp();
+  }
+  if (live) for (int i = s; i < n; i += 16) yv[i] = ext[p + i];
+  __syncwarp();
+}
+
 // scipy.signal.filtfilt(b, 1.0, y, padlen) for an FIR b (scipy/signal/_signaltools.py:4893-4924):
 // odd extension, zi = lfilter_zi(b, [1]) (suffix sums of b[1:]), forward, backward, crop.
 //   F[i] = sum_k b[k] ext[i-k] + (i < T-1 ? zi[i]*ext[0] : 0)          forward over the padded signal
@@ -568,22 +706,18 @@ __device__ __forceinline__ void fir_apply(Warp& w, const double* __restrict__ tg
 // bit 0 INTERP_*, bit 1 FILTER_BUTTER, bit 2 FILTER_FIR.  diff / detrend are always present.
 constexpr int F_INTERP = 1, F_BUTTER = 2, F_FIR = 4;
 
-template <int FEAT, int MINB>
-__global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const double* __restrict__ ring_t,
-                                                                      const double* __restrict__ ring_y,
-                                                                      const bpv_window_params p, const PreLayout L,
-                                                                      const double* __restrict__ sos_ws,
-                                                                      const double* __restrict__ taps_ws,
-                                                                      double* __restrict__ proc_x, double* __restrict__ proc_y,
-                                                                      int32_t* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const long long sig = (long long)blockIdx.x * wpb + wib;       // job * R + r
-  const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
-  if (sig >= nsig) return;
-  unsigned char* sm = smem_raw + (size_t)wib * L.total;
-  Warp w;
-  w.lane = threadIdx.x & 31;
+// Stage one signal's window: ring -> shared memory with ballot / popc compaction of the valid samples (Signal.reset_mask:
+// v = isfinite(x), w = isfinite(y); signal_data.py:43-45), writing the position-preserving pass-through copy on the way.
+// Returns ST_OK, or ST_GUARD when the reference's guard (signal_processor.py:200) leaves the window unprocessed.
+template <int FEAT>
+__device__ int gather_window(Warp& w, unsigned char* sm, const PreLayout& L, const bpv_window_params& p,
+                             const double* __restrict__ ring_t, const double* __restrict__ ring_y, long long sig,
+                             double* __restrict__ ox, double* __restrict__ oy) {
+  // xv / posb exist in the shared-memory plan only when the method list resamples (an instantiation may serve a subset
+  // of its stages)
+  bool has_interp = false;
+  if (FEAT & F_INTERP)
+    for (int i = 0; i < p.num_methods; ++i) has_interp |= (p.methods[i] == BPV_INTERP_LINEAR || p.methods[i] == BPV_INTERP_CUBIC);
   w.yv = reinterpret_cast<double*>(sm + L.yv);
   w.xv = reinterpret_cast<double*>(sm + L.xv);
   w.buf0 = reinterpret_cast<double*>(sm + L.buf0);
@@ -593,37 +727,21 @@ __global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const doub
   w.posb = reinterpret_cast<unsigned short*>(sm + L.posb);
   w.grid = false;
   w.fir_c = L.fir_c; w.fir_gt = L.fir_gt; w.fir_b = L.fir_b;
-
   const long long job = sig / p.R;
   const int r = (int)(sig % p.R);
   const int s = (int)(job / p.jobs_per_stream), j = (int)(job % p.jobs_per_stream);
   const long long head = p.head0 + (long long)j * p.head_step;
   const double* rt = ring_t + (long long)s * p.cap;
   const double* ry = ring_y + ((long long)s * p.R + r) * p.cap;
-  double* ox = proc_x + sig * p.window;
-  double* oy = proc_y + sig * p.window;
   const int W = p.window;
-  constexpr bool has_interp = (FEAT & F_INTERP) != 0;
-
-  // the job's filter coefficients are first needed after the gather and the detrend: start pulling them (taps | zi |
-  // autocorrelation: 24 lines, resp. 768 B of sos) towards the SM now, so that the filter stage does not open with a
-  // DRAM round trip
-  for (int i = 0; i < p.num_methods; ++i) {
-    if ((FEAT & F_FIR) && p.methods[i] == BPV_FILTER_FIR && w.lane < 24)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(taps_ws + job * FIR_WS_STRIDE + w.lane * 16));
-    if ((FEAT & F_BUTTER) && p.methods[i] == BPV_FILTER_BUTTER && w.lane * 16 < p.butter_order * 6)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(sos_ws + job * (p.butter_order * 6) + w.lane * 16));
-  }
-
-  // ---- gather + compaction (Signal.reset_mask: v = isfinite(x), w = isfinite(y); signal_data.py:43-45)
   int n = 0, m = 0;
   double xfirst = 0.0, xlast = 0.0;
   const unsigned lt = (1u << w.lane) - 1u;
   const long long gfirst = head - W + 1;                      // global index of window position 0
   const int kmin = gfirst < 0 ? (int)(-gfirst < W ? -gfirst : W) : 0;   // positions before the stream started: NaN
   const int slot0 = (int)(((gfirst % p.cap) + p.cap) % p.cap);       // ring slot of position 0 (one 64-bit modulo)
-  // stage the window (independent, coalesced loads: no ballot in this loop, so they all overlap), writing the
-  // position-preserving pass-through copy on the way; y is staged in yv[] and compacted in place below
+  // stage the window (independent, coalesced loads: no ballot in this loop, so they all overlap); y is staged in yv[]
+  // and compacted in place below
   double* xstage = L.buf_len >= W ? w.buf0 : nullptr;
   for (int k = w.lane; k < W; k += 32) {
     double x = nan_f64(), y = nan_f64();
@@ -660,62 +778,139 @@ __global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const doub
   __syncwarp();
   w.n = n; w.m = m; w.xfirst = xfirst; w.xlast = xlast;
   const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
-  int st = ST_OK;
-  if (!(n >= 2 && isfinite(fs))) {            // guard, signal_processor.py:200
-    if (w.lane == 0) status[sig] = ST_GUARD;
-    return;
+  return (n >= 2 && isfinite(fs)) ? ST_OK : ST_GUARD;
+}
+
+// One processing method that works on a single signal (everything but the two-signal Butterworth cascade).
+template <int FEAT>
+__device__ int apply_method(Warp& w, int method, const bpv_window_params& p, const DesignRef& dr, long long job) {
+  switch (method) {
+    case BPV_DIFF_1: diff1(w); break;
+    case BPV_DIFF_2: diff2(w); break;
+    case BPV_INTERP_LINEAR: if (FEAT & F_INTERP) interp_linear(w); break;
+    case BPV_INTERP_CUBIC: if (FEAT & F_INTERP) { if (!interp_cubic(w)) return ST_CUBIC_X; } break;
+    case BPV_DETREND_CONST: detrend_const(w); break;
+    case BPV_DETREND_LINEAR: detrend_linear(w); break;
+    case BPV_FILTER_BUTTER:
+      if (FEAT & F_BUTTER) {
+        const double* sg = dr.sos(job);
+        if (!isfinite(sg[0])) return ST_BAD_BANDS;
+        sos_filtfilt(w, sg, p.butter_order);
+      }
+      break;
+    case BPV_FILTER_FIR:
+      if (FEAT & F_FIR) {
+        const double* tg = dr.fir(job);
+        if (!isfinite(tg[0])) return ST_BAD_BANDS;
+        fir_apply(w, tg, p.fir_taps);
+      }
+      break;
+    default: break;
   }
-  const int jobi = (int)job;
-  for (int mi = 0; mi < p.num_methods && st == ST_OK; ++mi) {
-    switch (p.methods[mi]) {
-      case BPV_DIFF_1: diff1(w); break;
-      case BPV_DIFF_2: diff2(w); break;
-      case BPV_INTERP_LINEAR: if (FEAT & F_INTERP) interp_linear(w); break;
-      case BPV_INTERP_CUBIC: if (FEAT & F_INTERP) { if (!interp_cubic(w)) st = ST_CUBIC_X; } break;
-      case BPV_DETREND_CONST: detrend_const(w); break;
-      case BPV_DETREND_LINEAR: detrend_linear(w); break;
-      case BPV_FILTER_BUTTER:
-        if (FEAT & F_BUTTER) {
-          const double* sg = sos_ws + (long long)jobi * p.butter_order * 6;
-          if (!isfinite(sg[0])) { st = ST_BAD_BANDS; break; }
-          sos_filtfilt(w, sg, p.butter_order);
-        }
-        break;
-      case BPV_FILTER_FIR:
-        if (FEAT & F_FIR) {
-          const double* tg = taps_ws + (long long)jobi * FIR_WS_STRIDE;
-          if (!isfinite(tg[0])) { st = ST_BAD_BANDS; break; }
-          fir_apply(w, tg, p.fir_taps);
-        }
-        break;
-      default: break;
-    }
-  }
-  // ---- scatter back into the position-preserving window (y[valid] = ..., signal_processor.py)
+  return ST_OK;
+}
+
+// scatter back into the position-preserving window (y[valid] = ..., signal_processor.py:202-236)
+__device__ void scatter_window(const Warp& w, int st, int W, double* __restrict__ ox, double* __restrict__ oy,
+                               int32_t* __restrict__ status, long long sig) {
   if (st == ST_OK) {
     for (int i = w.lane; i < w.n; i += 32) {
       const int k = w.posv[i];
       oy[k] = w.yv[i];
       if (w.grid) ox[k] = w.xv[i];
     }
-  } else {
+  } else if (st != ST_GUARD) {
     for (int k = w.lane; k < W; k += 32) oy[k] = nan_f64();
   }
   if (w.lane == 0) status[sig] = st;
 }
 
-template <int FEAT, int MINB>
+__device__ __forceinline__ void prefetch_filters(int FEAT, int lane, const bpv_window_params& p, const DesignRef& dr, long long job) {
+  // the job's filter coefficients are first needed after the gather and the detrend: start pulling them (taps | zi |
+  // autocorrelation: 24 lines, resp. 768 B of sos) towards the SM now, so that the filter stage does not open with a
+  // DRAM round trip
+  for (int i = 0; i < p.num_methods; ++i) {
+    if ((FEAT & F_FIR) && p.methods[i] == BPV_FILTER_FIR && lane < 24)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(dr.fir(job) + lane * 16));
+    if ((FEAT & F_BUTTER) && p.methods[i] == BPV_FILTER_BUTTER && lane * 16 < p.butter_order * 6)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(dr.sos(job) + lane * 16));
+  }
+}
+
+// DUAL = false: one warp per signal.  DUAL = true (every instantiation with FILTER_BUTTER): one warp per PAIR of
+// consecutive signals — the single-signal stages run for one and then the other, the Butterworth cascade for both at once
+// (sos_filtfilt_dual); the warp's shared-memory slice holds two per-signal plans.
+template <int FEAT, int MINB, bool DUAL>
+__global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const double* __restrict__ ring_t,
+                                                                      const double* __restrict__ ring_y,
+                                                                      const bpv_window_params p, const PreLayout L,
+                                                                      const DesignRef dr,
+                                                                      double* __restrict__ proc_x, double* __restrict__ proc_y,
+                                                                      int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long unit = (long long)blockIdx.x * wpb + wib;
+  const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
+  const int W = p.window;
+  const int lane = threadIdx.x & 31;
+  if (!DUAL) {
+    const long long sig = unit;                                    // job * R + r
+    if (sig >= nsig) return;
+    Warp w;
+    w.lane = lane;
+    const long long job = sig / p.R;
+    prefetch_filters(FEAT, lane, p, dr, job);
+    double* ox = proc_x + sig * W;
+    double* oy = proc_y + sig * W;
+    int st = gather_window<FEAT>(w, smem_raw + (size_t)wib * L.total, L, p, ring_t, ring_y, sig, ox, oy);
+    for (int mi = 0; mi < p.num_methods && st == ST_OK; ++mi) st = apply_method<FEAT>(w, p.methods[mi], p, dr, job);
+    scatter_window(w, st, W, ox, oy, status, sig);
+  } else {
+    const long long sa = 2 * unit, sb = sa + 1;
+    if (sa >= nsig) return;
+    const bool hasb = sb < nsig;
+    Warp wa, wb;
+    wa.lane = wb.lane = lane;
+    const long long ja = sa / p.R, jb = (hasb ? sb : sa) / p.R;
+    prefetch_filters(FEAT, lane, p, dr, ja);
+    if (jb != ja) prefetch_filters(FEAT, lane, p, dr, jb);
+    unsigned char* sm = smem_raw + (size_t)wib * 2 * L.total;
+    double* oxa = proc_x + sa * W; double* oya = proc_y + sa * W;
+    double* oxb = proc_x + (hasb ? sb : sa) * W; double* oyb = proc_y + (hasb ? sb : sa) * W;
+    int sta = gather_window<FEAT>(wa, sm, L, p, ring_t, ring_y, sa, oxa, oya);
+    int stb = ST_GUARD;
+    if (hasb) stb = gather_window<FEAT>(wb, sm + L.total, L, p, ring_t, ring_y, sb, oxb, oyb);
+    else { wb = wa; }
+    for (int mi = 0; mi < p.num_methods && (sta == ST_OK || stb == ST_OK); ++mi) {
+      const int m = p.methods[mi];
+      if (m == BPV_FILTER_BUTTER) {
+        const double* ga = dr.sos(ja);
+        const double* gb = dr.sos(jb);
+        if (sta == ST_OK && !isfinite(ga[0])) sta = ST_BAD_BANDS;
+        if (stb == ST_OK && !isfinite(gb[0])) stb = ST_BAD_BANDS;
+        if (sta == ST_OK || stb == ST_OK) sos_filtfilt_dual(wa, wb, sta == ST_OK, stb == ST_OK, ga, gb, p.butter_order);
+      } else {
+        if (sta == ST_OK) sta = apply_method<FEAT & ~F_BUTTER>(wa, m, p, dr, ja);
+        if (stb == ST_OK) stb = apply_method<FEAT & ~F_BUTTER>(wb, m, p, dr, jb);
+      }
+    }
+    scatter_window(wa, sta, W, oxa, oya, status, sa);
+    if (hasb) scatter_window(wb, stb, W, oxb, oyb, status, sb);
+  }
+}
+
+template <int FEAT, int MINB, bool DUAL>
 static int launch_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params& p, const PreLayout& L,
-                             const double* sos_ws, const double* taps_ws, double* proc_x, double* proc_y, int32_t* status,
-                             cudaStream_t st) {
+                             const DesignRef& dr, double* proc_x, double* proc_y, int32_t* status, cudaStream_t st) {
   const int max_smem = 200 * 1024;
-  BPV_REQUIRE(L.total <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
+  const int per_warp = (DUAL ? 2 : 1) * L.total;                 // a warp holds one signal, or a pair of them
+  BPV_REQUIRE(per_warp <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
               p.window, L.total);
-  // warps (signals) per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
+  // warps per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
   const int reg_warps = 4 * MINB;                                // what the register budget of this instantiation allows
   int wpb = 1, best = 0;
   for (int c = 1; c <= 4; ++c) {
-    const int per_block = c * L.total + 1024;                    // + per-CTA reservation
+    const int per_block = c * per_warp + 1024;                   // + per-CTA reservation
     if (per_block > max_smem) break;
     int blocks = (227 * 1024) / per_block;
     if (blocks > 32) blocks = 32;
@@ -723,11 +918,12 @@ static int launch_preprocess(const double* ring_t, const double* ring_y, const b
     if (warps > reg_warps) warps = reg_warps;
     if (warps > best || (warps == best && c < wpb)) { best = warps; wpb = c; }
   }
-  const size_t smem = (size_t)wpb * L.total;
-  auto kern = window_preprocess_kernel<FEAT, MINB>;
+  const size_t smem = (size_t)wpb * per_warp;
+  auto kern = window_preprocess_kernel<FEAT, MINB, DUAL>;
   if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
   const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
-  kern<<<(unsigned)((nsig + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, p, L, sos_ws, taps_ws, proc_x, proc_y, status);
+  const long long units = DUAL ? (nsig + 1) / 2 : nsig;
+  kern<<<(unsigned)((units + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, p, L, dr, proc_x, proc_y, status);
   return check_launch("bpv_window_preprocess");
 }
 
@@ -747,14 +943,30 @@ static int parse_methods(const bpv_window_params* p, const char* who, bool& butt
 
 }  // namespace bpv
 
+// workspace of a launch: sos [J][16*6] | fir [J][FIR_WS_STRIDE] | ref int32 [J] (padded to 8 B) | miss list [J] x 16 B
+namespace bpv {
+struct WsPlan { long long sos, fir, ref, miss, total; };
+static WsPlan ws_plan(const bpv_window_params* p) {
+  const long long J = (long long)p->S * p->jobs_per_stream;
+  WsPlan w;
+  w.sos = 0;
+  w.fir = w.sos + J * MAX_SOS * 6 * 8;
+  w.ref = w.fir + J * FIR_WS_STRIDE * 8;
+  w.miss = w.ref + (J * 4 + 7) / 8 * 8;
+  w.total = w.miss + J * 16;
+  return w;
+}
+}  // namespace bpv
+
 extern "C" int64_t bpv_window_workspace_bytes(const bpv_window_params* p) {
   if (!p) return -1;
-  const int64_t J = (int64_t)p->S * p->jobs_per_stream;
-  return J * (int64_t)(bpv::MAX_SOS * 6 + bpv::FIR_WS_STRIDE) * 8;   // per job: sos[16][6] | taps[128] | zi[128] | autocorrelation[128]
+  return bpv::ws_plan(p).total;
 }
 
+extern "C" int64_t bpv_design_cache_bytes(void) { return bpv::DC_BYTES; }
+
 extern "C" int bpv_window_design(const double* ring_t, const bpv_window_params* p, void* workspace, int64_t workspace_bytes,
-                                 void* stream) {
+                                 void* cache, int64_t cache_bytes, void* stream) {
   using namespace bpv;
   if (int rc = check_filter_params(p, "bpv_window_design")) return rc;
   BPV_REQUIRE(ring_t, BPV_E_INVALID, "bpv_window_design: NULL pointer");
@@ -762,19 +974,23 @@ extern "C" int bpv_window_design(const double* ring_t, const bpv_window_params* 
   bool butter, fir, interp;
   if (int rc = parse_methods(p, "bpv_window_design", butter, fir, interp)) return rc;
   if (!butter && !fir) return 0;
-  BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
+  const WsPlan wp = ws_plan(p);
+  BPV_REQUIRE(workspace && workspace_bytes >= wp.total, BPV_E_INVALID,
               "bpv_window_design: workspace too small (see bpv_window_workspace_bytes)");
-  const long long J = (long long)p->S * p->jobs_per_stream;
-  double* sos_ws = (double*)workspace;
-  double* taps_ws = sos_ws + J * MAX_SOS * 6;
+  BPV_REQUIRE(!cache || cache_bytes >= DC_BYTES, BPV_E_INVALID, "bpv_window_design: design cache too small (see bpv_design_cache_bytes)");
+  unsigned char* ws = (unsigned char*)workspace;
+  double* sos_ws = (double*)(ws + wp.sos);
+  double* taps_ws = (double*)(ws + wp.fir);
   cudaStream_t st = (cudaStream_t)stream;
+  if (cache)
+    return launch_design_cached(ring_t, *p, butter, fir, (unsigned char*)cache, (int32_t*)(ws + wp.ref), ws + wp.miss, sos_ws, taps_ws, st);
   if (butter) if (int rc = launch_job_butter(ring_t, *p, sos_ws, st)) return rc;
   if (fir) if (int rc = launch_job_firls(ring_t, *p, taps_ws, st)) return rc;
   return 0;
 }
 
 extern "C" int bpv_window_filter(const double* ring_t, const double* ring_y, const bpv_window_params* p,
-                                 const void* workspace, int64_t workspace_bytes,
+                                 const void* workspace, int64_t workspace_bytes, const void* cache, int64_t cache_bytes,
                                  double* proc_x, double* proc_y, int32_t* status, void* stream) {
   using namespace bpv;
   if (int rc = check_filter_params(p, "bpv_window_preprocess")) return rc;
@@ -784,26 +1000,37 @@ extern "C" int bpv_window_filter(const double* ring_t, const double* ring_y, con
   BPV_REQUIRE(p->window <= 65535, BPV_E_TOO_LARGE, "bpv_window_preprocess: window > 65535");
   bool butter, fir, interp;
   if (int rc = parse_methods(p, "bpv_window_preprocess", butter, fir, interp)) return rc;
-  const long long J = (long long)p->S * p->jobs_per_stream;
-  const double* sos_ws = (const double*)workspace;
-  const double* taps_ws = sos_ws ? sos_ws + J * MAX_SOS * 6 : nullptr;
-  if (butter || fir)
-    BPV_REQUIRE(workspace && workspace_bytes >= bpv_window_workspace_bytes(p), BPV_E_INVALID,
+  const WsPlan wp = ws_plan(p);
+  if (butter || fir) {
+    BPV_REQUIRE(workspace && workspace_bytes >= wp.total, BPV_E_INVALID,
                 "bpv_window_preprocess: workspace too small (see bpv_window_workspace_bytes)");
+    BPV_REQUIRE(!cache || cache_bytes >= DC_BYTES, BPV_E_INVALID, "bpv_window_preprocess: design cache too small (see bpv_design_cache_bytes)");
+  }
+  const unsigned char* ws = (const unsigned char*)workspace;
+  DesignRef dr;
+  dr.sos_ws = ws ? (const double*)(ws + wp.sos) : nullptr;
+  dr.taps_ws = ws ? (const double*)(ws + wp.fir) : nullptr;
+  dr.ref = (ws && cache && (butter || fir)) ? (const int32_t*)(ws + wp.ref) : nullptr;
+  dr.cache = (const unsigned char*)cache;
   const PreLayout L = pre_layout(*p);
   cudaStream_t st = (cudaStream_t)stream;
-#define BPV_PRE(feat, minb) return launch_preprocess<feat, minb>(ring_t, ring_y, *p, L, sos_ws, taps_ws, proc_x, proc_y, status, st)
-  if (!interp && !butter && !fir) BPV_PRE(0, 6);
-  if (!interp && !butter) BPV_PRE(F_FIR, 5);
-  if (!interp && !fir) BPV_PRE(F_BUTTER, 5);
-  if (!fir) BPV_PRE(F_INTERP | F_BUTTER, 4);
-  BPV_PRE(F_INTERP | F_BUTTER | F_FIR, 4);
+#define BPV_PRE(feat, minb, dual) return launch_preprocess<feat, minb, dual>(ring_t, ring_y, *p, L, dr, proc_x, proc_y, status, st)
+  const bool single_sos = getenv("BPV_SOS_SINGLE") != nullptr;     // development / test switch: one signal per warp everywhere
+  if (!interp && !butter && !fir) BPV_PRE(0, 6, false);
+  if (!interp && !butter) BPV_PRE(F_FIR, 5, false);
+  if (single_sos) {
+    if (!interp && !fir) BPV_PRE(F_BUTTER, 4, false);
+    BPV_PRE(F_INTERP | F_BUTTER | F_FIR, 4, false);
+  }
+  if (!interp && !fir) BPV_PRE(F_BUTTER, 4, true);
+  if (!fir) BPV_PRE(F_INTERP | F_BUTTER, 4, true);
+  BPV_PRE(F_INTERP | F_BUTTER | F_FIR, 4, true);
 #undef BPV_PRE
 }
 
 extern "C" int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
                                      void* workspace, int64_t workspace_bytes,
                                      double* proc_x, double* proc_y, int32_t* status, void* stream) {
-  if (int rc = bpv_window_design(ring_t, p, workspace, workspace_bytes, stream)) return rc;
-  return bpv_window_filter(ring_t, ring_y, p, workspace, workspace_bytes, proc_x, proc_y, status, stream);
+  if (int rc = bpv_window_design(ring_t, p, workspace, workspace_bytes, nullptr, 0, stream)) return rc;
+  return bpv_window_filter(ring_t, ring_y, p, workspace, workspace_bytes, nullptr, 0, proc_x, proc_y, status, stream);
 }

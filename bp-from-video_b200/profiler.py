@@ -8,7 +8,7 @@ with a cheap wall-clock accumulator per decorated function.
 import functools
 import time
 
-PROFILER_ENABLED = False
+PROFILER_ENABLED = True      # as the reference (profiler.py:7): bp.py prints the per-stage table at exit; pbp.py:11 switches it off
 
 
 class Profiler:

@@ -22,25 +22,21 @@ class ROIConfig:
     relative_bbox: tuple[float, float, float, float]
 
 
-# landmark indices of the MediaPipe topologies the reference anchors on (roi.py:16-22), exported as module constants
-_LANDMARK = {
-    'FACE_DETECTION': {'NOSE': 2},
-    'FACE_LANDMARKS': {'NOSE': 4, 'FOREHEAD': 151, 'CHEEK': 330, 'EYEBROW': 337},
-    'HAND_LANDMARKS': {'WRIST': 0, 'MIDDLE': 9},
-}
-globals().update({f'{topo}_{part}_INDEX': idx for topo, parts in _LANDMARK.items() for part, idx in parts.items()})
-
-
-def _config(detector: model.ModelType, topo: str, parts: list[str], box: tuple[float, float, float, float]) -> ROIConfig:
-    return ROIConfig(detector, [_LANDMARK[topo][p] for p in parts], box)
-
+# landmark indices of the MediaPipe topologies the reference anchors on (roi.py:16-22)
+FACE_DETECTION_NOSE_INDEX = 2
+FACE_LANDMARKS_NOSE_INDEX = 4
+FACE_LANDMARKS_FOREHEAD_INDEX = 151
+FACE_LANDMARKS_CHEEK_INDEX = 330
+FACE_LANDMARKS_EYEBROW_INDEX = 337
+HAND_LANDMARKS_WRIST_INDEX = 0
+HAND_LANDMARKS_MIDDLE_INDEX = 9
 
 _FACE, _HAND = model.ModelType.FACE_LANDMARKER, model.ModelType.HAND_LANDMARKER
 # (left, top, right, bottom) fractions of the detection bbox around the anchor (roi.py:24-28)
-FACE_CHEEK_CONFIG = _config(_FACE, 'FACE_LANDMARKS', ['CHEEK'], (-0.05, -0.05, 0.15, 0.05))
-FACE_EYEBROW_CONFIG = _config(_FACE, 'FACE_LANDMARKS', ['EYEBROW'], (-0.10, -0.15, 0.25, 0.00))
-FACE_FOREHEAD_CONFIG = _config(_FACE, 'FACE_LANDMARKS', ['FOREHEAD'], (-0.00, -0.10, 0.20, 0.05))
-HAND_WRIST_CONFIG = _config(_HAND, 'HAND_LANDMARKS', ['WRIST'], (-0.10, -0.10, 0.10, 0.10))
-HAND_PALM_CONFIG = _config(_HAND, 'HAND_LANDMARKS', ['WRIST', 'MIDDLE'], (-0.10, -0.10, 0.10, 0.10))
+FACE_CHEEK_CONFIG = ROIConfig(_FACE, [FACE_LANDMARKS_CHEEK_INDEX], (-0.05, -0.05, 0.15, 0.05))
+FACE_EYEBROW_CONFIG = ROIConfig(_FACE, [FACE_LANDMARKS_EYEBROW_INDEX], (-0.10, -0.15, 0.25, 0.00))
+FACE_FOREHEAD_CONFIG = ROIConfig(_FACE, [FACE_LANDMARKS_FOREHEAD_INDEX], (-0.00, -0.10, 0.20, 0.05))
+HAND_WRIST_CONFIG = ROIConfig(_HAND, [HAND_LANDMARKS_WRIST_INDEX], (-0.10, -0.10, 0.10, 0.10))
+HAND_PALM_CONFIG = ROIConfig(_HAND, [HAND_LANDMARKS_WRIST_INDEX, HAND_LANDMARKS_MIDDLE_INDEX], (-0.10, -0.10, 0.10, 0.10))
 
 SELECTED_ROI_CONFIGS = [FACE_FOREHEAD_CONFIG, HAND_PALM_CONFIG]   # roi.py:30

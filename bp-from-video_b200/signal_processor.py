@@ -151,6 +151,7 @@ class SignalProcessor:
         self.ls_num_freqs = ls_num_freqs            # extension (BASELINE config 3); None = reference grid F = n
         self.device = device
         self._engine = None
+        self._engine_key = None
         self._staging = None
 
     # ------------------------------------------------------------------------------------------
@@ -164,15 +165,42 @@ class SignalProcessor:
         return [_code(m) for m in self.processing_methods]
 
     def _get_engine(self):
-        """The S=1 batched engine behind process(); created on first use (inside pbp's child process)."""
+        """The S=1 batched engine behind process(); created on first use (inside pbp's child process).  Its device ring
+        mirrors store.sg_raw: it is rebuilt and re-seeded from the store whenever the geometry (signal_max_samples, number
+        of ROIs) or the store itself has been replaced since the last frame, so edits between frames behave as they do
+        in the reference, which reads everything from self.store every frame."""
         from bpv.engine import BatchedSignalProcessor
-        if self._engine is None:
+        key = (self.num_signals, int(self.signal_max_samples), id(self.store), id(self.store.sg_raw))
+        if self._engine is None or self._engine_key != key:
+            self.num_signals = len(self.selected_roi_configs)
             self._engine = BatchedSignalProcessor(1, self.num_signals, signal_max_samples=self.signal_max_samples,
                                                   max_frames_per_step=1, store_arrays=True, device=self.device)
+            self._seed_engine(self._engine)
+            self._engine_key = (self.num_signals, int(self.signal_max_samples), id(self.store), id(self.store.sg_raw))
         e = self._engine          # attributes may be edited between frames, as users of the reference do
         e.color_channel = _code(self.color_channel, 1)
         e.methods, e.transform, e.kw = self._methods(), _code(self.spectrum_transform), self._kw()
         return e
+
+    def _seed_engine(self, eng) -> None:
+        """Load the raw-sample window of the store (a restored / replaced SignalStore, or a fresh NaN-prefilled one) into
+        the engine's ring: the last W samples of sg_raw become global indices 0 .. W-1."""
+        import torch
+        W, sigs = eng.W, list(self.store.sg_raw.signals)
+        if len(sigs) != eng.R:
+            raise ValueError(f'store.sg_raw holds {len(sigs)} signals, the processor has {eng.R} ROIs')
+        t = np.full(W, np.nan)
+        y = np.full((eng.R, W), np.nan)
+        for r, sg in enumerate(sigs):
+            x, v = np.asarray(sg.x, dtype=float)[-W:], np.asarray(sg.y, dtype=float)[-W:]
+            if r == 0 and x.size:
+                t[W - x.size:] = x
+            if v.size:
+                y[r, W - v.size:] = v
+        eng.reset()
+        eng.ring_t[0, :W] = torch.from_numpy(t).to(eng.device)
+        eng.ring_y[0, :, :W] = torch.from_numpy(y).to(eng.device)
+        eng.count = W
 
     def _stage_frame(self, frame):
         """Frame -> pinned host staging buffer the ROI kernel reads zero-copy (only ROI rows cross PCIe)."""
@@ -306,6 +334,22 @@ class SignalProcessor:
                 groups.append([s])
         return groups
 
+    @staticmethod
+    def _decided(x32, y32, idx, x_peak, y_peak):
+        """float32 device arrays -> the float64 arrays of the store, made consistent with the float64 peak decision of the
+        device: the winning bin carries the float64 (x, y) of the peak, and no other finite bin may beat it under numpy's
+        first-maximum rule (a float32-rounded neighbour of a near-tie could).  So the returned SignalStore answers
+        get_peaks() exactly as sg_bpm / sg_ptt recorded it, as the reference's store does."""
+        x, y = np.asarray(x32, dtype=float).copy(), np.asarray(y32, dtype=float).copy()
+        idx = int(idx)
+        if 0 <= idx < y.size and np.isfinite(y_peak):
+            below = np.nextafter(y_peak, -np.inf)
+            head, tail = y[:idx], y[idx + 1:]
+            head[head >= y_peak] = below           # earlier bins must be strictly smaller (first maximum wins)
+            tail[tail > y_peak] = y_peak
+            x[idx], y[idx] = x_peak, y_peak
+        return x, y
+
     def _spectrum_signal(self, freqs, mags):
         sig = signal_data.Signal(list(freqs), list(mags), s_maxlen=len(freqs))
         sig.set_range((self.min_freq, self.max_freq), (self.min_mag, self.max_mag))
@@ -372,18 +416,22 @@ class SignalProcessor:
         samples = res.samples.cpu().numpy()[0, 0]
         status = res.status.cpu().numpy()
         peak_f, lag_s = res.peak_freq.cpu().numpy()[0], res.lag_sec.cpu().numpy()[0]
-        self._raise_status(status)
         R, W = self.num_signals, self.signal_max_samples
-        st.sg_raw.add_samples(ts, [np.float64(v) for v in samples])
+        st.sg_raw.add_samples(ts, [np.float64(v) for v in samples])     # before any raise, as the reference (:307-308)
+        self._raise_status(status)
         st.sg_proc = signal_data.SignalGroup(signals=[signal_data.Signal(host['proc_x'][0, r], host['proc_y'][0, r], W) for r in range(R)])
         nb = host['num_bins'][0]
-        st.sg_spec = signal_data.SignalGroup(signals=[self._spectrum_signal(host['freqs'][0, r, :nb[r]].astype(float),
-                                                                            host['mags'][0, r, :nb[r]].astype(float)) for r in range(R)])
+        pidx, pmag = res.peak_idx.cpu().numpy()[0], res.peak_mag.cpu().numpy()[0]
+        st.sg_spec = signal_data.SignalGroup(signals=[
+            self._spectrum_signal(*self._decided(host['freqs'][0, r, :nb[r]], host['mags'][0, r, :nb[r]], pidx[r], peak_f[r], pmag[r]))
+            for r in range(R)])
         st.sg_bpm.add_samples(ts, [f * 60 for f in peak_f])             # peak decided in float64 on the device
         pairs = math.comb(R, 2)
         nl = host['num_lags'][0] if pairs else []
-        st.sg_corr = signal_data.SignalGroup(signals=[self._corr_signal(host['lags'][0, k, :nl[k]].astype(float),
-                                                                        host['corr'][0, k, :nl[k]].astype(float)) for k in range(pairs)])
+        lidx, lcorr = res.lag_idx.cpu().numpy()[0], res.lag_corr.cpu().numpy()[0]
+        st.sg_corr = signal_data.SignalGroup(signals=[
+            self._corr_signal(*self._decided(host['lags'][0, k, :nl[k]], host['corr'][0, k, :nl[k]], lidx[k], lag_s[k], lcorr[k]))
+            for k in range(pairs)])
         st.sg_ptt.add_samples(ts, [t * 1000 for t in lag_s])
         return st.snapshot()
 

@@ -198,16 +198,22 @@ int64_t bpv_window_workspace_bytes(const bpv_window_params* p);
 int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_window_params* p,
                           void* workspace, int64_t workspace_bytes,
                           double* proc_x, double* proc_y, int32_t* status, void* stream);
-/* The two halves of bpv_window_preprocess, for callers that overlap them:
+/* The two halves of bpv_window_preprocess, for callers that overlap them or keep a design cache:
  * bpv_window_design — make_filter for every window job (signal_processor.py:158-173, called per frame and signal at
  *   :226, :232): needs only the timestamps (ring_t), so it can run on another stream as soon as they are pushed, beside
  *   the ROI sampling of the same frames.  Fills `workspace` (per job: Butterworth sos | FIR taps | lfilter_zi | tap
  *   autocorrelation).
- * bpv_window_filter — process_signal given the designs in `workspace` (same stream, or after an event on the design). */
+ * bpv_window_filter — process_signal given the designs (same stream, or after an event on the design).
+ * cache (optional, may be NULL): caller-owned device memory of bpv_design_cache_bytes() bytes, zero-initialised, kept
+ *   across calls.  make_filter is a pure function of the window's sampling rate; the cache is a table keyed by the 64 bits
+ *   of fs, so a rate that has been designed before (constant-fps streams: every window, every stream on the same clock)
+ *   costs a lookup instead of a design.  Hits return the very bits a fresh design produces.  The table belongs to ONE
+ *   set of filter parameters (orders, taps, band edges): zero it when they change.  Pass the same cache to both calls. */
+int64_t bpv_design_cache_bytes(void);
 int bpv_window_design(const double* ring_t, const bpv_window_params* p, void* workspace, int64_t workspace_bytes,
-                      void* stream);
+                      void* cache, int64_t cache_bytes, void* stream);
 int bpv_window_filter(const double* ring_t, const double* ring_y, const bpv_window_params* p,
-                      const void* workspace, int64_t workspace_bytes,
+                      const void* workspace, int64_t workspace_bytes, const void* cache, int64_t cache_bytes,
                       double* proc_x, double* proc_y, int32_t* status, void* stream);
 
 /* F3 + F4(a) spectrum and HR peak — replaces transform_signal(s) + SignalGroup.get_peaks on

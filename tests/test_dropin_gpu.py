@@ -131,3 +131,71 @@ def test_method_surface_matches_oracle():
     proc.color_channel = 'nope'
     with pytest.raises((NotImplementedError, ValueError, TypeError)):
         proc.sample_signal(big, (0, 0, 1, 1, 5, 5))
+
+
+@pytest.mark.parametrize('name', ['c1_butter_ls', 'c2_detrend_fir_welch', 'lin_const_fir_dft'])
+def test_returned_store_is_self_consistent(name):
+    """recomputing the peaks from the returned store (as the reference's own process() does,
+    signal_processor.py:310, 312) gives exactly what sg_bpm / sg_ptt recorded — the float32 device spectra are made
+    consistent with the float64 peak decision."""
+    import signal_processor as sp
+    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = h.CASES[name]
+    g = h.load_case(name)
+    frames = h.case_frames(g)
+    proc = sp.SignalProcessor(None, roi_ms, window, 50, color_channel=sp.SignalColorChannel[channel],
+                              processing_methods=[sp.SignalProcessingMethod[m] for m in methods],
+                              spectrum_transform=sp.SignalSpectrumTransform[transform], **kw)
+    for i in range(n):
+        store = proc.process(_Frame(frames[i], float(g['ts'][i])), _results(g, i))
+        assert h.same([f * 60 for f, _ in store.sg_spec.get_peaks()], [s.y[-1] for s in store.sg_bpm]), (name, i)
+        assert h.same([t * 1000 for t, _ in store.sg_corr.get_peaks()], [s.y[-1] for s in store.sg_ptt]), (name, i)
+
+
+def test_store_replacement_reseeds_the_device_ring():
+    """The reference reads everything from self.store each frame, so a caller may restore a pickled store (pbp.py ships
+    stores between processes) or swap it: the drop-in re-seeds its device ring from the new store."""
+    import signal_processor as sp
+    name = 'c2_detrend_fir_welch'
+    channel, methods, transform, window, n, fps, irregular, p_none, roi_ms, kw = h.CASES[name]
+    g = h.load_case(name)
+    frames = h.case_frames(g)
+    mk = lambda: sp.SignalProcessor(None, roi_ms, window, 50, color_channel=sp.SignalColorChannel[channel],
+                                    processing_methods=[sp.SignalProcessingMethod[m] for m in methods],
+                                    spectrum_transform=sp.SignalSpectrumTransform[transform], **kw)
+    a, b = mk(), mk()
+    cut = n // 2
+    full = [a.process(_Frame(frames[i], float(g['ts'][i])), _results(g, i)) for i in range(n)]
+    for i in range(cut):
+        st = b.process(_Frame(frames[i], float(g['ts'][i])), _results(g, i))
+    c = mk()
+    c.store = pickle.loads(pickle.dumps(st))
+    for i in range(cut, n):
+        got = c.process(_Frame(frames[i], float(g['ts'][i])), _results(g, i))
+        assert h.same([s.y[-1] for s in got.sg_bpm], [s.y[-1] for s in full[i].sg_bpm]), i
+        assert h.same([s.y[-1] for s in got.sg_ptt], [s.y[-1] for s in full[i].sg_ptt]), i
+        assert h.same(np.asarray(got.sg_raw.signals[0].y), np.asarray(full[i].sg_raw.signals[0].y)), i
+
+
+def test_exception_keeps_store_and_ring_in_step():
+    """INTERP_CUBIC on duplicate timestamps raises ValueError out of process() (scipy CubicSpline in the reference); the
+    reference has appended the raw sample by then (signal_processor.py:307-308), and so has the drop-in: the frames after
+    the failure see the same window in the store and on the device."""
+    import signal_processor as sp
+    rng = np.random.default_rng(0)
+    H, W = h.IMG_H, h.IMG_W
+    proc = sp.SignalProcessor(None, 1, 24, 50, color_channel=sp.SignalColorChannel.GREEN,
+                              processing_methods=[sp.SignalProcessingMethod.INTERP_CUBIC], spectrum_transform=sp.SignalSpectrumTransform.DFT_RFFT)
+    face = [((10, 5, 50, 45), np.full((478, 2), 30, np.int64))]
+    hand = [((40, 30, 70, 55), np.full((21, 2), 50, np.int64))]
+    ts = [0.1, 0.2, 0.3, 0.3, 0.4, 0.5]
+    raised = 0
+    for i, t in enumerate(ts):
+        fr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        try:
+            store = proc.process(_Frame(fr, t), _Res(face, hand))
+        except ValueError:
+            raised += 1
+        assert np.isfinite(np.asarray(proc.store.sg_raw.signals[0].y)).sum() == i + 1
+        ring = proc._engine.ring_y[0, 0].cpu().numpy()
+        assert np.isfinite(ring).sum() == i + 1
+    assert raised >= 1

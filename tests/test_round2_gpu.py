@@ -270,3 +270,70 @@ def test_engine_on_second_gpu_while_current_device_is_first():
     assert rb.peak_freq.device == torch.device('cuda:1')
     sa, sb = _snap(ra), {k: v.to('cuda:0') for k, v in _snap(rb).items()}
     assert _same(sa, sb)
+
+
+@pytest.mark.parametrize('methods', [[orc.FILTER_BUTTER], [orc.INTERP_CUBIC, orc.FILTER_BUTTER], [orc.DETREND_LINEAR, orc.FILTER_BUTTER, orc.DIFF_1],
+                                     [orc.FILTER_FIR, orc.FILTER_BUTTER]])
+@pytest.mark.parametrize('R', [1, 2, 3])
+def test_two_signal_butterworth_cascade_is_bit_identical(methods, R, monkeypatch):
+    """FILTER_BUTTER runs two signals per warp (lanes 0-15 / 16-31 each own a 16-section cascade); the arithmetic per lane
+    is that of the one-signal-per-warp kernel (BPV_SOS_SINGLE=1), so every output bit must agree — for odd signal counts,
+    pairs that straddle window jobs (R = 1, 3), windows of different lengths in one warp, guard failures and bad bands."""
+    from tests.test_window_gpu import make_windows, to_ring, params
+    from bpv import ops
+    S, W = 45, 120
+    fill = [W, W - 1, 100, 64, 33, 17, 5, 3, 2, 1, 0]
+    t, y = make_windows(77 + R, S, W, R, fps=30.0, fill=fill)
+    t[7] = np.where(np.isfinite(t[7]), t[7][np.isfinite(t[7])][0] + np.arange(W) * 0.4, np.nan)      # 2.5 fps: band edges invalid
+    rt, ry = to_ring(t, y)
+    p = params(S, R, W, methods, fir_taps=31)
+    monkeypatch.delenv('BPV_SOS_SINGLE', raising=False)
+    px2, py2, st2 = ops.window_preprocess(rt, ry, p)
+    monkeypatch.setenv('BPV_SOS_SINGLE', '1')
+    px1, py1, st1 = ops.window_preprocess(rt, ry, p)
+    assert torch.equal(st1, st2)
+    assert torch.equal(py1.view(torch.int64), py2.view(torch.int64))
+    assert torch.equal(px1.view(torch.int64), px2.view(torch.int64))
+    assert int((st1 == 0).sum()) > S // 2 and int((st1 == 3).sum()) >= 1
+
+
+@pytest.mark.parametrize('methods,transform', [([orc.DETREND_LINEAR, orc.FILTER_FIR], orc.PGRAM_WELCH),
+                                               ([orc.FILTER_BUTTER], orc.DFT_RFFT),
+                                               ([orc.FILTER_FIR, orc.FILTER_BUTTER], orc.PGRAM_WELCH)])
+@pytest.mark.parametrize('irregular', [False, True])
+def test_design_cache_is_bit_identical_to_fresh_designs(methods, transform, irregular):
+    """The fs-keyed design cache (hits on regular timestamps; all-distinct rates, table overflow, own-slot fallback and the
+    clear-on-thrash path on jittered ones with 300 streams x 4 jobs > 256 slots) returns exactly the bits of per-job designs."""
+    from bpv import synth
+    from bpv.engine import BatchedSignalProcessor
+    S, T, W, steps = 300, 4, 140, 9
+    rng = np.random.default_rng(5)
+    ts = np.stack([synth.timestamps(rng, T * steps, 30.0, irregular=irregular, drop=0.02 if irregular else 0.0,
+                                    origin=rng.uniform(0, 3) if irregular else 0.0) for _ in range(S)])
+    raw = np.stack([synth.raw_signals(rng, ts[s], R=2, p_nan=0.02).T for s in range(S)])
+    outs = []
+    for cache in (False, True):
+        eng = BatchedSignalProcessor(S, 2, signal_max_samples=W, max_frames_per_step=T, processing_methods=methods,
+                                     spectrum_transform=transform, design_cache=cache, store_arrays=True, fir_taps=63)
+        run = []
+        for k in range(steps):
+            res = eng.step_signals(torch.from_numpy(raw[:, k * T:(k + 1) * T].copy()).cuda(), torch.from_numpy(ts[:, k * T:(k + 1) * T].copy()).cuda())
+            run.append((_snap(res), res.arrays['proc_y'].clone()))
+        outs.append(run)
+    for (a, pa), (b, pb) in zip(*outs):
+        assert _same(a, b)
+        assert torch.equal(pa.view(torch.int64), pb.view(torch.int64))
+
+
+def test_design_cache_is_dropped_when_filter_parameters_change():
+    """The table is keyed by fs only; the engine empties it when the band edges / orders it was filled under change (the
+    drop-in SignalProcessor lets callers edit them between frames)."""
+    S, T = 8, 3
+    feed = _signal_steps(31, S, T, 24)
+    a = _engine(S, 40, T, design_cache=True)
+    b = _engine(S, 40, T, design_cache=False)
+    for k, f in enumerate(feed):
+        if k == 12:
+            for e in (a, b):
+                e.kw = dict(e.kw, min_freq=1.1, fir_df=0.25)
+        assert _same(_snap(a.step_signals(*f)), _snap(b.step_signals(*f))), k
