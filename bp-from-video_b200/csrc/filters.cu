@@ -134,6 +134,7 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
   double f[FIRLS_EPL], x[FIRLS_EPL];
 #pragma unroll
   for (int m = 0; m < FIRLS_EPL; ++m) { f[m] = 0.0; x[m] = 0.0; }
+  double dmin = 1.0;
   const double r0inv = 1.0 / r[0];
   if (sub == 0) { f[0] = r0inv; x[0] = bt[M] * r0inv; fA[0] = r0inv; }
   __syncwarp();
@@ -165,7 +166,9 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
     const int dk = k < M ? M - k : k - M;
     const double ykk = bt[dk];
     const double ef = group_sum_d(ef0 + ef1), ex = group_sum_d(ex0 + ex1);
-    const double dinv = 1.0 / (1.0 - ef * ef);
+    const double den2 = 1.0 - ef * ef;               // 1 - (reflection coefficient)^2 = ratio of successive leading minors
+    dmin = fmin(dmin, den2);
+    const double dinv = 1.0 / den2;
     const double gd = (ykk - ex) * dinv;
     double* fw = fn + sub;
 #define FIRLS_UPD(m)                                                           \
@@ -194,6 +197,12 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
 #undef FIRLS_UPD
     __syncwarp();
   }
+  // scipy solves Q a = b by Cholesky and, when LAPACK reports the matrix rank deficient / ill-conditioned (rcond < eps),
+  // falls back to lstsq (_fir_filter_design.py:1156-1168).  The Toeplitz recursion has no such fallback: a leading minor
+  // ratio at rounding level is reported as a failed design (NaN taps -> status 3 -> ValueError in the drop-in) instead of
+  // returning taps that differ from the reference's.  Unreachable for the reference's band layout (cond(T) <= 7e4, i.e.
+  // 1 - ef^2 >= 1e-5, over every valid fs).
+  const bool solved = dmin > 1.0e-13;
   // taps out (NaN when scipy would raise), staged through shared memory for lfilter_zi
   double* hs = r;                                                 // [128] taps, zero padded
   __syncwarp();
@@ -201,7 +210,7 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
   for (int m = 0; m < FIRLS_EPL; ++m) {
     const int i = sub + FIRLS_LPD * m;
     hs[i] = i < n ? x[m] : 0.0;
-    if (live && i < n) out[i] = ok ? x[m] : nan_f64();
+    if (live && i < n) out[i] = (ok && solved) ? x[m] : nan_f64();
   }
   __syncwarp();
   if (zi_out && live) {

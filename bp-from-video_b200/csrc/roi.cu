@@ -469,6 +469,240 @@ __global__ void __launch_bounds__(THREADS) roi_staged_kernel(const RoiArgs a, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, double-buffered variant of the staged path.  The one-ROI-per-CTA kernel above has its loads in flight for
+// only part of a CTA's life (launch, the dependent box load, address set-up, the reduction and the exit carry none), and
+// a 16 384-CTA grid on 148 x 9 slots ends in a partial wave.  Here a CTA lives for the whole launch and claims ROIs from a
+// global counter (perfect balance, no tail); it owns TWO stages of K slots per thread, and issues the cp.async of its
+// next ROI before it waits for the current one, so every CTA always has one whole ROI tile in flight and usually two.
+// ROIs that do not fit one stage (wider than THREADS vectors, or more than K row steps) are processed in place, round by
+// round, as the kernel above does.  work[0] = next ROI, work[1] = CTAs done; the last CTA out resets both.
+// ---------------------------------------------------------------------------------------------
+struct PTile {
+  long long roi;
+  uintptr_t p0;                 // address of this thread's first vector
+  long long step;               // bytes between its row steps
+  int nrows, row_bytes, ncols, nslots;
+  bool has_box, simple;
+  uint32_t cT[4], cG[4], cB[4];
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int THREADS, int K>
+__device__ __forceinline__ void ptile_setup(PTile& t, const RoiArgs& a, long long roi, int gt) {
+  t.roi = roi;
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  const int4 b = __ldg(reinterpret_cast<const int4*>(a.boxes) + roi);
+  t.has_box = b.x != BPV_NO_BOX;
+  uintptr_t base = 0;
+  if (t.has_box) {
+    py_slice(b.x, b.z, a.W, xs, xe);
+    py_slice(b.y, b.w, a.H, ys, ye);
+    const long long f = roi / a.R;
+    const uint8_t* fp = a.frame_ptrs ? a.frame_ptrs[f] : a.frames + f * a.frame_stride;
+    base = reinterpret_cast<uintptr_t>(fp) + (uintptr_t)((long long)ys * a.row_stride + (long long)xs * 3);
+  }
+  t.nrows = ye - ys; t.ncols = xe - xs; t.row_bytes = (xe - xs) * 3;
+  t.nslots = 0; t.simple = true; t.p0 = base; t.step = 0;
+  if (t.nrows > 0 && t.row_bytes > 0) {
+    const int off = (int)(base & 15);
+    const int vpr = (off + t.row_bytes + 15) >> 4;
+    if (vpr > THREADS) { t.simple = false; return; }
+    const int rps = THREADS / vpr, r0 = gt / vpr, v0 = gt - r0 * vpr;
+    if (t.nrows > rps * K) { t.simple = false; return; }
+    if (r0 < rps && r0 < t.nrows) {
+      const int rel = 16 * v0 - off;
+      const int lo = rel < 0 ? -rel : 0;
+      const int e = t.row_bytes - rel;
+      const int hi = e < 16 ? e : 16;
+      const int ph = (rel + 15) % 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = byte_mask(lo - 4 * j, hi - 4 * j);
+        t.cT[j] = m & 0x01010101u;
+        t.cG[j] = m & sel_word((ph + 2) % 3, j);
+        t.cB[j] = m & sel_word(ph, j);
+      }
+      t.p0 = base - off + (uintptr_t)((long long)r0 * a.row_stride + 16 * v0);
+      t.step = (long long)rps * a.row_stride;
+      t.nslots = (t.nrows - r0 + rps - 1) / rps;
+    }
+  }
+}
+
+// One turn of the pipeline: issue the tile after `t` into the other stage, wait for `t`, reduce and emit it.
+// CUR is a compile-time stage index so that both tiles stay in registers.
+template <int THREADS, int K, bool WANT_SUMS, int CUR>
+__device__ __forceinline__ bool roi_pipeline_turn(const RoiArgs& a, PTile& t, PTile& n, unsigned int* __restrict__ work,
+                                                  long long* s_claim, unsigned long long (*part)[THREADS / 32][3],
+                                                  uint32_t slot0, unsigned long long pol) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t STAGE_BYTES = THREADS * K * 16;
+  const int gt = threadIdx.x, wid = gt >> 5, lane = gt & 31;
+  const long long rn = s_claim[CUR ^ 1];
+  const bool have_next = rn < a.num_rois;
+  unsigned int claim = 0xffffffffu;
+  if (gt == 0 && have_next) claim = atomicAdd(work, 1u);          // the ROI after next; published before the barrier below
+  const uint32_t sb_next = slot0 + (uint32_t)(CUR ^ 1) * STAGE_BYTES, sb_cur = slot0 + (uint32_t)CUR * STAGE_BYTES;
+  if (have_next) {
+    ptile_setup<THREADS, K>(n, a, rn, gt);
+#pragma unroll
+    for (int u = 0; u < K; ++u)
+      if (u < n.nslots) cp_async16_64B(sb_next + (uint32_t)(u * THREADS * 16), reinterpret_cast<const void*>(n.p0 + u * n.step), pol);
+    cp_async_commit();
+    cp_async_wait_group<1>();
+  } else {
+    cp_async_wait_group<0>();
+  }
+  uint32_t sG = 0, sT = 0, sB = 0;
+  if (t.simple) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      if (u < t.nslots) {
+        const uint4 d = lds128(sb_cur + (uint32_t)(u * THREADS * 16));
+        sT = __dp4a(d.x, t.cT[0], __dp4a(d.y, t.cT[1], __dp4a(d.z, t.cT[2], __dp4a(d.w, t.cT[3], sT))));
+        sG = __dp4a(d.x, t.cG[0], __dp4a(d.y, t.cG[1], __dp4a(d.z, t.cG[2], __dp4a(d.w, t.cG[3], sG))));
+        if (WANT_SUMS)
+          sB = __dp4a(d.x, t.cB[0], __dp4a(d.y, t.cB[1], __dp4a(d.z, t.cB[2], __dp4a(d.w, t.cB[3], sB))));
+      }
+    }
+  } else {
+    // a tile larger than one stage: round by round through this stage's slots (waits for everything in flight)
+    const uintptr_t base = t.p0;
+    const int off = (int)(base & 15);
+    const int vpr = (off + t.row_bytes + 15) >> 4;
+    int rps, r0, v0;
+    if (vpr >= THREADS) { rps = 1; r0 = 0; v0 = gt; }
+    else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
+    const long long step = (long long)rps * a.row_stride;
+    for (int v = v0; v < vpr; v += THREADS) {
+      const int rel = 16 * v - off;
+      const int lo = rel < 0 ? -rel : 0;
+      const int e = t.row_bytes - rel;
+      const int hi = e < 16 ? e : 16;
+      const int ph = (rel + 15) % 3;
+      uint32_t cT[4], cG[4], cB[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = byte_mask(lo - 4 * j, hi - 4 * j);
+        cT[j] = m & 0x01010101u;
+        cG[j] = m & sel_word((ph + 2) % 3, j);
+        cB[j] = m & sel_word(ph, j);
+      }
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(base - off) + (long long)r0 * a.row_stride + 16 * v;
+      for (int r = r0; r < t.nrows; r += rps * K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u)
+          if (r + u * rps < t.nrows) cp_async16_64B(sb_cur + (uint32_t)(u * THREADS * 16), p + u * step, pol);
+        cp_async_commit();
+        cp_async_wait_group<0>();
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+          if (r + u * rps < t.nrows) {
+            const uint4 d = lds128(sb_cur + (uint32_t)(u * THREADS * 16));
+            sT = __dp4a(d.x, cT[0], __dp4a(d.y, cT[1], __dp4a(d.z, cT[2], __dp4a(d.w, cT[3], sT))));
+            sG = __dp4a(d.x, cG[0], __dp4a(d.y, cG[1], __dp4a(d.z, cG[2], __dp4a(d.w, cG[3], sG))));
+            if (WANT_SUMS)
+              sB = __dp4a(d.x, cB[0], __dp4a(d.y, cB[1], __dp4a(d.z, cB[2], __dp4a(d.w, cB[3], sB))));
+          }
+        }
+        p += K * step;
+      }
+    }
+  }
+  const unsigned long long N = (unsigned long long)(t.nrows > 0 ? t.nrows : 0) * (unsigned long long)(t.ncols > 0 ? t.ncols : 0);
+  unsigned long long tG, tT, tB = 0;
+  if (N < 5600000ull) {
+    tG = warp_sum<uint32_t>(sG); tT = warp_sum<uint32_t>(sT);
+    if (WANT_SUMS) tB = warp_sum<uint32_t>(sB);
+  } else {
+    tG = warp_sum_u64(sG); tT = warp_sum_u64(sT);
+    if (WANT_SUMS) tB = warp_sum_u64(sB);
+  }
+  if (lane == 0) { part[CUR][wid][0] = tG; part[CUR][wid][1] = tT; part[CUR][wid][2] = tB; }
+  if (gt == 0) s_claim[CUR] = have_next ? (long long)claim : a.num_rois;   // everyone holds t.roi in registers by now
+  __syncthreads();
+  if (gt == 0) {
+    tG = tT = tB = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { tG += part[CUR][w][0]; tT += part[CUR][w][1]; tB += part[CUR][w][2]; }
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tT - tG - tB; o.w = N;
+      *reinterpret_cast<ulonglong4*>(a.out_sums + 4 * t.roi) = o;
+    }
+    double val;
+    if (!t.has_box || N == 0) val = nan_f64();
+    else if (a.mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(3 * (long long)tG - (long long)tT + 2 * (long long)N) / (double)(4 * N);
+    a.out_value[t.roi] = val;
+  }
+  return have_next;
+}
+
+template <int THREADS, int K, bool WANT_SUMS>
+__global__ void __launch_bounds__(THREADS, 4) roi_pipelined_kernel(const RoiArgs a, unsigned int* __restrict__ work) {
+  extern __shared__ __align__(128) uint8_t stage[];
+  __shared__ long long s_claim[2];
+  __shared__ unsigned long long part[2][THREADS / 32][3];
+  const int gt = threadIdx.x;
+  const unsigned long long pol = l2_evict_first_policy();
+  const uint32_t slot0 = smem_u32(stage) + 16u * (uint32_t)gt;
+  if (gt == 0) {
+    s_claim[0] = (long long)atomicAdd(work, 1u);
+    s_claim[1] = (long long)atomicAdd(work, 1u);
+  }
+  __syncthreads();
+  PTile T0, T1;
+  if (s_claim[0] < a.num_rois) {
+    ptile_setup<THREADS, K>(T0, a, s_claim[0], gt);
+#pragma unroll
+    for (int u = 0; u < K; ++u)
+      if (u < T0.nslots) cp_async16_64B(slot0 + (uint32_t)(u * THREADS * 16), reinterpret_cast<const void*>(T0.p0 + u * T0.step), pol);
+    cp_async_commit();
+    for (;;) {
+      if (!roi_pipeline_turn<THREADS, K, WANT_SUMS, 0>(a, T0, T1, work, s_claim, part, slot0, pol)) break;
+      if (!roi_pipeline_turn<THREADS, K, WANT_SUMS, 1>(a, T1, T0, work, s_claim, part, slot0, pol)) break;
+    }
+  }
+  if (gt == 0) {
+    __threadfence();
+    if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0u; work[1] = 0u; __threadfence(); }   // last CTA out: ready for the next launch
+  }
+}
+
+// work counters of the persistent kernel: a small ring so that launches in flight on different streams never share one
+constexpr int ROI_WORK_SLOTS = 64;
+__device__ unsigned int g_roi_work[ROI_WORK_SLOTS][2];
+
+template <int THREADS, int K>
+static int launch_pipelined(const RoiArgs& a, cudaStream_t st) {
+  static unsigned next_slot = 0;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  unsigned int* work = nullptr;
+  cudaError_t e = cudaGetSymbolAddress((void**)&work, g_roi_work);
+  if (e != cudaSuccess) { set_error("bpv_roi_sample_u8: cudaGetSymbolAddress: %s", cudaGetErrorString(e)); return (int)e; }
+  work += 2 * (next_slot++ % ROI_WORK_SLOTS);
+  const int smem = 2 * THREADS * K * 16;
+  auto k1 = roi_pipelined_kernel<THREADS, K, true>;
+  auto k0 = roi_pipelined_kernel<THREADS, K, false>;
+  (void)ensure_dyn_smem((const void*)k1, smem, true);
+  (void)ensure_dyn_smem((const void*)k0, smem, true);
+  long long grid = (long long)sms * 4;
+  if (grid > a.num_rois) grid = a.num_rois;
+  if (a.out_sums) k1<<<(unsigned)grid, THREADS, smem, st>>>(a, work);
+  else k0<<<(unsigned)grid, THREADS, smem, st>>>(a, work);
+  return 0;
+}
+
 template <int THREADS, int K, int STAGE>
 static void launch_staged(const RoiArgs& a, int stage_bytes, cudaStream_t st) {
   const int smem = STAGE == 1 ? THREADS * K * 16 : stage_bytes;
@@ -765,6 +999,12 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
   return check_launch("bpv_roi_sample_resized_u8");
 }
 
+// BPV_ROI_PIPELINED=0/1 selects the one-ROI-per-CTA staged kernel or the persistent double-buffered one (default below)
+static bool roi_pipelined_enabled() {
+  const char* v = getenv("BPV_ROI_PIPELINED");
+  return v ? v[0] == '1' : false;
+}
+
 extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
                                  int64_t frame_stride_bytes, int64_t row_stride_bytes,
                                  int32_t H, int32_t W, int64_t num_frames,
@@ -807,6 +1047,7 @@ extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* fr
       else launch_rows<128, 2>(a, (unsigned)((n + 1) / 2), st);
     }
     else if (g == 32) launch_rows<32, 5>(a, grid, st);
+    else if (roi_pipelined_enabled()) { if (int rc = launch_pipelined<128, 12>(a, st)) return rc; }
     else launch_staged<128, 12, 1>(a, 0, st);
   } else {                           // generic path: alignment changes row by row
     if (g == 32) roi_sample_kernel<32, 4><<<grid, 256, 0, st>>>(a);

@@ -1015,7 +1015,11 @@ extern "C" int bpv_window_filter(const double* ring_t, const double* ring_y, con
   const PreLayout L = pre_layout(*p);
   cudaStream_t st = (cudaStream_t)stream;
 #define BPV_PRE(feat, minb, dual) return launch_preprocess<feat, minb, dual>(ring_t, ring_y, *p, L, dr, proc_x, proc_y, status, st)
-  const bool single_sos = getenv("BPV_SOS_SINGLE") != nullptr;     // development / test switch: one signal per warp everywhere
+  // Two signals per warp pay off while enough warps stay resident to hide the stages that run for one signal after the
+  // other (the spline's serial Thomas sweep above all): with the 46 KB per signal of a 1200-sample cubic + Butterworth
+  // window only two such warps fit an SM and the pair is slower than two single-signal warps (measured on config 4:
+  // 3.57 ms against 2.86 ms per step), so large plans keep one signal per warp.  BPV_SOS_SINGLE = test switch.
+  const bool single_sos = getenv("BPV_SOS_SINGLE") != nullptr || (227 * 1024) / (2 * L.total + 1024) < 8;
   if (!interp && !butter && !fir) BPV_PRE(0, 6, false);
   if (!interp && !butter) BPV_PRE(F_FIR, 5, false);
   if (single_sos) {

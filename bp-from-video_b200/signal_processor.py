@@ -238,7 +238,8 @@ class SignalProcessor:
         if (status == 2).any():
             raise ValueError('`x` must be strictly increasing sequence.')       # scipy CubicSpline, via INTERP_CUBIC
         if (status == 3).any():
-            raise ValueError('filter band edges are invalid for this sampling rate (scipy.signal raises here)')
+            raise ValueError('filter band edges are invalid for this sampling rate (scipy.signal raises here), or the '
+                             'least-squares FIR system is too ill-conditioned for the Toeplitz solver (scipy falls back to lstsq)')
 
     # ------------------------------------------------------------------------------------------
     # the reference's method surface

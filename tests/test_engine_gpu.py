@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 # model fits <= 3 points exactly (p == 1 at every bin) and the 3-5 xcorr lags are near-tied, so the argmax is
 # decided by the last bits of scipy's summation order.  Values are still compared (with residue-level atol);
 # bit-exact peak bins / lags are required from MIN_N samples on.
-MIN_N = 4
+MIN_N = 4      # evidence: tests/test_degenerate_windows_cpu.py (the reference flips its own argmax under a 1-ulp input change below 4 samples, never from 4 on)
 # ... and a processed window whose amplitude is below RESIDUE x the raw level is rounding noise of the
 # filter (e.g. order-16 Butterworth at 120 fps on < ~20 samples: output ~1e-22 for an input of 140).
 RESIDUE = 1e-9

@@ -3,7 +3,7 @@
 # Usage: tools/gpu_round.sh <tag> [full]
 tag=${1:-r2a}; full=${2:-}
 mkdir -p gpurun_out
-KF='regex:roi_|ring_push|firls|butter|window_preprocess|spectrum_dense|welch|xcorr|ls_coarse|ls_peak|running_mean|calc_rois|pack_records|dft_'
+KF='regex:roi_|ring_push|firls|butter|window_preprocess|spectrum_dense|welch|xcorr|ls_coarse|ls_peak|running_mean|calc_rois|pack_records|dft_|design_probe|miss_'
 python -m pytest tests -m gpu -q --maxfail=25 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -30 gpurun_out/${tag}_pytest.log | cut -c1-220
 python bench.py --steps 100 --warmup 5 > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
