@@ -771,9 +771,17 @@ static inline bool launch_variant(const RoiArgs&, unsigned, cudaStream_t) { retu
 // the BGR frame the reference would have sampled, bit for bit.
 // One 128-thread CTA per ROI, threads laid out rows x 16-pixel vector columns as in the BGR kernels.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sat_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+__device__ __forceinline__ int sat_u8(int v) {
+  int r;
+  asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));           // one instruction instead of a min / max pair
+  return r;
+}
 
-template <bool WANT_SUMS>
+// VEC: the frame base and the pitch are 16-byte aligned, so the 16 Y bytes and the 16 UV bytes (8 chroma pairs) of a
+// 16-pixel group are ONE 128-bit load each (the byte-load version issued 32 loads per group); ALL = false (GREEN without
+// sums): only the green channel is converted.  Thread layout as the BGR kernels: rows x 16-pixel vector columns, so a
+// thread's column — and with it the mask of its pixels that lie inside [xs, xe) — is loop invariant.
+template <bool WANT_SUMS, bool VEC, bool ALL>
 __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch,
                                                        int H, int W, int R, int mode, long long num_rois,
                                                        const int32_t* __restrict__ boxes,
@@ -798,27 +806,50 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
     else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
     for (int v = v0; v < vpr; v += THREADS) {
       const int xv = x0 + 16 * v;
+      unsigned inm = 0;                                       // pixels of the group inside [xs, xe)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) inm |= (xv + e >= xs && xv + e < xe) ? 1u << e : 0u;
       for (int r = r0; r < nrows; r += rps) {
         const int y = ys + r;
         const uint8_t* yrow = yp + (long long)y * pitch + xv;
         const uint8_t* uvrow = uvp + (long long)(y >> 1) * pitch + xv;
+        uint32_t yw[4], cw[4];
+        if (VEC) {
+          // whole aligned vectors: bytes beyond the row's last pixel lie inside the pitch (pitch % 16 == 0)
+          const uint4 a4 = ld_stream_v4(yrow), c4 = ld_stream_v4(uvrow);
+          yw[0] = a4.x; yw[1] = a4.y; yw[2] = a4.z; yw[3] = a4.w;
+          cw[0] = c4.x; cw[1] = c4.y; cw[2] = c4.z; cw[3] = c4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            yw[j] = cw[j] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 4 * j + k;
+              if (inm >> e & 1) yw[j] |= (uint32_t)yrow[e] << (8 * k);
+              if (inm >> (e & ~1) & 3) cw[j] |= (uint32_t)uvrow[e] << (8 * k);   // a pair's U and V when either pixel is in range
+            }
+          }
+        }
 #pragma unroll
         for (int pr = 0; pr < 8; ++pr) {
-          const int x = xv + 2 * pr;
-          if (x + 1 < xs || x >= xe) continue;
-          const int uu = (int)uvrow[2 * pr] - 128, vv = (int)uvrow[2 * pr + 1] - 128;
-          const int ruv = (1 << 19) + 1673527 * vv;
+          if (!(inm >> (2 * pr) & 3u)) continue;
+          const uint32_t c2 = cw[pr >> 1] >> (16 * (pr & 1));
+          const int uu = (int)(c2 & 0xffu) - 128, vv = (int)(c2 >> 8 & 0xffu) - 128;
           const int guv = (1 << 19) - 852492 * vv - 409993 * uu;
+          const int ruv = (1 << 19) + 1673527 * vv;
           const int buv = (1 << 19) + 2116026 * uu;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int xx = x + e;
-            if (xx < xs || xx >= xe) continue;
-            const int yy = (int)yrow[2 * pr + e] - 16;
+            const int px = 2 * pr + e;
+            if (!(inm >> px & 1u)) continue;
+            const int yy = (int)(yw[px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;
             const int yc = (yy > 0 ? yy : 0) * 1220542;
-            sR += (uint32_t)sat_u8((yc + ruv) >> 20);
             sG += (uint32_t)sat_u8((yc + guv) >> 20);
-            sB += (uint32_t)sat_u8((yc + buv) >> 20);
+            if (ALL) {
+              sR += (uint32_t)sat_u8((yc + ruv) >> 20);
+              sB += (uint32_t)sat_u8((yc + buv) >> 20);
+            }
           }
         }
       }
@@ -876,7 +907,36 @@ __device__ __forceinline__ ResizeTap resize_tap(int d, double scale, int sn, boo
   return t;
 }
 
-template <bool WANT_SUMS>
+// 6 consecutive bytes (two BGR pixels) starting at byte `off` of a 4-byte aligned row, as (pixel 0, pixel 1) packed
+// B | G << 8 | R << 16: two or three aligned 32-bit loads and funnel shifts instead of six byte loads.  `limit` = bytes
+// that may be read from `row` (whole words are read around the pixels): the tail of a frame's last row takes byte loads.
+__device__ __forceinline__ void load_two_pixels(const uint8_t* __restrict__ row, int off, int limit, uint32_t& p0, uint32_t& p1) {
+  if ((off & ~3) + 12 > limit) {
+    p0 = row[off] | row[off + 1] << 8 | row[off + 2] << 16;
+    p1 = row[off + 3] | row[off + 4] << 8 | row[off + 5] << 16;
+    return;
+  }
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (off & ~3));
+  const int sh = 8 * (off & 3);
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t lo = __funnelshift_r(w0, w1, sh);                 // bytes off .. off+3
+  uint32_t hi = w1 >> sh;                                          // bytes off+4 .. (off+7 needs the next word)
+  if ((off & 3) == 3) hi = __funnelshift_r(w1, __ldg(w + 2), sh);
+  p0 = lo & 0xffffffu;
+  p1 = (lo >> 24 | hi << 8) & 0xffffffu;
+}
+__device__ __forceinline__ uint32_t load_pixel(const uint8_t* __restrict__ row, int off, int limit) {
+  if ((off & ~3) + 8 > limit) return row[off] | row[off + 1] << 8 | row[off + 2] << 16;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (off & ~3));
+  const int sh = 8 * (off & 3);
+  uint32_t v = __ldg(w) >> sh;
+  if ((off & 3) > 1) v = __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
+  return v & 0xffffffu;
+}
+
+// WORDS: frame base and strides are 4-byte aligned, so the two source pixels of a horizontal tap pair come from aligned
+// 32-bit loads (load_two_pixels) instead of six byte loads per row.
+template <bool WANT_SUMS, bool WORDS>
 __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                           int sh, int sw, int dh, int dw, int R, int mode, long long num_rois,
                                                           const int32_t* __restrict__ boxes,
@@ -902,28 +962,55 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
       for (int r = gt; r < nrows; r += THREADS) rtap[r] = resize_tap(ys + r, scale_y, sh, false);
     }
     __syncthreads();
-    const long long npix = (long long)nrows * ncols;
-    for (long long i = gt; i < npix; i += THREADS) {
-      const int r = (int)(i / ncols), c = (int)(i - (long long)r * ncols);
-      int px[3];
-      if (area2) {
-        const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride + 6LL * (xs + c);
-        const uint8_t* p1 = p0 + row_stride;
+    // threads laid out rows x columns (no per-pixel division): a thread keeps its column taps in registers
+    int rps, r0, c0;
+    if (ncols >= THREADS) { rps = 1; r0 = 0; c0 = gt; }
+    else { rps = THREADS / ncols; r0 = gt / ncols; c0 = gt - r0 * ncols; if (r0 >= rps) c0 = ncols; }
+    for (int c = c0; c < ncols; c += THREADS) {
+      ResizeTap tc;
+      if (!area2) tc = ctap[c];
+      for (int r = r0; r < nrows; r += rps) {
+        int px[3];
+        if (area2) {
+          const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride;
+          const uint8_t* p1 = p0 + row_stride;
+          const int off = 6 * (xs + c);
+          uint32_t a0, a1, b0, b1;
+          const int lim1 = 2 * (ys + r) + 1 == sh - 1 ? 3 * sw : 0x7fffffff;       // a frame's last row must not be overrun
+          if (WORDS) { load_two_pixels(p0, off, 0x7fffffff, a0, a1); load_two_pixels(p1, off, lim1, b0, b1); }
+          else {
+            a0 = p0[off] | p0[off + 1] << 8 | p0[off + 2] << 16; a1 = p0[off + 3] | p0[off + 4] << 8 | p0[off + 5] << 16;
+            b0 = p1[off] | p1[off + 1] << 8 | p1[off + 2] << 16; b1 = p1[off + 3] | p1[off + 4] << 8 | p1[off + 5] << 16;
+          }
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) px[ch] = ((int)p0[ch] + (int)p0[3 + ch] + (int)p1[ch] + (int)p1[3 + ch] + 2) >> 2;
-      } else {
-        const ResizeTap tc = ctap[c], tr = rtap[r];
-        const uint8_t* r0 = fp + (long long)tr.i0 * row_stride;
-        const uint8_t* r1 = fp + (long long)tr.i1 * row_stride;
+          for (int ch = 0; ch < 3; ++ch)
+            px[ch] = ((int)(a0 >> (8 * ch) & 255) + (int)(a1 >> (8 * ch) & 255) + (int)(b0 >> (8 * ch) & 255) + (int)(b1 >> (8 * ch) & 255) + 2) >> 2;
+        } else {
+          const ResizeTap tr = rtap[r];
+          const uint8_t* q0 = fp + (long long)tr.i0 * row_stride;
+          const uint8_t* q1 = fp + (long long)tr.i1 * row_stride;
+          uint32_t a0, a1, b0, b1;             // (row 0 | row 1) x (column tap 0 | 1)
+          if (WORDS) {
+            const int l0 = tr.i0 == sh - 1 ? 3 * sw : 0x7fffffff, l1 = tr.i1 == sh - 1 ? 3 * sw : 0x7fffffff;
+            if (tc.i1 == tc.i0 + 1) { load_two_pixels(q0, 3 * tc.i0, l0, a0, a1); load_two_pixels(q1, 3 * tc.i0, l1, b0, b1); }
+            else {
+              a0 = load_pixel(q0, 3 * tc.i0, l0); a1 = load_pixel(q0, 3 * tc.i1, l0);
+              b0 = load_pixel(q1, 3 * tc.i0, l1); b1 = load_pixel(q1, 3 * tc.i1, l1);
+            }
+          } else {
+            a0 = q0[3 * tc.i0] | q0[3 * tc.i0 + 1] << 8 | q0[3 * tc.i0 + 2] << 16; a1 = q0[3 * tc.i1] | q0[3 * tc.i1 + 1] << 8 | q0[3 * tc.i1 + 2] << 16;
+            b0 = q1[3 * tc.i0] | q1[3 * tc.i0 + 1] << 8 | q1[3 * tc.i0 + 2] << 16; b1 = q1[3 * tc.i1] | q1[3 * tc.i1 + 1] << 8 | q1[3 * tc.i1 + 2] << 16;
+          }
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const int h0 = (int)r0[3 * tc.i0 + ch] * tc.w0 + (int)r0[3 * tc.i1 + ch] * tc.w1;
-          const int h1 = (int)r1[3 * tc.i0 + ch] * tc.w0 + (int)r1[3 * tc.i1 + ch] * tc.w1;
-          const int v = (((tr.w0 * (h0 >> 4)) >> 16) + ((tr.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
-          px[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
+          for (int ch = 0; ch < 3; ++ch) {
+            const int h0 = (int)(a0 >> (8 * ch) & 255) * tc.w0 + (int)(a1 >> (8 * ch) & 255) * tc.w1;
+            const int h1 = (int)(b0 >> (8 * ch) & 255) * tc.w0 + (int)(b1 >> (8 * ch) & 255) * tc.w1;
+            const int v = (((tr.w0 * (h0 >> 4)) >> 16) + ((tr.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            px[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
+          }
         }
+        sB += (uint32_t)px[0]; sG += (uint32_t)px[1]; sR += (uint32_t)px[2];
       }
-      sB += (uint32_t)px[0]; sG += (uint32_t)px[1]; sR += (uint32_t)px[2];
     }
   }
   const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(ncols > 0 ? ncols : 0);
@@ -966,9 +1053,15 @@ extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_b
   if (num_frames == 0) return 0;
   const long long n = num_frames * R;
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_sums) roi_nv12_kernel<true><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes,
-                                                                   (unsigned long long*)out_sums, out_value);
-  else roi_nv12_kernel<false><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, nullptr, out_value);
+  // 128-bit loads need aligned rows; the Y plane of frame f starts at f * frame_stride and the UV plane H * pitch later
+  const bool vec = (((uintptr_t)frames | (uintptr_t)frame_stride_bytes | (uintptr_t)pitch_bytes) & 15) == 0;
+  const bool all = mode != BPV_GREEN;
+#define BPV_NV12(S, V, A) roi_nv12_kernel<S, V, A><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, \
+                                                                              (unsigned long long*)out_sums, out_value)
+  if (out_sums) { if (vec) BPV_NV12(true, true, true); else BPV_NV12(true, false, true); }
+  else if (all) { if (vec) BPV_NV12(false, true, true); else BPV_NV12(false, false, true); }
+  else { if (vec) BPV_NV12(false, true, false); else BPV_NV12(false, false, false); }
+#undef BPV_NV12
   return check_launch("bpv_roi_sample_nv12");
 }
 
@@ -989,13 +1082,18 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
   if (num_frames == 0) return 0;
   const long long n = num_frames * R;
   const int smem = (dst_h + dst_w) * (int)sizeof(ResizeTap);        // worst case: a ROI spanning the whole resized frame
-  if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<true>, smem)) return rc;
-  if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<false>, smem)) return rc;
+  // aligned 32-bit loads read whole words around a pixel pair: rows must start word aligned
+  const bool words = (((uintptr_t)frames | (uintptr_t)frame_stride_bytes | (uintptr_t)row_stride_bytes) & 3) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_sums) roi_resized_kernel<true><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, dst_w,
-                                                                      R, mode, n, boxes, (unsigned long long*)out_sums, out_value);
-  else roi_resized_kernel<false><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, dst_w,
-                                                                 R, mode, n, boxes, nullptr, out_value);
+#define BPV_RSZ(S, Wd)                                                                                                         \
+  do {                                                                                                                         \
+    if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<S, Wd>, smem)) return rc;                                      \
+    roi_resized_kernel<S, Wd><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, \
+                                                              dst_w, R, mode, n, boxes, (unsigned long long*)out_sums, out_value); \
+  } while (0)
+  if (out_sums) { if (words) BPV_RSZ(true, true); else BPV_RSZ(true, false); }
+  else { if (words) BPV_RSZ(false, true); else BPV_RSZ(false, false); }
+#undef BPV_RSZ
   return check_launch("bpv_roi_sample_resized_u8");
 }
 

@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'bp-from-video_b200'))
 from bpv import ops, synth  # noqa: E402
 
-N, H, W = 2048, 1080, 1920
+N, H, W = int(os.environ.get('INGEST_FRAMES', 8192)), 1080, 1920      # 8192 frames: 51 GB of BGR / 25 GB of NV12 in HBM, far beyond L2
+PEAK = 6466.5                                                           # measured copy bandwidth (MEASURED_PEAKS.json), GB/s
 rng = np.random.default_rng(0)
 boxes_np = synth.roi_boxes(rng, N, H, W)
 boxes = torch.from_numpy(boxes_np).cuda()
@@ -39,10 +40,13 @@ bgr = torch.empty((N, H, W, 3), dtype=torch.uint8, device='cuda')
 for i in range(0, N, 64):
     bgr[i:i + 64].random_(0, 256)
 t = timeit(lambda: ops.roi_sample(bgr, boxes, 1, roi_pixels_hint=5800))
-print(f'BGR      {N} frames: {t*1e3:8.1f} us  {3*px/t/1e6:8.1f} GB/s of ROI bytes  {N/t*1e3/1e6:6.2f} M frames/s')
+t_bgr = t
+print(f'BGR      {N} frames: {t*1e3:8.1f} us  {3*px/t/1e6:8.1f} GB/s of ROI bytes = {3*px/t/1e6/PEAK:.3f} of the copy peak  {N/t*1e3/1e6:6.2f} M frames/s')
 nv = torch.empty((N, H * 3 // 2, W), dtype=torch.uint8, device='cuda').random_(0, 256)
 t = timeit(lambda: ops.roi_sample_nv12(nv, H, W, boxes, 1))
-print(f'NV12     {N} frames: {t*1e3:8.1f} us  {1.5*px/t/1e6:8.1f} GB/s of ROI bytes  {N/t*1e3/1e6:6.2f} M frames/s')
+print(f'NV12     {N} frames: {t*1e3:8.1f} us  {1.5*px/t/1e6:8.1f} GB/s of ROI bytes (1.5 B/px) = {1.5*px/t/1e6/PEAK:.3f} of the copy peak  {N/t*1e3/1e6:6.2f} M frames/s  = {t/t_bgr:.2f} x the BGR kernel per frame')
+t = timeit(lambda: ops.roi_sample_nv12(nv, H, W, boxes, 0))
+print(f'NV12 GREEN {N} frames: {t*1e3:8.1f} us  = {t/t_bgr:.2f} x the BGR kernel per frame')
 del nv
 # VideoReader target_res: 1080p source sampled as if resized to 720p; boxes scaled to the 720p frame
 dh, dw = 720, 1280
@@ -51,4 +55,4 @@ ok = b720[..., 0] != synth.NO_BOX
 b720[ok] = np.rint(b720[ok] * (dw / W)).astype(np.int32)
 b720_d = torch.from_numpy(b720).cuda()
 t = timeit(lambda: ops.roi_sample_resized(bgr, dh, dw, b720_d, 1))
-print(f'resized  {N} frames (1080p -> 720p boxes): {t*1e3:8.1f} us  {N/t*1e3/1e6:6.2f} M frames/s')
+print(f'resized  {N} frames (1080p -> 720p boxes): {t*1e3:8.1f} us  {N/t*1e3/1e6:6.2f} M frames/s  = {t/t_bgr:.2f} x the BGR kernel per frame')
