@@ -785,7 +785,7 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=400, help='cpu_baseline of the GPU arm: frames per core')
     ap.add_argument('--e2e-frames', type=int, default=8, help='frames per stream per e2e step (pinned host memory)')
     ap.add_argument('--port', action='store_true', help='CPU arms: time the oracle port even if baseline/_ref exists')
-    ap.add_argument('--numa', action='store_true', help='N > 1: bind each rank to the CPUs of its GPU\'s NUMA node')
+    ap.add_argument('--bind-numa', dest='numa', action='store_true', help='N > 1: bind each rank to the CPUs of its GPU\'s NUMA node')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-other', action='store_true', help='skip the other_shapes / latency blocks')
     args = ap.parse_args()

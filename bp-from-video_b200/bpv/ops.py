@@ -27,6 +27,12 @@ def _run(dev: torch.device, name: str, *args) -> None:
         check(fn(*args, stream_handle(idx)), name)
 
 
+def _require(cond: bool, msg: str) -> None:
+    """Argument check that survives `python -O` (unlike assert)."""
+    if not cond:
+        raise ValueError(msg)
+
+
 def _dev_accessible(t: torch.Tensor) -> bool:
     return t.is_cuda or t.is_pinned()
 
@@ -36,11 +42,11 @@ def roi_sample(frames: torch.Tensor, boxes: torch.Tensor, mode: int, *, want_sum
     """F1.  frames uint8 [N,H,W,3] (CUDA, or pinned host memory for the zero-copy path; rows may be
     strided), boxes int32 [N,R,4] (CUDA).  Returns (value f64 [N,R], sums u64-as-int64 [N,R,4] | None).
     Reference: signal_processor.py:176-193."""
-    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3
-    assert _dev_accessible(frames), 'frames must live in CUDA or pinned host memory'
-    assert frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR'
+    _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3, 'bad argument: ' + 'frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3')
+    _require(_dev_accessible(frames), 'frames must live in CUDA or pinned host memory')
+    _require(frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR')
     N, H, W, _ = frames.shape
-    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4
+    _require(boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4, 'bad argument: ' + 'boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4')
     R = boxes.shape[1]
     dev = boxes.device
     if out_value is None:
@@ -85,7 +91,7 @@ def running_mean(ring, g0: int, values, scale: float):
     (sg_bpm / sg_ptt + get_means, signal_processor.py:310, 312; signal_data.py:60-63)."""
     S, C_, H = ring.shape
     T = values.shape[1]
-    assert values.shape == (S, T, C_) and values.is_contiguous()
+    _require(values.shape == (S, T, C_) and values.is_contiguous(), 'bad argument: ' + 'values.shape == (S, T, C_) and values.is_contiguous()')
     mean = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
     mean_int = torch.empty((S, T, C_), dtype=torch.float64, device=ring.device)
     _run(ring.device, 'bpv_running_mean', ptr(ring), S, C_, H, int(g0), T, ptr(values), float(scale), ptr(mean), ptr(mean_int))
@@ -255,7 +261,7 @@ def firls_design(fs: torch.Tensor, p: WindowParams):
 def view_boxes(boxes: torch.Tensor, view_w: int, view_h: int, left: int = 0, flip_horizontally: bool = False, out=None):
     """Map boxes int32 [..., 4] expressed in the VideoReader view (portrait crop frame[:, left:left+view_w], optional
     horizontal flip; video_reader.py:97-103) onto the decoded frame.  No pixel is copied."""
-    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[-1] == 4
+    _require(boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[-1] == 4, 'bad argument: ' + 'boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[-1] == 4')
     out = torch.empty_like(boxes) if out is None else out
     _run(boxes.device, 'bpv_view_boxes', ptr(boxes), boxes.numel() // 4, int(view_w), int(view_h), int(left), int(bool(flip_horizontally)),
                                ptr(out))
@@ -294,7 +300,7 @@ def unpack_records32(rec: torch.Tensor, R: int, P: int):
 def dft256_tc(z: torch.Tensor) -> torch.Tensor:
     """256-point DFT of real segments z f32 [rows, 256] on the tensor cores (tcgen05, 3xTF32): returns f32 [rows, 256] with
     [:, :129] = Re X[0..128] and [:, 129:] = -Im X[1..127]."""
-    assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2 and z.shape[1] == 256
+    _require(z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2 and z.shape[1] == 256, 'bad argument: ' + 'z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 2 and z.shape[1] == 256')
     d = torch.empty_like(z)
     _run(z.device, 'bpv_dft256_tc', ptr(z), z.shape[0], ptr(d))
     return d
@@ -304,10 +310,10 @@ def roi_sample_nv12(frames: torch.Tensor, H: int, W: int, boxes: torch.Tensor, m
     """F1 on NV12 frames: frames uint8 [N, 3H/2, pitch] (Y plane rows then interleaved UV rows; CUDA or pinned host
     memory), boxes int32 [N, R, 4] in pixel coordinates of the H x W image.  Returns (value f64 [N,R], sums | None): the
     sums of the BGR frame cv2.cvtColor(nv12, COLOR_YUV2BGR_NV12) would give."""
-    assert frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[1] == H * 3 // 2 and frames.stride(2) == 1
-    assert _dev_accessible(frames) and boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous()
+    _require(frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[1] == H * 3 // 2 and frames.stride(2) == 1, 'bad argument: ' + 'frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[1] == H * 3 // 2 and frames.stride(2) == 1')
+    _require(_dev_accessible(frames) and boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous(), 'bad argument: ' + '_dev_accessible(frames) and boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous()')
     N, R = boxes.shape[0], boxes.shape[1]
-    assert frames.shape[0] == N
+    _require(frames.shape[0] == N, 'bad argument: ' + 'frames.shape[0] == N')
     out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None
     fstride = frames.stride(0) if N > 1 else frames.shape[1] * frames.stride(1)
@@ -320,10 +326,10 @@ def roi_sample_resized(frames: torch.Tensor, dst_h: int, dst_w: int, boxes: torc
     """F1 on frames the reference would first have resized with cv2.resize(frame, (dst_w, dst_h)) (video_reader.py:95-96):
     frames uint8 [N, H, W, 3] source frames, boxes int32 [N, R, 4] in the RESIZED frame.  Bit-exact with sampling
     cv2.resize's output; the resized frame is never materialised."""
-    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and _dev_accessible(frames)
-    assert frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR'
+    _require(frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and _dev_accessible(frames), 'bad argument: ' + 'frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and _dev_accessible(frames)')
+    _require(frames.stride(3) == 1 and frames.stride(2) == 3, 'pixels must be packed BGR')
     N, H, W, _ = frames.shape
-    assert boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4
+    _require(boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4, 'bad argument: ' + 'boxes.is_cuda and boxes.dtype == torch.int32 and boxes.is_contiguous() and boxes.shape[0] == N and boxes.shape[2] == 4')
     R = boxes.shape[1]
     out_value = torch.empty((N, R), dtype=torch.float64, device=boxes.device)
     sums = torch.empty((N, R, 4), dtype=torch.int64, device=boxes.device) if want_sums else None

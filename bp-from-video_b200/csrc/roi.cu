@@ -801,6 +801,9 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
   if (nrows > 0 && ncols > 0) {
     const int x0 = xs & ~15;                                  // 16-pixel aligned vector columns (x0 even: UV pairs intact)
     const int vpr = (xe - x0 + 15) >> 4;
+    // the row unit is a CHROMA row: the two luma rows 2c and 2c + 1 share its UV samples, so their chroma terms are
+    // computed once and the two Y vectors are independent loads in flight together
+    const int c_lo = ys >> 1, c_hi = (ye - 1) >> 1, ncr = c_hi - c_lo + 1;
     int rps, r0, v0;
     if (vpr >= THREADS) { rps = 1; r0 = 0; v0 = gt; }
     else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
@@ -809,24 +812,32 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
       unsigned inm = 0;                                       // pixels of the group inside [xs, xe)
 #pragma unroll
       for (int e = 0; e < 16; ++e) inm |= (xv + e >= xs && xv + e < xe) ? 1u << e : 0u;
-      for (int r = r0; r < nrows; r += rps) {
-        const int y = ys + r;
-        const uint8_t* yrow = yp + (long long)y * pitch + xv;
-        const uint8_t* uvrow = uvp + (long long)(y >> 1) * pitch + xv;
-        uint32_t yw[4], cw[4];
+      for (int r = r0; r < ncr; r += rps) {
+        const int cy = c_lo + r;
+        const bool row_on[2] = {2 * cy >= ys, 2 * cy + 1 < ye};
+        const uint8_t* yrow = yp + (long long)(2 * cy) * pitch + xv;
+        const uint8_t* uvrow = uvp + (long long)cy * pitch + xv;
+        uint32_t yw[2][4], cw[4];
         if (VEC) {
           // whole aligned vectors: bytes beyond the row's last pixel lie inside the pitch (pitch % 16 == 0)
-          const uint4 a4 = ld_stream_v4(yrow), c4 = ld_stream_v4(uvrow);
-          yw[0] = a4.x; yw[1] = a4.y; yw[2] = a4.z; yw[3] = a4.w;
+          const uint4 c4 = ld_stream_v4(uvrow);
+          uint4 a4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+          if (row_on[0]) a4 = ld_stream_v4(yrow);
+          if (row_on[1]) b4 = ld_stream_v4(yrow + pitch);
+          yw[0][0] = a4.x; yw[0][1] = a4.y; yw[0][2] = a4.z; yw[0][3] = a4.w;
+          yw[1][0] = b4.x; yw[1][1] = b4.y; yw[1][2] = b4.z; yw[1][3] = b4.w;
           cw[0] = c4.x; cw[1] = c4.y; cw[2] = c4.z; cw[3] = c4.w;
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            yw[j] = cw[j] = 0;
+            yw[0][j] = yw[1][j] = cw[j] = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int e = 4 * j + k;
-              if (inm >> e & 1) yw[j] |= (uint32_t)yrow[e] << (8 * k);
+              if (inm >> e & 1) {
+                if (row_on[0]) yw[0][j] |= (uint32_t)yrow[e] << (8 * k);
+                if (row_on[1]) yw[1][j] |= (uint32_t)yrow[pitch + e] << (8 * k);
+              }
               if (inm >> (e & ~1) & 3) cw[j] |= (uint32_t)uvrow[e] << (8 * k);   // a pair's U and V when either pixel is in range
             }
           }
@@ -840,15 +851,19 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
           const int ruv = (1 << 19) + 1673527 * vv;
           const int buv = (1 << 19) + 2116026 * uu;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int px = 2 * pr + e;
-            if (!(inm >> px & 1u)) continue;
-            const int yy = (int)(yw[px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;
-            const int yc = (yy > 0 ? yy : 0) * 1220542;
-            sG += (uint32_t)sat_u8((yc + guv) >> 20);
-            if (ALL) {
-              sR += (uint32_t)sat_u8((yc + ruv) >> 20);
-              sB += (uint32_t)sat_u8((yc + buv) >> 20);
+          for (int ro = 0; ro < 2; ++ro) {
+            if (!row_on[ro]) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int px = 2 * pr + e;
+              if (!(inm >> px & 1u)) continue;
+              const int yy = (int)(yw[ro][px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;
+              const int yc = (yy > 0 ? yy : 0) * 1220542;
+              sG += (uint32_t)sat_u8((yc + guv) >> 20);
+              if (ALL) {
+                sR += (uint32_t)sat_u8((yc + ruv) >> 20);
+                sB += (uint32_t)sat_u8((yc + buv) >> 20);
+              }
             }
           }
         }
@@ -966,50 +981,63 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
     int rps, r0, c0;
     if (ncols >= THREADS) { rps = 1; r0 = 0; c0 = gt; }
     else { rps = THREADS / ncols; r0 = gt / ncols; c0 = gt - r0 * ncols; if (r0 >= rps) c0 = ncols; }
+    constexpr int U = 4;                     // row steps per iteration: their 4 x U source loads are all in flight together
     for (int c = c0; c < ncols; c += THREADS) {
       ResizeTap tc;
       if (!area2) tc = ctap[c];
-      for (int r = r0; r < nrows; r += rps) {
-        int px[3];
-        if (area2) {
-          const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride;
-          const uint8_t* p1 = p0 + row_stride;
-          const int off = 6 * (xs + c);
-          uint32_t a0, a1, b0, b1;
-          const int lim1 = 2 * (ys + r) + 1 == sh - 1 ? 3 * sw : 0x7fffffff;       // a frame's last row must not be overrun
-          if (WORDS) { load_two_pixels(p0, off, 0x7fffffff, a0, a1); load_two_pixels(p1, off, lim1, b0, b1); }
-          else {
-            a0 = p0[off] | p0[off + 1] << 8 | p0[off + 2] << 16; a1 = p0[off + 3] | p0[off + 4] << 8 | p0[off + 5] << 16;
-            b0 = p1[off] | p1[off + 1] << 8 | p1[off + 2] << 16; b1 = p1[off + 3] | p1[off + 4] << 8 | p1[off + 5] << 16;
-          }
+      for (int rb = r0; rb < nrows; rb += rps * U) {
+        uint32_t a0[U], a1[U], b0[U], b1[U];          // (source row 0 | 1) x (column tap 0 | 1), packed B | G << 8 | R << 16
+        int wr0[U], wr1[U];
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch)
-            px[ch] = ((int)(a0 >> (8 * ch) & 255) + (int)(a1 >> (8 * ch) & 255) + (int)(b0 >> (8 * ch) & 255) + (int)(b1 >> (8 * ch) & 255) + 2) >> 2;
-        } else {
-          const ResizeTap tr = rtap[r];
-          const uint8_t* q0 = fp + (long long)tr.i0 * row_stride;
-          const uint8_t* q1 = fp + (long long)tr.i1 * row_stride;
-          uint32_t a0, a1, b0, b1;             // (row 0 | row 1) x (column tap 0 | 1)
-          if (WORDS) {
-            const int l0 = tr.i0 == sh - 1 ? 3 * sw : 0x7fffffff, l1 = tr.i1 == sh - 1 ? 3 * sw : 0x7fffffff;
-            if (tc.i1 == tc.i0 + 1) { load_two_pixels(q0, 3 * tc.i0, l0, a0, a1); load_two_pixels(q1, 3 * tc.i0, l1, b0, b1); }
+        for (int u = 0; u < U; ++u) {
+          const int r = rb + u * rps;
+          a0[u] = a1[u] = b0[u] = b1[u] = 0; wr0[u] = wr1[u] = 0;
+          if (r >= nrows) continue;
+          if (area2) {
+            const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride;
+            const uint8_t* p1 = p0 + row_stride;
+            const int off = 6 * (xs + c);
+            const int lim1 = 2 * (ys + r) + 1 == sh - 1 ? 3 * sw : 0x7fffffff;       // a frame's last row must not be overrun
+            if (WORDS) { load_two_pixels(p0, off, 0x7fffffff, a0[u], a1[u]); load_two_pixels(p1, off, lim1, b0[u], b1[u]); }
             else {
-              a0 = load_pixel(q0, 3 * tc.i0, l0); a1 = load_pixel(q0, 3 * tc.i1, l0);
-              b0 = load_pixel(q1, 3 * tc.i0, l1); b1 = load_pixel(q1, 3 * tc.i1, l1);
+              a0[u] = p0[off] | p0[off + 1] << 8 | p0[off + 2] << 16; a1[u] = p0[off + 3] | p0[off + 4] << 8 | p0[off + 5] << 16;
+              b0[u] = p1[off] | p1[off + 1] << 8 | p1[off + 2] << 16; b1[u] = p1[off + 3] | p1[off + 4] << 8 | p1[off + 5] << 16;
             }
           } else {
-            a0 = q0[3 * tc.i0] | q0[3 * tc.i0 + 1] << 8 | q0[3 * tc.i0 + 2] << 16; a1 = q0[3 * tc.i1] | q0[3 * tc.i1 + 1] << 8 | q0[3 * tc.i1 + 2] << 16;
-            b0 = q1[3 * tc.i0] | q1[3 * tc.i0 + 1] << 8 | q1[3 * tc.i0 + 2] << 16; b1 = q1[3 * tc.i1] | q1[3 * tc.i1 + 1] << 8 | q1[3 * tc.i1 + 2] << 16;
-          }
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const int h0 = (int)(a0 >> (8 * ch) & 255) * tc.w0 + (int)(a1 >> (8 * ch) & 255) * tc.w1;
-            const int h1 = (int)(b0 >> (8 * ch) & 255) * tc.w0 + (int)(b1 >> (8 * ch) & 255) * tc.w1;
-            const int v = (((tr.w0 * (h0 >> 4)) >> 16) + ((tr.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            px[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
+            const ResizeTap tr = rtap[r];
+            wr0[u] = tr.w0; wr1[u] = tr.w1;
+            const uint8_t* q0 = fp + (long long)tr.i0 * row_stride;
+            const uint8_t* q1 = fp + (long long)tr.i1 * row_stride;
+            if (WORDS) {
+              const int l0 = tr.i0 == sh - 1 ? 3 * sw : 0x7fffffff, l1 = tr.i1 == sh - 1 ? 3 * sw : 0x7fffffff;
+              if (tc.i1 == tc.i0 + 1) { load_two_pixels(q0, 3 * tc.i0, l0, a0[u], a1[u]); load_two_pixels(q1, 3 * tc.i0, l1, b0[u], b1[u]); }
+              else {
+                a0[u] = load_pixel(q0, 3 * tc.i0, l0); a1[u] = load_pixel(q0, 3 * tc.i1, l0);
+                b0[u] = load_pixel(q1, 3 * tc.i0, l1); b1[u] = load_pixel(q1, 3 * tc.i1, l1);
+              }
+            } else {
+              a0[u] = q0[3 * tc.i0] | q0[3 * tc.i0 + 1] << 8 | q0[3 * tc.i0 + 2] << 16; a1[u] = q0[3 * tc.i1] | q0[3 * tc.i1 + 1] << 8 | q0[3 * tc.i1 + 2] << 16;
+              b0[u] = q1[3 * tc.i0] | q1[3 * tc.i0 + 1] << 8 | q1[3 * tc.i0 + 2] << 16; b1[u] = q1[3 * tc.i1] | q1[3 * tc.i1 + 1] << 8 | q1[3 * tc.i1 + 2] << 16;
+            }
           }
         }
-        sB += (uint32_t)px[0]; sG += (uint32_t)px[1]; sR += (uint32_t)px[2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (rb + u * rps >= nrows) continue;
+          int px[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const int A0 = (int)(a0[u] >> (8 * ch) & 255), A1 = (int)(a1[u] >> (8 * ch) & 255);
+            const int B0 = (int)(b0[u] >> (8 * ch) & 255), B1 = (int)(b1[u] >> (8 * ch) & 255);
+            if (area2) px[ch] = (A0 + A1 + B0 + B1 + 2) >> 2;
+            else {
+              const int h0 = A0 * tc.w0 + A1 * tc.w1, h1 = B0 * tc.w0 + B1 * tc.w1;
+              const int v = (((wr0[u] * (h0 >> 4)) >> 16) + ((wr1[u] * (h1 >> 4)) >> 16) + 2) >> 2;
+              px[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
+            }
+          }
+          sB += (uint32_t)px[0]; sG += (uint32_t)px[1]; sR += (uint32_t)px[2];
+        }
       }
     }
   }
