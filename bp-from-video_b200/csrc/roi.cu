@@ -842,31 +842,43 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
             }
           }
         }
-#pragma unroll
-        for (int pr = 0; pr < 8; ++pr) {
-          if (!(inm >> (2 * pr) & 3u)) continue;
-          const uint32_t c2 = cw[pr >> 1] >> (16 * (pr & 1));
-          const int uu = (int)(c2 & 0xffu) - 128, vv = (int)(c2 >> 8 & 0xffu) - 128;
-          const int guv = (1 << 19) - 852492 * vv - 409993 * uu;
-          const int ruv = (1 << 19) + 1673527 * vv;
-          const int buv = (1 << 19) + 2116026 * uu;
-#pragma unroll
-          for (int ro = 0; ro < 2; ++ro) {
-            if (!row_on[ro]) continue;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int px = 2 * pr + e;
-              if (!(inm >> px & 1u)) continue;
-              const int yy = (int)(yw[ro][px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;
-              const int yc = (yy > 0 ? yy : 0) * 1220542;
-              sG += (uint32_t)sat_u8((yc + guv) >> 20);
-              if (ALL) {
-                sR += (uint32_t)sat_u8((yc + ruv) >> 20);
-                sB += (uint32_t)sat_u8((yc + buv) >> 20);
-              }
-            }
-          }
+        // interior vectors (all 16 pixels and both rows in range: most of a ROI) take the predicate-free body
+        const bool full = inm == 0xffffu && row_on[0] && row_on[1];
+#define BPV_NV12_BODY(PIXEL_ON, ROW_ON)                                                                     \
+        _Pragma("unroll")                                                                                   \
+        for (int pr = 0; pr < 8; ++pr) {                                                                    \
+          if (!(PIXEL_ON(2 * pr) || PIXEL_ON(2 * pr + 1))) continue;                                        \
+          const uint32_t c2 = cw[pr >> 1] >> (16 * (pr & 1));                                               \
+          const int uu = (int)(c2 & 0xffu) - 128, vv = (int)(c2 >> 8 & 0xffu) - 128;                        \
+          const int guv = (1 << 19) - 852492 * vv - 409993 * uu;                                            \
+          const int ruv = (1 << 19) + 1673527 * vv;                                                         \
+          const int buv = (1 << 19) + 2116026 * uu;                                                         \
+          _Pragma("unroll")                                                                                 \
+          for (int ro = 0; ro < 2; ++ro) {                                                                  \
+            if (!ROW_ON(ro)) continue;                                                                      \
+            _Pragma("unroll")                                                                               \
+            for (int e = 0; e < 2; ++e) {                                                                   \
+              const int px = 2 * pr + e;                                                                    \
+              if (!PIXEL_ON(px)) continue;                                                                  \
+              const int yy = (int)(yw[ro][px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;                         \
+              const int yc = (yy > 0 ? yy : 0) * 1220542;                                                   \
+              sG += (uint32_t)sat_u8((yc + guv) >> 20);                                                     \
+              if (ALL) {                                                                                    \
+                sR += (uint32_t)sat_u8((yc + ruv) >> 20);                                                   \
+                sB += (uint32_t)sat_u8((yc + buv) >> 20);                                                   \
+              }                                                                                             \
+            }                                                                                               \
+          }                                                                                                 \
         }
+#define BPV_ALWAYS(i) true
+#define BPV_PIX(i) ((inm >> (i)) & 1u)
+#define BPV_ROW(i) row_on[i]
+        if (full) { BPV_NV12_BODY(BPV_ALWAYS, BPV_ALWAYS) }
+        else { BPV_NV12_BODY(BPV_PIX, BPV_ROW) }
+#undef BPV_NV12_BODY
+#undef BPV_ALWAYS
+#undef BPV_PIX
+#undef BPV_ROW
       }
     }
   }
@@ -951,7 +963,7 @@ __device__ __forceinline__ uint32_t load_pixel(const uint8_t* __restrict__ row, 
 
 // WORDS: frame base and strides are 4-byte aligned, so the two source pixels of a horizontal tap pair come from aligned
 // 32-bit loads (load_two_pixels) instead of six byte loads per row.
-template <bool WANT_SUMS, bool WORDS>
+template <bool WANT_SUMS, bool WORDS, bool ALL, int U>
 __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                           int sh, int sw, int dh, int dw, int R, int mode, long long num_rois,
                                                           const int32_t* __restrict__ boxes,
@@ -981,7 +993,8 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
     int rps, r0, c0;
     if (ncols >= THREADS) { rps = 1; r0 = 0; c0 = gt; }
     else { rps = THREADS / ncols; r0 = gt / ncols; c0 = gt - r0 * ncols; if (r0 >= rps) c0 = ncols; }
-    constexpr int U = 4;                     // row steps per iteration: their 4 x U source loads are all in flight together
+    // U row steps per iteration: their 4 x U source loads are all in flight together.  ALL = false (GREEN without sums):
+    // only the green channel goes through the bilinear arithmetic.
     for (int c = c0; c < ncols; c += THREADS) {
       ResizeTap tc;
       if (!area2) tc = ctap[c];
@@ -1024,9 +1037,10 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (rb + u * rps >= nrows) continue;
-          int px[3];
+          int px[3] = {0, 0, 0};
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
+            if (!ALL && ch != 1) continue;
             const int A0 = (int)(a0[u] >> (8 * ch) & 255), A1 = (int)(a1[u] >> (8 * ch) & 255);
             const int B0 = (int)(b0[u] >> (8 * ch) & 255), B1 = (int)(b1[u] >> (8 * ch) & 255);
             if (area2) px[ch] = (A0 + A1 + B0 + B1 + 2) >> 2;
@@ -1113,14 +1127,28 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
   // aligned 32-bit loads read whole words around a pixel pair: rows must start word aligned
   const bool words = (((uintptr_t)frames | (uintptr_t)frame_stride_bytes | (uintptr_t)row_stride_bytes) & 3) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define BPV_RSZ(S, Wd)                                                                                                         \
+#define BPV_RSZ(S, Wd, A, Uu)                                                                                                  \
   do {                                                                                                                         \
-    if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<S, Wd>, smem)) return rc;                                      \
-    roi_resized_kernel<S, Wd><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, dst_h, \
-                                                              dst_w, R, mode, n, boxes, (unsigned long long*)out_sums, out_value); \
+    if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<S, Wd, A, Uu>, smem)) return rc;                               \
+    roi_resized_kernel<S, Wd, A, Uu><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, \
+                                                                     dst_h, dst_w, R, mode, n, boxes,                            \
+                                                                     (unsigned long long*)out_sums, out_value);                  \
   } while (0)
-  if (out_sums) { if (words) BPV_RSZ(true, true); else BPV_RSZ(true, false); }
-  else { if (words) BPV_RSZ(false, true); else BPV_RSZ(false, false); }
+  // development switch for one A/B measurement: BPV_RESIZE_VARIANT = "<words 0|1><row steps 1|4>", e.g. "01"
+  const char* var = getenv("BPV_RESIZE_VARIANT");
+  const bool use_words = words && !(var && var[0] == '0');
+  const bool u4 = !(var && var[0] && var[1] == '1');
+  const bool all = mode != BPV_GREEN;
+  if (out_sums) {
+    if (use_words) { if (u4) BPV_RSZ(true, true, true, 4); else BPV_RSZ(true, true, true, 1); }
+    else { if (u4) BPV_RSZ(true, false, true, 4); else BPV_RSZ(true, false, true, 1); }
+  } else if (all) {
+    if (use_words) { if (u4) BPV_RSZ(false, true, true, 4); else BPV_RSZ(false, true, true, 1); }
+    else { if (u4) BPV_RSZ(false, false, true, 4); else BPV_RSZ(false, false, true, 1); }
+  } else {
+    if (use_words) { if (u4) BPV_RSZ(false, true, false, 4); else BPV_RSZ(false, true, false, 1); }
+    else { if (u4) BPV_RSZ(false, false, false, 4); else BPV_RSZ(false, false, false, 1); }
+  }
 #undef BPV_RSZ
   return check_launch("bpv_roi_sample_resized_u8");
 }

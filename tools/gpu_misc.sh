@@ -1,10 +1,8 @@
 #!/bin/bash
-# 1-GPU experiments: F1 against box shape (is the config-2 gap per-CTA overhead or segment length?), ingest kernels in HBM
-tag=${1:-r2f}
-o=gpurun_out/${tag}_roi_shapes.txt; : > $o
-for box in 96,65 96,260 96,520 384,65 192,130 288,22; do
-  echo "== box $box" >> $o
-  timeout 300 python tools/bench_roi.py --frames 4096 --iters 30 --box $box 2>&1 | tail -1 >> $o
-done
+# 1-GPU experiments: ingest kernels in HBM (and the resize variants)
+tag=${1:-r2h}
+python -m pytest tests/test_roi_gpu.py -m gpu -q 2>&1 | tail -2
+o=gpurun_out/${tag}_ingest.txt; : > $o
+python tools/bench_ingest.py >> $o 2>&1
+for v in 11 01 00; do BPV_RESIZE_VARIANT=$v python tools/bench_ingest.py 2>&1 | grep resized >> $o; done
 cat $o
-python tools/bench_ingest.py > gpurun_out/${tag}_ingest.txt 2>&1; cat gpurun_out/${tag}_ingest.txt
