@@ -469,8 +469,11 @@ __global__ void __launch_bounds__(THREADS) roi_staged_kernel(const RoiArgs a, co
   }
 }
 
+#ifdef BPV_ROI_TUNING
 // ---------------------------------------------------------------------------------------------
-// Persistent, double-buffered variant of the staged path.  The one-ROI-per-CTA kernel above has its loads in flight for
+// Persistent, double-buffered variant of the staged path (tuning builds only: -DBPV_ROI_TUNING, BPV_ROI_PIPELINED=1).
+// MEASURED AND REJECTED on the config-2 boxes: 77.8 us per 8192 frames against 64.5 us for the one-ROI-per-CTA kernel
+// (profiles/r2d_roi_ab.txt) — 128 registers and 49 KB per CTA leave 4 CTAs per SM where the simple kernel runs 9.  The one-ROI-per-CTA kernel above has its loads in flight for
 // only part of a CTA's life (launch, the dependent box load, address set-up, the reduction and the exit carry none), and
 // a 16 384-CTA grid on 148 x 9 slots ends in a partial wave.  Here a CTA lives for the whole launch and claims ROIs from a
 // global counter (perfect balance, no tail); it owns TWO stages of K slots per thread, and issues the cp.async of its
@@ -703,6 +706,8 @@ static int launch_pipelined(const RoiArgs& a, cudaStream_t st) {
   return 0;
 }
 
+#endif  // BPV_ROI_TUNING
+
 template <int THREADS, int K, int STAGE>
 static void launch_staged(const RoiArgs& a, int stage_bytes, cudaStream_t st) {
   const int smem = STAGE == 1 ? THREADS * K * 16 : stage_bytes;
@@ -842,43 +847,33 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
             }
           }
         }
-        // interior vectors (all 16 pixels and both rows in range: most of a ROI) take the predicate-free body
-        const bool full = inm == 0xffffu && row_on[0] && row_on[1];
-#define BPV_NV12_BODY(PIXEL_ON, ROW_ON)                                                                     \
-        _Pragma("unroll")                                                                                   \
-        for (int pr = 0; pr < 8; ++pr) {                                                                    \
-          if (!(PIXEL_ON(2 * pr) || PIXEL_ON(2 * pr + 1))) continue;                                        \
-          const uint32_t c2 = cw[pr >> 1] >> (16 * (pr & 1));                                               \
-          const int uu = (int)(c2 & 0xffu) - 128, vv = (int)(c2 >> 8 & 0xffu) - 128;                        \
-          const int guv = (1 << 19) - 852492 * vv - 409993 * uu;                                            \
-          const int ruv = (1 << 19) + 1673527 * vv;                                                         \
-          const int buv = (1 << 19) + 2116026 * uu;                                                         \
-          _Pragma("unroll")                                                                                 \
-          for (int ro = 0; ro < 2; ++ro) {                                                                  \
-            if (!ROW_ON(ro)) continue;                                                                      \
-            _Pragma("unroll")                                                                               \
-            for (int e = 0; e < 2; ++e) {                                                                   \
-              const int px = 2 * pr + e;                                                                    \
-              if (!PIXEL_ON(px)) continue;                                                                  \
-              const int yy = (int)(yw[ro][px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;                         \
-              const int yc = (yy > 0 ? yy : 0) * 1220542;                                                   \
-              sG += (uint32_t)sat_u8((yc + guv) >> 20);                                                     \
-              if (ALL) {                                                                                    \
-                sR += (uint32_t)sat_u8((yc + ruv) >> 20);                                                   \
-                sB += (uint32_t)sat_u8((yc + buv) >> 20);                                                   \
-              }                                                                                             \
-            }                                                                                               \
-          }                                                                                                 \
+        // (a predicate-free copy of this body for interior vectors was measured: 217 us against 144 us per 8192 frames —
+        // the doubled code costs more than the skipped tests save; profiles/r2h_ingest.txt)
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+          if (!(inm >> (2 * pr) & 3u)) continue;
+          const uint32_t c2 = cw[pr >> 1] >> (16 * (pr & 1));
+          const int uu = (int)(c2 & 0xffu) - 128, vv = (int)(c2 >> 8 & 0xffu) - 128;
+          const int guv = (1 << 19) - 852492 * vv - 409993 * uu;
+          const int ruv = (1 << 19) + 1673527 * vv;
+          const int buv = (1 << 19) + 2116026 * uu;
+#pragma unroll
+          for (int ro = 0; ro < 2; ++ro) {
+            if (!row_on[ro]) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int px = 2 * pr + e;
+              if (!(inm >> px & 1u)) continue;
+              const int yy = (int)(yw[ro][px >> 2] >> (8 * (px & 3)) & 0xffu) - 16;
+              const int yc = (yy > 0 ? yy : 0) * 1220542;
+              sG += (uint32_t)sat_u8((yc + guv) >> 20);
+              if (ALL) {
+                sR += (uint32_t)sat_u8((yc + ruv) >> 20);
+                sB += (uint32_t)sat_u8((yc + buv) >> 20);
+              }
+            }
+          }
         }
-#define BPV_ALWAYS(i) true
-#define BPV_PIX(i) ((inm >> (i)) & 1u)
-#define BPV_ROW(i) row_on[i]
-        if (full) { BPV_NV12_BODY(BPV_ALWAYS, BPV_ALWAYS) }
-        else { BPV_NV12_BODY(BPV_PIX, BPV_ROW) }
-#undef BPV_NV12_BODY
-#undef BPV_ALWAYS
-#undef BPV_PIX
-#undef BPV_ROW
       }
     }
   }
@@ -934,36 +929,11 @@ __device__ __forceinline__ ResizeTap resize_tap(int d, double scale, int sn, boo
   return t;
 }
 
-// 6 consecutive bytes (two BGR pixels) starting at byte `off` of a 4-byte aligned row, as (pixel 0, pixel 1) packed
-// B | G << 8 | R << 16: two or three aligned 32-bit loads and funnel shifts instead of six byte loads.  `limit` = bytes
-// that may be read from `row` (whole words are read around the pixels): the tail of a frame's last row takes byte loads.
-__device__ __forceinline__ void load_two_pixels(const uint8_t* __restrict__ row, int off, int limit, uint32_t& p0, uint32_t& p1) {
-  if ((off & ~3) + 12 > limit) {
-    p0 = row[off] | row[off + 1] << 8 | row[off + 2] << 16;
-    p1 = row[off + 3] | row[off + 4] << 8 | row[off + 5] << 16;
-    return;
-  }
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (off & ~3));
-  const int sh = 8 * (off & 3);
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
-  const uint32_t lo = __funnelshift_r(w0, w1, sh);                 // bytes off .. off+3
-  uint32_t hi = w1 >> sh;                                          // bytes off+4 .. (off+7 needs the next word)
-  if ((off & 3) == 3) hi = __funnelshift_r(w1, __ldg(w + 2), sh);
-  p0 = lo & 0xffffffu;
-  p1 = (lo >> 24 | hi << 8) & 0xffffffu;
-}
-__device__ __forceinline__ uint32_t load_pixel(const uint8_t* __restrict__ row, int off, int limit) {
-  if ((off & ~3) + 8 > limit) return row[off] | row[off + 1] << 8 | row[off + 2] << 16;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (off & ~3));
-  const int sh = 8 * (off & 3);
-  uint32_t v = __ldg(w) >> sh;
-  if ((off & 3) > 1) v = __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
-  return v & 0xffffffu;
-}
-
-// WORDS: frame base and strides are 4-byte aligned, so the two source pixels of a horizontal tap pair come from aligned
-// 32-bit loads (load_two_pixels) instead of six byte loads per row.
-template <bool WANT_SUMS, bool WORDS, bool ALL, int U>
+// ALL = false (GREEN without sums): only the green channel goes through the bilinear arithmetic.  The four source pixels
+// of an output pixel are read with byte loads (L1 serves them: neighbouring threads share lines); U = 4 row steps per
+// iteration keep 4 x 12 of them in flight.  Measured per 8192 frames of 1080p -> 720p boxes (profiles/r2h_ingest.txt):
+// byte loads + 4 row steps 289 us (green only 139 us), one row step 315 us, aligned 32-bit loads + funnel shifts 391-507 us.
+template <bool WANT_SUMS, bool ALL, int U>
 __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                           int sh, int sw, int dh, int dw, int R, int mode, long long num_rois,
                                                           const int32_t* __restrict__ boxes,
@@ -1010,28 +980,15 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
             const uint8_t* p0 = fp + (long long)(2 * (ys + r)) * row_stride;
             const uint8_t* p1 = p0 + row_stride;
             const int off = 6 * (xs + c);
-            const int lim1 = 2 * (ys + r) + 1 == sh - 1 ? 3 * sw : 0x7fffffff;       // a frame's last row must not be overrun
-            if (WORDS) { load_two_pixels(p0, off, 0x7fffffff, a0[u], a1[u]); load_two_pixels(p1, off, lim1, b0[u], b1[u]); }
-            else {
-              a0[u] = p0[off] | p0[off + 1] << 8 | p0[off + 2] << 16; a1[u] = p0[off + 3] | p0[off + 4] << 8 | p0[off + 5] << 16;
-              b0[u] = p1[off] | p1[off + 1] << 8 | p1[off + 2] << 16; b1[u] = p1[off + 3] | p1[off + 4] << 8 | p1[off + 5] << 16;
-            }
+            a0[u] = p0[off] | p0[off + 1] << 8 | p0[off + 2] << 16; a1[u] = p0[off + 3] | p0[off + 4] << 8 | p0[off + 5] << 16;
+            b0[u] = p1[off] | p1[off + 1] << 8 | p1[off + 2] << 16; b1[u] = p1[off + 3] | p1[off + 4] << 8 | p1[off + 5] << 16;
           } else {
             const ResizeTap tr = rtap[r];
             wr0[u] = tr.w0; wr1[u] = tr.w1;
             const uint8_t* q0 = fp + (long long)tr.i0 * row_stride;
             const uint8_t* q1 = fp + (long long)tr.i1 * row_stride;
-            if (WORDS) {
-              const int l0 = tr.i0 == sh - 1 ? 3 * sw : 0x7fffffff, l1 = tr.i1 == sh - 1 ? 3 * sw : 0x7fffffff;
-              if (tc.i1 == tc.i0 + 1) { load_two_pixels(q0, 3 * tc.i0, l0, a0[u], a1[u]); load_two_pixels(q1, 3 * tc.i0, l1, b0[u], b1[u]); }
-              else {
-                a0[u] = load_pixel(q0, 3 * tc.i0, l0); a1[u] = load_pixel(q0, 3 * tc.i1, l0);
-                b0[u] = load_pixel(q1, 3 * tc.i0, l1); b1[u] = load_pixel(q1, 3 * tc.i1, l1);
-              }
-            } else {
-              a0[u] = q0[3 * tc.i0] | q0[3 * tc.i0 + 1] << 8 | q0[3 * tc.i0 + 2] << 16; a1[u] = q0[3 * tc.i1] | q0[3 * tc.i1 + 1] << 8 | q0[3 * tc.i1 + 2] << 16;
-              b0[u] = q1[3 * tc.i0] | q1[3 * tc.i0 + 1] << 8 | q1[3 * tc.i0 + 2] << 16; b1[u] = q1[3 * tc.i1] | q1[3 * tc.i1 + 1] << 8 | q1[3 * tc.i1 + 2] << 16;
-            }
+            a0[u] = q0[3 * tc.i0] | q0[3 * tc.i0 + 1] << 8 | q0[3 * tc.i0 + 2] << 16; a1[u] = q0[3 * tc.i1] | q0[3 * tc.i1 + 1] << 8 | q0[3 * tc.i1 + 2] << 16;
+            b0[u] = q1[3 * tc.i0] | q1[3 * tc.i0 + 1] << 8 | q1[3 * tc.i0 + 2] << 16; b1[u] = q1[3 * tc.i1] | q1[3 * tc.i1 + 1] << 8 | q1[3 * tc.i1 + 2] << 16;
           }
         }
 #pragma unroll
@@ -1124,40 +1081,27 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
   if (num_frames == 0) return 0;
   const long long n = num_frames * R;
   const int smem = (dst_h + dst_w) * (int)sizeof(ResizeTap);        // worst case: a ROI spanning the whole resized frame
-  // aligned 32-bit loads read whole words around a pixel pair: rows must start word aligned
-  const bool words = (((uintptr_t)frames | (uintptr_t)frame_stride_bytes | (uintptr_t)row_stride_bytes) & 3) == 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define BPV_RSZ(S, Wd, A, Uu)                                                                                                  \
-  do {                                                                                                                         \
-    if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<S, Wd, A, Uu>, smem)) return rc;                               \
-    roi_resized_kernel<S, Wd, A, Uu><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w, \
-                                                                     dst_h, dst_w, R, mode, n, boxes,                            \
-                                                                     (unsigned long long*)out_sums, out_value);                  \
+#define BPV_RSZ(S, A)                                                                                                       \
+  do {                                                                                                                      \
+    if (int rc = ensure_dyn_smem((const void*)roi_resized_kernel<S, A, 4>, smem)) return rc;                                 \
+    roi_resized_kernel<S, A, 4><<<(unsigned)n, 128, smem, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h, src_w,   \
+                                                                dst_h, dst_w, R, mode, n, boxes,                             \
+                                                                (unsigned long long*)out_sums, out_value);                   \
   } while (0)
-  // development switch for one A/B measurement: BPV_RESIZE_VARIANT = "<words 0|1><row steps 1|4>", e.g. "01"
-  const char* var = getenv("BPV_RESIZE_VARIANT");
-  const bool use_words = words && !(var && var[0] == '0');
-  const bool u4 = !(var && var[0] && var[1] == '1');
-  const bool all = mode != BPV_GREEN;
-  if (out_sums) {
-    if (use_words) { if (u4) BPV_RSZ(true, true, true, 4); else BPV_RSZ(true, true, true, 1); }
-    else { if (u4) BPV_RSZ(true, false, true, 4); else BPV_RSZ(true, false, true, 1); }
-  } else if (all) {
-    if (use_words) { if (u4) BPV_RSZ(false, true, true, 4); else BPV_RSZ(false, true, true, 1); }
-    else { if (u4) BPV_RSZ(false, false, true, 4); else BPV_RSZ(false, false, true, 1); }
-  } else {
-    if (use_words) { if (u4) BPV_RSZ(false, true, false, 4); else BPV_RSZ(false, true, false, 1); }
-    else { if (u4) BPV_RSZ(false, false, false, 4); else BPV_RSZ(false, false, false, 1); }
-  }
+  if (out_sums) BPV_RSZ(true, true);
+  else if (mode != BPV_GREEN) BPV_RSZ(false, true);
+  else BPV_RSZ(false, false);
 #undef BPV_RSZ
   return check_launch("bpv_roi_sample_resized_u8");
 }
 
-// BPV_ROI_PIPELINED=0/1 selects the one-ROI-per-CTA staged kernel or the persistent double-buffered one (default below)
+#ifdef BPV_ROI_TUNING
 static bool roi_pipelined_enabled() {
   const char* v = getenv("BPV_ROI_PIPELINED");
   return v ? v[0] == '1' : false;
 }
+#endif
 
 extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* frame_ptrs,
                                  int64_t frame_stride_bytes, int64_t row_stride_bytes,
@@ -1201,7 +1145,9 @@ extern "C" int bpv_roi_sample_u8(const uint8_t* frames, const uint8_t* const* fr
       else launch_rows<128, 2>(a, (unsigned)((n + 1) / 2), st);
     }
     else if (g == 32) launch_rows<32, 5>(a, grid, st);
+#ifdef BPV_ROI_TUNING
     else if (roi_pipelined_enabled()) { if (int rc = launch_pipelined<128, 12>(a, st)) return rc; }
+#endif
     else launch_staged<128, 12, 1>(a, 0, st);
   } else {                           // generic path: alignment changes row by row
     if (g == 32) roi_sample_kernel<32, 4><<<grid, 256, 0, st>>>(a);

@@ -1,11 +1,11 @@
 #!/bin/bash
-# 2-GPU session: NCCL parity tests on real kernels, device-placement test, the N=2 bench line (with and without NUMA binding)
+# multi-GPU session: NCCL parity tests on real kernels, device-placement test, the N-GPU bench line (+ NUMA-bound e2e variant)
 tag=${1:-r2e}; n=${2:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/${tag}_topo.txt 2>&1
-python -m pytest tests/test_dist_gpu.py tests/test_round2_gpu.py tests/test_roi_gpu.py -m gpu -q --maxfail=10 > gpurun_out/${tag}_pytest_multi.log 2>&1; tail -6 gpurun_out/${tag}_pytest_multi.log | cut -c1-200
+python -m pytest tests/test_dist_gpu.py tests/test_round2_gpu.py -m gpu -q --maxfail=10 -k "sharded or second_gpu" > gpurun_out/${tag}_pytest_multi.log 2>&1; tail -4 gpurun_out/${tag}_pytest_multi.log | cut -c1-200
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 60 --warmup 5 \
-   > gpurun_out/${tag}_bench_c2_${n}gpu.json 2> gpurun_out/${tag}_bench_${n}gpu.err; echo "bench rc=$?"; tail -c 600 gpurun_out/${tag}_bench_${n}gpu.err
+   > gpurun_out/${tag}_bench_c2_${n}gpu.json 2> gpurun_out/${tag}_bench_${n}gpu.err; echo "bench rc=$?"; tail -c 400 gpurun_out/${tag}_bench_${n}gpu.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 60 --warmup 5 --bind-numa --no-other \
    > gpurun_out/${tag}_bench_c2_${n}gpu_numa.json 2>> gpurun_out/${tag}_bench_${n}gpu.err; echo "bench numa rc=$?"
 python - <<PY
