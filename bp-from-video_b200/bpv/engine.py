@@ -129,7 +129,7 @@ class BatchedSignalProcessor:
         need = max(_cabi.lib().bpv_window_workspace_bytes(p), 16)
         self._ws = torch.empty(need, dtype=torch.uint8, device=dev)                 # per-job filter designs
         need = max(_cabi.lib().bpv_spectrum_workspace_bytes(p, self._mb), 16)
-        self._ws_spec = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._ws_spec = torch.zeros(need, dtype=torch.uint8, device=dev)    # zeroed: holds the DFT twiddle images' header
         self.launches_per_step = self._extra_launches = 0
         self._has_filter = any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
         # design cache (include/bpv.h bpv_window_design): make_filter is a pure function of fs, so sampling rates that were
@@ -310,13 +310,21 @@ class BatchedSignalProcessor:
         spo = None if spo is None or spo['peak_idx'].shape[0] != J else spo
         xco = None if xco is None or xco['lag_idx'].shape[0] != J else xco
         if (self.overlap & OVERLAP_XCORR) and self.P:
+            # launch order matters for co-residency: the spectrum kernels' CTAs are small (Welch: 24 KB of shared memory),
+            # the xcorr CTAs large (51 KB); with xcorr first its 4 CTAs fill an SM's shared memory and the spectrum only
+            # gets in as they retire (168 us for the pair against 103 + 75 serial); spectrum first leaves room for two xcorr
+            # CTAs beside five Welch CTAs.  BPV_XC_FIRST=1 restores the other order (measurement switch).
             side, ev = self._streams()
             ev['pre'].record(main)
             side.wait_event(ev['pre'])
+            xc_first = os.environ.get('BPV_XC_FIRST', '') == '1'
+            if not xc_first:
+                sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
             with torch.cuda.stream(side):
                 xc = ops.window_xcorr(px, py, p, store=self.store_arrays, out=xco)
                 ev['xc'].record(side)
-            sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
+            if xc_first:
+                sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
             main.wait_event(ev['xc'])
         else:
             sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)

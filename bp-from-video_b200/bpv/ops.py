@@ -209,9 +209,12 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
         o['peak_freq'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
     if 'peak_mag' not in o:
         o['peak_mag'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
-    need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if not store else 0
+    # scratch for the coarse spectrum when it is not stored; for DFT_RFFT also the persistent twiddle operand images of the
+    # tensor-core kernel (zero-initialised: a header tells the kernel whether they are built) — pass the same workspace
+    # every call to build them once
+    need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if (not store or p.transform == _cabi.DFT_RFFT) else 0
     if need and (workspace is None or workspace.numel() < need):
-        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
     _run(proc_y.device, 'bpv_window_spectrum', ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
                                     ptr(o['freqs']), ptr(o['mags']),
                                     ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']))

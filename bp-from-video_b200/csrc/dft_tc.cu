@@ -20,6 +20,7 @@
 // visible to the tensor core with fence.proxy.async; one thread issues the MMAs; tcgen05.commit -> mbarrier tells the
 // CTA when the chunk buffers may be overwritten and when the accumulator is complete; tcgen05.ld (32 lanes x 32 columns
 // per warp) brings each row's spectrum back to the thread that owns that segment.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bpv {
@@ -664,15 +665,230 @@ __global__ void __launch_bounds__(128) dft_peak_kernel(const double* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant of dft_tc_kernel (round 2).  The kernel above spends ~4x longer generating its B operand (table look-ups,
+// hi / lo splits, 4 shared-memory stores per thread and k block) than the tensor core spends consuming it.  The twiddle
+// matrix depends only on n = W, so it is computed ONCE (dft_image_kernel, into the caller's workspace, kept across
+// launches: a header remembers the n it was built for) as ready-made operand images — for every (bin chunk, k block) the
+// 32 KB [B hi | B lo] block in exactly the K-major canonical shared-memory layout the UMMA descriptors expect — and the
+// main kernel fetches one image per k block with a single cp.async.bulk (TMA, UBLKCP) that completes on an mbarrier:
+//   thread 0      producer + issuer: keeps the B images of blocks kb+1, kb+2 in flight (4-stage ring: full[s] barriers
+//                 armed with expect_tx, empty[s] barriers arrived by tcgen05.commit), waits full[s], issues the 6 MMAs
+//   all threads   convert the float64 samples of block kb to the A operand (hi / lo split), as before
+// Waits are bounded: a barrier that never completes traps instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr int DTM_NS = 4;                                   // ring stages
+constexpr int DTM_STAGE = 48 * 1024;                        // A hi | A lo [4][128][4] (16 KB) + B hi | B lo [4][256][4] (32 KB)
+constexpr int DTM_B_BYTES = 32 * 1024;
+constexpr int DTM_OFF_BAD = DTM_NS * DTM_STAGE;             // int [128]
+constexpr int DTM_OFF_BAR = DTM_OFF_BAD + 512;              // full[NS] | empty[NS] (u64 each) | tmem slot (u32)
+constexpr int DTM_SMEM = DTM_OFF_BAR + 16 * DTM_NS + 16;
+constexpr unsigned long long DTM_MAGIC = 0x62707644465431ULL;   // "bpvDFT1"
+
+__host__ __device__ inline long long dtc_image_bytes(int W) {
+  const long long NB = (W + DTC_KB - 1) / DTC_KB, nbc = (W / 2 + 1 + 127) / 128;
+  return 256 + nbc * NB * DTM_B_BYTES;                      // header (magic, n) + images
+}
+
+// One CTA per (k block, bin chunk): 1024 operand items (chunk c, column col) of 4 consecutive samples each.
+__global__ void __launch_bounds__(256) dft_image_kernel(int n, unsigned char* __restrict__ ws) {
+  const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(ws);
+  if (hdr[0] == DTM_MAGIC && hdr[1] == (unsigned long long)n) return;          // built for this n by an earlier launch
+  const int F = n / 2 + 1, NB = (n + DTC_KB - 1) / DTC_KB;
+  const int kb = blockIdx.x, bc = blockIdx.y;
+  float4* Bhi = reinterpret_cast<float4*>(ws + 256 + ((long long)bc * NB + kb) * DTM_B_BYTES);
+  float4* Blo = Bhi + 4 * TC_N;
+  for (int it = threadIdx.x; it < 4 * TC_N; it += blockDim.x) {
+    const int c = it / TC_N, col = it % TC_N;
+    const int kcol = bc * 128 + (col & 127);
+    float hv[4], lv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = kb * DTC_KB + 4 * c + e;
+      double v = 0.0;
+      if (kcol < F && j < n) {
+        const long long idx = ((long long)j * kcol) % n;
+        double s_, c_;
+        sincospi(2.0 * (double)idx / (double)n, &s_, &c_);
+        v = col < 128 ? c_ : s_;
+      }
+      hv[e] = tc_hi((float)v);
+      lv[e] = (float)(v - (double)hv[e]);
+    }
+    Bhi[it] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    Blo[it] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+  }
+}
+__global__ void dft_image_seal_kernel(int n, unsigned char* __restrict__ ws) {
+  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(ws);
+  hdr[0] = DTM_MAGIC; hdr[1] = (unsigned long long)n;
+}
+
+__device__ __forceinline__ void tc_wait_bounded(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 2000000000LL) __trap();   // ~1 s: a protocol error must not hang the device
+  }
+}
+__device__ __forceinline__ void tc_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_tma_kernel(const double* __restrict__ proc_y, int W, long long nsig, int max_bins,
+                                                                    const unsigned char* __restrict__ img,
+                                                                    float* __restrict__ mags, int32_t* __restrict__ num_bins) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int n = W, F = n / 2 + 1;
+  int* bad = reinterpret_cast<int*>(smem + DTM_OFF_BAD);
+  uint8_t* barp = smem + DTM_OFF_BAR;
+  const uint32_t bar = tc_smem_u32(barp), slot = bar + 16 * DTM_NS;
+  auto full = [&](int s_) { return bar + 8u * (uint32_t)s_; };
+  auto empty = [&](int s_) { return bar + 8u * (uint32_t)(DTM_NS + s_); };
+  if (tid < 128) bad[tid] = 0;
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (tid == 0) {
+      for (int s_ = 0; s_ < 2 * DTM_NS; ++s_) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u * (uint32_t)s_) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 16 * DTM_NS);
+
+  const long long sig0 = (long long)blockIdx.x * TC_M;
+  const int k0 = blockIdx.y * 128;
+  const int NB = (n + DTC_KB - 1) / DTC_KB;
+  const unsigned char* my_img = img + 256 + (long long)blockIdx.y * NB * DTM_B_BYTES;
+  const uint32_t smem0 = tc_smem_u32(smem);
+  if (tid == 0) {                                           // B images of the first two k blocks
+    for (int kb = 0; kb < 2 && kb < NB; ++kb)
+      tc_bulk_load(smem0 + (uint32_t)kb * DTM_STAGE + 16384, my_img + (long long)kb * DTM_B_BYTES, DTM_B_BYTES, full(kb));
+  }
+  const int arow = tid >> 2, aq = tid & 3;
+  const long long asig = sig0 + arow;
+  const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
+  const bool vec_ok = (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0;
+  int mybad = 0;
+  double cur[4], nxt[4];
+  auto fetch = [&](int kb, double (&dst)[4]) {
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int j = kb * DTC_KB + 8 * hlf + 2 * aq;
+      if (asig < nsig && j + 1 < n && vec_ok) {
+        const double2 v = *reinterpret_cast<const double2*>(ay + j);
+        dst[2 * hlf] = v.x; dst[2 * hlf + 1] = v.y;
+      } else {
+        dst[2 * hlf] = (asig < nsig && j < n) ? ay[j] : 0.0;
+        dst[2 * hlf + 1] = (asig < nsig && j + 1 < n) ? ay[j + 1] : 0.0;
+      }
+    }
+  };
+  fetch(0, cur);
+  for (int kb = 0; kb < NB; ++kb) {
+    const int st = kb % DTM_NS;
+    uint8_t* stage = smem + st * DTM_STAGE;
+    if (kb + 1 < NB) fetch(kb + 1, nxt);
+    if (kb >= DTM_NS) tc_wait_bounded(empty(st), (uint32_t)((kb / DTM_NS - 1) & 1));      // block kb-NS has been consumed
+    if (tid == 0 && kb + 2 < NB) {                          // keep two B images in flight
+      const int k2 = kb + 2, s2 = k2 % DTM_NS;
+      if (k2 >= DTM_NS) tc_wait_bounded(empty(s2), (uint32_t)((k2 / DTM_NS - 1) & 1));
+      tc_bulk_load(smem0 + (uint32_t)s2 * DTM_STAGE + 16384, my_img + (long long)k2 * DTM_B_BYTES, DTM_B_BYTES, full(s2));
+    }
+    {
+      float hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double v = cur[e];
+        if (!isfinite(v)) mybad = 1;
+        hv[e] = tc_hi((float)v);
+        lv[e] = (float)(v - (double)hv[e]);
+      }
+      float2* Ah2 = reinterpret_cast<float2*>(stage);
+      float2* Al2 = reinterpret_cast<float2*>(stage + 8192);
+      const int o0 = (((aq >> 1) * TC_M + arow) << 1) + (aq & 1), o1 = (((2 + (aq >> 1)) * TC_M + arow) << 1) + (aq & 1);
+      Ah2[o0] = make_float2(hv[0], hv[1]); Al2[o0] = make_float2(lv[0], lv[1]);
+      Ah2[o1] = make_float2(hv[2], hv[3]); Al2[o1] = make_float2(lv[2], lv[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      tc_wait_bounded(full(st), (uint32_t)((kb / DTM_NS) & 1));      // the TMA has landed this block's B image
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem0 + (uint32_t)st * DTM_STAGE;
+#pragma unroll
+      for (int ks = 0; ks < DTC_KB / 8; ++ks) {
+        const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
+        const uint64_t dbh = tc_desc(sa + 16384 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sa + 32768 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
+        tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
+        tc_mma_tf32(tmem, dal, dbh, 1);
+        tc_mma_tf32(tmem, dah, dbl, 1);
+      }
+      tc_commit(empty(st));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
+  }
+  if (mybad) bad[arow] = 1;
+  tc_wait_bounded(empty((NB - 1) % DTM_NS), (uint32_t)(((NB - 1) / DTM_NS) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();                                         // bad[] complete
+  if (tid < TC_M) {
+    const long long sig = sig0 + tid;
+    const bool rowbad = bad[tid] != 0;
+    const float sc = 2.f / (float)n;
+    for (int c32 = 0; c32 < 4; ++c32) {
+      float re[32], im[32];
+      __syncwarp();
+      tc_load32(tmem, 32 * c32, re);
+      tc_load32(tmem, 128 + 32 * c32, im);
+      if (sig < nsig && !rowbad) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + 32 * c32 + i;
+          if (k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(re[i] * re[i] + im[i] * im[i]);
+        }
+      }
+    }
+    if (sig < nsig && rowbad && blockIdx.y == 0) num_bins[sig] = -2;     // the float64 kernel takes this window
+    if (sig < nsig && !rowbad && blockIdx.y == 0) num_bins[sig] = -1;    // marker: coarse spectrum ready for dft_peak_kernel
+  }
+  tc_teardown(tmem);
+}
+
+long long dft_tc_image_bytes(int W) { return dtc_image_bytes(W); }
+
+// image_ws: caller-owned, persistent device memory of dft_tc_image_bytes(W) bytes (zero-initialised once) for the TMA-fed
+// kernel, or NULL for the kernel that generates its operands itself.  BPV_DFT_TMA=0 forces the latter (measurement switch).
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
-                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, cudaStream_t st) {
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, cudaStream_t st) {
   const int smem = dtc_smem(W), smem_p = W * 16;
-  if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
   if (int rc = ensure_dyn_smem((const void*)dft_peak_kernel, smem_p)) return rc;
   const int F = W / 2 + 1;
   dim3 grid((unsigned)((nsig + TC_M - 1) / TC_M), (unsigned)((F + 127) / 128));
-  dft_tc_kernel<<<grid, DTC_THREADS, smem, st>>>(proc_y, W, nsig, max_bins, mags, num_bins);
-  if (int rc = check_launch("dft_tc_kernel")) return rc;
+  const char* env = getenv("BPV_DFT_TMA");
+  if (image_ws && !(env && env[0] == '0')) {
+    if (int rc = ensure_dyn_smem((const void*)dft_tc_tma_kernel, DTM_SMEM)) return rc;
+    const int NB = (W + DTC_KB - 1) / DTC_KB;
+    dft_image_kernel<<<dim3((unsigned)NB, grid.y), 256, 0, st>>>(W, (unsigned char*)image_ws);
+    if (int rc = check_launch("dft_image_kernel")) return rc;
+    dft_image_seal_kernel<<<1, 1, 0, st>>>(W, (unsigned char*)image_ws);
+    if (int rc = check_launch("dft_image_seal_kernel")) return rc;
+    dft_tc_tma_kernel<<<grid, DTC_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, (const unsigned char*)image_ws, mags, num_bins);
+    if (int rc = check_launch("dft_tc_tma_kernel")) return rc;
+  } else {
+    if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
+    dft_tc_kernel<<<grid, DTC_THREADS, smem, st>>>(proc_y, W, nsig, max_bins, mags, num_bins);
+    if (int rc = check_launch("dft_tc_kernel")) return rc;
+  }
   dft_peak_kernel<<<(unsigned)((nsig + 3) / 4), 128, smem_p, st>>>(proc_x, proc_y, W, nsig, max_bins, spec_f, mags, num_bins, peak_idx,
                                                                  peak_freq, peak_mag);
   return check_launch("dft_peak_kernel");

@@ -17,8 +17,9 @@
 
 namespace bpv {
 
+long long dft_tc_image_bytes(int W);
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
-                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, cudaStream_t st);
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, cudaStream_t st);
 int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
                     double* peak_freq, double* peak_mag, cudaStream_t st);
 
@@ -771,10 +772,17 @@ __global__ void __launch_bounds__(32 * LSP_WPB) ls_peak_warp_kernel(const double
 
 }  // namespace bpv
 
+// workspace plan: [coarse magnitudes / LS psd when the spectrum is not stored, rounded up to 256 B] [DFT_RFFT on the tensor
+// cores: the twiddle operand images of dft_tc.cu — persistent across calls, zero-initialised once by the caller]
+static int64_t spectrum_coarse_bytes(const bpv_window_params* p, int32_t max_bins) {
+  if (p->transform == BPV_PGRAM_WELCH) return 0;
+  return ((int64_t)p->S * p->jobs_per_stream * p->R * max_bins * 4 + 255) / 256 * 256;
+}
 extern "C" int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins) {
   if (!p) return -1;
-  if (p->transform == BPV_PGRAM_WELCH) return 0;
-  return (int64_t)p->S * p->jobs_per_stream * p->R * max_bins * 4;    // LS psd / DFT coarse magnitudes when not stored
+  int64_t b = spectrum_coarse_bytes(p, max_bins);
+  if (p->transform == BPV_DFT_RFFT && p->window >= 16 && p->window <= 2048) b += bpv::dft_tc_image_bytes(p->window);
+  return b;
 }
 
 extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,
@@ -826,12 +834,15 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
       const bool use_tc = env ? env[0] == '1' : interp;
       if (use_tc) {
         float* coarse = spec_mag;
+        const int64_t cb = spectrum_coarse_bytes(p, max_bins);
         if (!coarse) {
-          BPV_REQUIRE(workspace && workspace_bytes >= (int64_t)nsig * max_bins * 4, BPV_E_INVALID,
+          BPV_REQUIRE(workspace && workspace_bytes >= cb, BPV_E_INVALID,
                       "bpv_window_spectrum: workspace too small (see bpv_spectrum_workspace_bytes)");
           coarse = (float*)workspace;
         }
-        if (int rc = launch_dft_tc(proc_x, proc_y, W, nsig, max_bins, spec_f, coarse, num_bins, peak_idx, peak_freq, peak_mag, st)) return rc;
+        // the twiddle operand images live behind the coarse area when the caller's workspace has room for them
+        void* images = (workspace && workspace_bytes >= cb + dft_tc_image_bytes(W)) ? (void*)((unsigned char*)workspace + cb) : nullptr;
+        if (int rc = launch_dft_tc(proc_x, proc_y, W, nsig, max_bins, spec_f, coarse, num_bins, peak_idx, peak_freq, peak_mag, images, st)) return rc;
         only_flagged = 1;
       }
     }
@@ -843,7 +854,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
   BPV_REQUIRE(max_bins >= Fmax, BPV_E_INVALID, "bpv_window_spectrum: max_bins %d < %d", max_bins, Fmax);
   float* psd = spec_mag;
   if (!psd) {
-    BPV_REQUIRE(workspace && workspace_bytes >= bpv_spectrum_workspace_bytes(p, max_bins), BPV_E_INVALID,
+    BPV_REQUIRE(workspace && workspace_bytes >= spectrum_coarse_bytes(p, max_bins), BPV_E_INVALID,
                 "bpv_window_spectrum: workspace too small (see bpv_spectrum_workspace_bytes)");
     psd = (float*)workspace;
   }

@@ -222,8 +222,10 @@ int bpv_window_filter(const double* ring_t, const double* ring_y, const bpv_wind
  * spec_f, spec_mag float32 [J, R, max_bins] (first num_bins[j,r] entries valid; may be NULL to skip
  * storing the spectrum); num_bins int32 [J, R]; peak_idx int32 [J, R] (-1 = none);
  * peak_freq, peak_mag float64 [J, R] (NaN = none).  The peak is decided in float64.
- * workspace: device scratch of bpv_spectrum_workspace_bytes() bytes, needed only for PGRAM_LS when the
- * spectrum is not stored (spec_mag == NULL).
+ * workspace: device memory of bpv_spectrum_workspace_bytes() bytes: scratch for the coarse spectrum of PGRAM_LS / DFT_RFFT
+ * when it is not stored (spec_mag == NULL), followed — for DFT_RFFT — by the twiddle operand images of the tensor-core
+ * kernel.  Zero it once and pass the SAME buffer on every call: the images are built on first use and reused while the
+ * window length stays the same.  Without it (NULL / too small) DFT_RFFT generates its operands inside the kernel.
  */
 int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins);
 int bpv_window_spectrum(const double* proc_x, const double* proc_y, const bpv_window_params* p,

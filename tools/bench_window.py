@@ -38,7 +38,7 @@ while g < a.W:
     g += a.T
 eng.windows = keep
 fam = {}
-orig = {k: getattr(ops, k) for k in ('ring_push', 'window_preprocess', 'window_spectrum', 'window_xcorr')}
+orig = {k: getattr(ops, k) for k in ('ring_push', 'window_design', 'window_filter', 'window_spectrum', 'window_xcorr')}
 
 
 def timed(fn, key):
