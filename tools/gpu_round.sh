@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$KF" -c 400 --csv 
     python bench.py --steps 3 --warmup 3 --no-cpu --no-other > gpurun_out/${tag}_ncu.log 2>&1; echo "ncu rc=$?"
 if [ -n "$full" ]; then
   # ring prefill = 10 step_signals x 5 kernels; each warm-up step = 7 kernels -> skip past the warm-up, capture one full step
-  ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 71 --launch-count 7 -f -o gpurun_out/${tag}_c2 \
+  ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 90 --launch-count 10 -f -o gpurun_out/${tag}_c2 \
       python bench.py --steps 1 --warmup 3 --no-cpu --no-other > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 python - <<PY
