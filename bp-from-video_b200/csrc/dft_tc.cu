@@ -666,23 +666,28 @@ __global__ void __launch_bounds__(128) dft_peak_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-fed variant of dft_tc_kernel (round 2).  The kernel above spends ~4x longer generating its B operand (table look-ups,
-// hi / lo splits, 4 shared-memory stores per thread and k block) than the tensor core spends consuming it.  The twiddle
-// matrix depends only on n = W, so it is computed ONCE (dft_image_kernel, into the caller's workspace, kept across
-// launches: a header remembers the n it was built for) as ready-made operand images — for every (bin chunk, k block) the
-// 32 KB [B hi | B lo] block in exactly the K-major canonical shared-memory layout the UMMA descriptors expect — and the
-// main kernel fetches one image per k block with a single cp.async.bulk (TMA, UBLKCP) that completes on an mbarrier:
-//   thread 0      producer + issuer: keeps the B images of blocks kb+1, kb+2 in flight (4-stage ring: full[s] barriers
-//                 armed with expect_tx, empty[s] barriers arrived by tcgen05.commit), waits full[s], issues the 6 MMAs
-//   all threads   convert the float64 samples of block kb to the A operand (hi / lo split), as before
+// TMA-fed, warp-specialised variant of dft_tc_kernel (round 2).  The kernel above spends ~4x longer generating its B
+// operand (table look-ups, hi / lo splits, 4 shared-memory stores per thread and k block) than the tensor core spends
+// consuming it, and paces every k block with a CTA barrier.  The twiddle matrix depends only on n = W, so it is computed
+// ONCE (dft_image_kernel, into the caller's workspace, kept across launches: a header remembers the n it was built for)
+// as ready-made operand images — for every (bin chunk, k block) the 32 KB [B hi | B lo] block in exactly the K-major
+// canonical shared-memory layout the UMMA descriptors expect.  Roles in the CTA (17 warps, no CTA barrier in the loop):
+//   warps 0-15    A producers: float64 samples of k block kb -> hi / lo tf32 operand in A stage kb % 3, then
+//                 fence.proxy.async + one mbarrier arrive per warp on fullA
+//   warp 16       lane 0 is the TMA producer AND the MMA issuer: keeps the B images of the next 3 k blocks in flight
+//                 (one cp.async.bulk = UBLKCP of 32 KB each, completing on fullB with expect_tx; 5-stage ring), waits
+//                 fullA / fullB, issues the 6 tcgen05.mma of the block and commits them to emptyA / emptyB
 // Waits are bounded: a barrier that never completes traps instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------
-constexpr int DTM_NS = 4;                                   // ring stages
-constexpr int DTM_STAGE = 48 * 1024;                        // A hi | A lo [4][128][4] (16 KB) + B hi | B lo [4][256][4] (32 KB)
-constexpr int DTM_B_BYTES = 32 * 1024;
-constexpr int DTM_OFF_BAD = DTM_NS * DTM_STAGE;             // int [128]
-constexpr int DTM_OFF_BAR = DTM_OFF_BAD + 512;              // full[NS] | empty[NS] (u64 each) | tmem slot (u32)
-constexpr int DTM_SMEM = DTM_OFF_BAR + 16 * DTM_NS + 16;
+constexpr int DTM_NSA = 3, DTM_NSB = 5;                     // ring stages of the A / B operands
+constexpr int DTM_A_BYTES = 16 * 1024, DTM_B_BYTES = 32 * 1024;
+constexpr int DTM_OFF_B = DTM_NSA * DTM_A_BYTES;            // B ring behind the A ring
+constexpr int DTM_OFF_BAD = DTM_OFF_B + DTM_NSB * DTM_B_BYTES;   // int [128]
+constexpr int DTM_OFF_BAR = DTM_OFF_BAD + 512;              // fullA[3] emptyA[3] fullB[5] emptyB[5] (u64 each) | tmem slot (u32)
+constexpr int DTM_NBAR = 2 * DTM_NSA + 2 * DTM_NSB;
+constexpr int DTM_SMEM = DTM_OFF_BAR + 8 * DTM_NBAR + 16;
+constexpr int DTM_THREADS = DTC_THREADS + 32;               // 16 producer warps + the control warp
+constexpr int DTM_PREFETCH = DTM_NSB - 2;                   // B images in flight ahead of the MMAs
 constexpr unsigned long long DTM_MAGIC = 0x62707644465431ULL;   // "bpvDFT1"
 
 __host__ __device__ inline long long dtc_image_bytes(int W) {
@@ -738,72 +743,103 @@ __device__ __forceinline__ void tc_bulk_load(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tc_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
 
-__global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_tma_kernel(const double* __restrict__ proc_y, int W, long long nsig, int max_bins,
+__global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double* __restrict__ proc_y, int W, long long nsig, int max_bins,
                                                                     const unsigned char* __restrict__ img,
                                                                     float* __restrict__ mags, int32_t* __restrict__ num_bins) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int n = W, F = n / 2 + 1;
   int* bad = reinterpret_cast<int*>(smem + DTM_OFF_BAD);
   uint8_t* barp = smem + DTM_OFF_BAR;
-  const uint32_t bar = tc_smem_u32(barp), slot = bar + 16 * DTM_NS;
-  auto full = [&](int s_) { return bar + 8u * (uint32_t)s_; };
-  auto empty = [&](int s_) { return bar + 8u * (uint32_t)(DTM_NS + s_); };
+  const uint32_t bar = tc_smem_u32(barp), slot = bar + 8 * DTM_NBAR;
+  const uint32_t fullA = bar, emptyA = bar + 8 * DTM_NSA, fullB = bar + 16 * DTM_NSA, emptyB = fullB + 8 * DTM_NSB;
   if (tid < 128) bad[tid] = 0;
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (tid == 0) {
-      for (int s_ = 0; s_ < 2 * DTM_NS; ++s_) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u * (uint32_t)s_) : "memory");
+      for (int s_ = 0; s_ < DTM_NSA; ++s_) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fullA + 8u * s_), "r"(DTC_THREADS / 32) : "memory");   // one arrive per producer warp
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(emptyA + 8u * s_) : "memory");
+      }
+      for (int s_ = 0; s_ < DTM_NSB; ++s_) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(fullB + 8u * s_) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(emptyB + 8u * s_) : "memory");
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 16 * DTM_NS);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 8 * DTM_NBAR);
 
   const long long sig0 = (long long)blockIdx.x * TC_M;
   const int k0 = blockIdx.y * 128;
   const int NB = (n + DTC_KB - 1) / DTC_KB;
-  const unsigned char* my_img = img + 256 + (long long)blockIdx.y * NB * DTM_B_BYTES;
   const uint32_t smem0 = tc_smem_u32(smem);
-  if (tid == 0) {                                           // B images of the first two k blocks
-    for (int kb = 0; kb < 2 && kb < NB; ++kb)
-      tc_bulk_load(smem0 + (uint32_t)kb * DTM_STAGE + 16384, my_img + (long long)kb * DTM_B_BYTES, DTM_B_BYTES, full(kb));
-  }
-  const int arow = tid >> 2, aq = tid & 3;
-  const long long asig = sig0 + arow;
-  const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
-  const bool vec_ok = (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0;
-  int mybad = 0;
-  double cur[4], nxt[4];
-  auto fetch = [&](int kb, double (&dst)[4]) {
+  if (wid == DTC_THREADS / 32) {
+    // ---- control warp: TMA producer + MMA issuer (one thread)
+    if (lane == 0) {
+      const unsigned char* my_img = img + 256 + (long long)blockIdx.y * NB * DTM_B_BYTES;
+      for (int kb = 0; kb < DTM_PREFETCH && kb < NB; ++kb)
+        tc_bulk_load(smem0 + DTM_OFF_B + (uint32_t)(kb % DTM_NSB) * DTM_B_BYTES, my_img + (long long)kb * DTM_B_BYTES, DTM_B_BYTES,
+                     fullB + 8u * (kb % DTM_NSB));
+      for (int kb = 0; kb < NB; ++kb) {
+        const int k2 = kb + DTM_PREFETCH;
+        if (k2 < NB) {
+          const int s2 = k2 % DTM_NSB;
+          if (k2 >= DTM_NSB) tc_wait_bounded(emptyB + 8u * s2, (uint32_t)((k2 / DTM_NSB - 1) & 1));    // its previous image has been consumed
+          tc_bulk_load(smem0 + DTM_OFF_B + (uint32_t)s2 * DTM_B_BYTES, my_img + (long long)k2 * DTM_B_BYTES, DTM_B_BYTES, fullB + 8u * s2);
+        }
+        const int sa_ = kb % DTM_NSA, sb_ = kb % DTM_NSB;
+        tc_wait_bounded(fullA + 8u * sa_, (uint32_t)((kb / DTM_NSA) & 1));
+        tc_wait_bounded(fullB + 8u * sb_, (uint32_t)((kb / DTM_NSB) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem0 + (uint32_t)sa_ * DTM_A_BYTES, sb = smem0 + DTM_OFF_B + (uint32_t)sb_ * DTM_B_BYTES;
 #pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-      const int j = kb * DTC_KB + 8 * hlf + 2 * aq;
-      if (asig < nsig && j + 1 < n && vec_ok) {
-        const double2 v = *reinterpret_cast<const double2*>(ay + j);
-        dst[2 * hlf] = v.x; dst[2 * hlf + 1] = v.y;
-      } else {
-        dst[2 * hlf] = (asig < nsig && j < n) ? ay[j] : 0.0;
-        dst[2 * hlf + 1] = (asig < nsig && j + 1 < n) ? ay[j + 1] : 0.0;
+        for (int ks = 0; ks < DTC_KB / 8; ++ks) {
+          const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
+          const uint64_t dbh = tc_desc(sb + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sb + 16384 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
+          tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
+          tc_mma_tf32(tmem, dal, dbh, 1);
+          tc_mma_tf32(tmem, dah, dbl, 1);
+        }
+        tc_commit(emptyA + 8u * sa_);
+        tc_commit(emptyB + 8u * sb_);
       }
     }
-  };
-  fetch(0, cur);
-  for (int kb = 0; kb < NB; ++kb) {
-    const int st = kb % DTM_NS;
-    uint8_t* stage = smem + st * DTM_STAGE;
-    if (kb + 1 < NB) fetch(kb + 1, nxt);
-    if (kb >= DTM_NS) tc_wait_bounded(empty(st), (uint32_t)((kb / DTM_NS - 1) & 1));      // block kb-NS has been consumed
-    if (tid == 0 && kb + 2 < NB) {                          // keep two B images in flight
-      const int k2 = kb + 2, s2 = k2 % DTM_NS;
-      if (k2 >= DTM_NS) tc_wait_bounded(empty(s2), (uint32_t)((k2 / DTM_NS - 1) & 1));
-      tc_bulk_load(smem0 + (uint32_t)s2 * DTM_STAGE + 16384, my_img + (long long)k2 * DTM_B_BYTES, DTM_B_BYTES, full(s2));
-    }
-    {
+  } else {
+    // ---- producer warps: the A operand
+    const int arow = tid >> 2, aq = tid & 3;
+    const long long asig = sig0 + arow;
+    const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
+    const bool vec_ok = (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0;
+    int mybad = 0;
+    double cur[4], nxt[4];
+    auto fetch = [&](int kb, double (&dst)[4]) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int j = kb * DTC_KB + 8 * hlf + 2 * aq;
+        if (asig < nsig && j + 1 < n && vec_ok) {
+          const double2 v = *reinterpret_cast<const double2*>(ay + j);
+          dst[2 * hlf] = v.x; dst[2 * hlf + 1] = v.y;
+        } else {
+          dst[2 * hlf] = (asig < nsig && j < n) ? ay[j] : 0.0;
+          dst[2 * hlf + 1] = (asig < nsig && j + 1 < n) ? ay[j + 1] : 0.0;
+        }
+      }
+    };
+    fetch(0, cur);
+    for (int kb = 0; kb < NB; ++kb) {
+      const int st = kb % DTM_NSA;
+      uint8_t* stage = smem + st * DTM_A_BYTES;
+      if (kb + 1 < NB) fetch(kb + 1, nxt);
+      if (kb >= DTM_NSA) tc_wait_bounded(emptyA + 8u * st, (uint32_t)((kb / DTM_NSA - 1) & 1));      // block kb-3 has been consumed
       float hv[4], lv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -817,28 +853,16 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dft_tc_tma_kernel(const double
       const int o0 = (((aq >> 1) * TC_M + arow) << 1) + (aq & 1), o1 = (((2 + (aq >> 1)) * TC_M + arow) << 1) + (aq & 1);
       Ah2[o0] = make_float2(hv[0], hv[1]); Al2[o0] = make_float2(lv[0], lv[1]);
       Ah2[o1] = make_float2(hv[2], hv[3]); Al2[o1] = make_float2(lv[2], lv[3]);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      tc_wait_bounded(full(st), (uint32_t)((kb / DTM_NS) & 1));      // the TMA has landed this block's B image
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = smem0 + (uint32_t)st * DTM_STAGE;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) tc_arrive(fullA + 8u * st);
 #pragma unroll
-      for (int ks = 0; ks < DTC_KB / 8; ++ks) {
-        const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
-        const uint64_t dbh = tc_desc(sa + 16384 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sa + 32768 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
-        tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
-        tc_mma_tf32(tmem, dal, dbh, 1);
-        tc_mma_tf32(tmem, dah, dbl, 1);
-      }
-      tc_commit(empty(st));
+      for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
+    if (mybad) bad[arow] = 1;
   }
-  if (mybad) bad[arow] = 1;
-  tc_wait_bounded(empty((NB - 1) % DTM_NS), (uint32_t)(((NB - 1) / DTM_NS) & 1));
+  // the commit of the last block completes when every MMA has: the accumulator is final
+  tc_wait_bounded(emptyA + 8u * ((NB - 1) % DTM_NSA), (uint32_t)(((NB - 1) / DTM_NSA) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();                                         // bad[] complete
   if (tid < TC_M) {
@@ -882,7 +906,7 @@ int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long n
     if (int rc = check_launch("dft_image_kernel")) return rc;
     dft_image_seal_kernel<<<1, 1, 0, st>>>(W, (unsigned char*)image_ws);
     if (int rc = check_launch("dft_image_seal_kernel")) return rc;
-    dft_tc_tma_kernel<<<grid, DTC_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, (const unsigned char*)image_ws, mags, num_bins);
+    dft_tc_tma_kernel<<<grid, DTM_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, (const unsigned char*)image_ws, mags, num_bins);
     if (int rc = check_launch("dft_tc_tma_kernel")) return rc;
   } else {
     if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
