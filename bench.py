@@ -61,8 +61,8 @@ OTHER_SHAPES = {
                desc='configs[4]: 65536 streams x 10 s windows over all GPUs, ROI -> Butterworth -> Lomb-Scargle -> HR -> PTT + NCCL record gather'),
 }
 METRIC, UNIT = 'roi_sampled_frames_per_s', 'frames/s'
-# dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch (ncu --set full; profiles/r1w_c2_summary.md, same boxes)
-ROI_NCU_TRAFFIC_BYTES = 336.0e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch (ncu --set full; profiles/r2l_c2_summary.md: 331.6 + 5.6 MB, same boxes)
+ROI_NCU_TRAFFIC_BYTES = 337.2e6
 FRAME_PERIOD_MS = 1000.0 / 30.0
 
 
