@@ -333,14 +333,11 @@ class BatchedSignalProcessor:
         n_design = sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
         n_pre = 1 + n_design + (1 if n_design and self._dcache is not None else 0)     # filter + designs (+ cache probe)
         n_spec = 2 if self.transform == _cabi.PGRAM_LS else 1
-        if (self.transform == _cabi.PGRAM_WELCH and not self.store_arrays and 256 <= self.W <= 383
-                and os.environ.get('BPV_WELCH_TC', '') == '1'):
-            n_spec = 2                  # welch_tc_kernel (tensor cores) + welch_warp_kernel for the windows it flags
         if self.transform == _cabi.DFT_RFFT and 16 <= self.W <= 2048:
             env = os.environ.get('BPV_DFT_TC')
             interp = any(m in (_cabi.INTERP_LINEAR, _cabi.INTERP_CUBIC) for m in self.methods)
             if (env[:1] == '1') if env is not None else interp:
-                n_spec = 3              # dft_tc_kernel + dft_peak_kernel + spectrum_dense_kernel for the flagged windows
+                n_spec = 5              # dft_image + seal + dft_tc_tma + dft_peak kernels + spectrum_dense_kernel for the flagged windows
         n_push = 2 if _designed else 1
         self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P else 0)
         arrays = {}

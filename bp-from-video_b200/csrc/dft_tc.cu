@@ -205,220 +205,10 @@ __global__ void __launch_bounds__(TC_M, 1) dft256_tc_kernel(const float* __restr
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// PGRAM_WELCH on the tensor cores: scipy.signal.welch(y, fs) with every default (signal_processor.py:260) for windows
-// whose valid count n gives exactly one 256-sample segment (256 <= n < 384: nperseg = 256, noverlap = 128 ->
-// (n - 128) / 128 == 1), which is every steady-state window of the 300-sample configurations.
-//   prologue  each of the 16 warps prepares 8 of the CTA's 128 signals: coalesced window loads held in registers,
-//             ballot compaction of the finite samples, segment mean, Hann, and the fp32 segment written straight into
-//             the K-major operand tile; per-row fs / mean kept in shared memory
-//   contract  tc_dft256<.., false>: 32 tcgen05.mma kind::tf32 (M 128, N 256, K 8) into a 128 x 256 fp32 TMEM accumulator
-//   epilogue  thread = signal (warps 0-3 own the four TMEM lane quarters): one-sided density from the accumulator row,
-//             coarse maximum, candidate list = every bin within WELCH_TC_BAND of it
-//   decide    each warp re-reads its 8 windows and evaluates the candidate bins as float64 dot products, so the reported
-//             peak bin and value are float64 decisions (first-max rule), exactly as the Lomb-Scargle and xcorr kernels do.
-// Signals outside the one-segment range (warm-up) are flagged num_bins = -2 and taken by welch_warp_kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int WTC_THREADS = 512;
-constexpr int WTC_MAXW = 383;                          // largest window with at most one segment
-constexpr int WTC_REG = (WTC_MAXW + 31) / 32;           // window samples per lane
-constexpr int WTC_MAXC = 7;                             // candidate bins re-evaluated per window before falling back
-constexpr float WELCH_TC_BAND = 0.10f;                  // relative band below the coarse maximum (single-pass tf32: <= 3.4 % per bin)
-constexpr int WTC_OFF_MEAN = TC_SMEM;                   // double [128]
-constexpr int WTC_OFF_FS = WTC_OFF_MEAN + 128 * 8;      // double [128]
-constexpr int WTC_OFF_N = WTC_OFF_FS + 128 * 8;         // int [128]: 1 = eligible row
-constexpr int WTC_OFF_SW = WTC_OFF_N + 128 * 4;         // double: sum of squared window
-constexpr int WTC_SMEM = WTC_OFF_SW + 16;
-
-__global__ void __launch_bounds__(WTC_THREADS, 1) welch_tc_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
-                                                                  int W, long long nsig,
-                                                                  int32_t* __restrict__ num_bins, int32_t* __restrict__ peak_idx,
-                                                                  double* __restrict__ peak_freq, double* __restrict__ peak_mag) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  double2* tw = reinterpret_cast<double2*>(smem + TC_OFF_TW);
-  float* Z = reinterpret_cast<float*>(smem + TC_OFF_Z);
-  double* s_mean = reinterpret_cast<double*>(smem + WTC_OFF_MEAN);
-  double* s_fs = reinterpret_cast<double*>(smem + WTC_OFF_FS);
-  int* s_ok = reinterpret_cast<int*>(smem + WTC_OFF_N);
-  double* s_sw = reinterpret_cast<double*>(smem + WTC_OFF_SW);
-  for (int i = tid; i < 256; i += WTC_THREADS) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
-  const uint32_t tmem = tc_setup(smem);                 // CTA barrier inside: the twiddle table is complete after it
-  if (wid == 0) {                                       // sum of the squared periodic Hann window (as welch_warp_kernel)
-    double sw = 0.0;
-    for (int i = lane; i < 256; i += 32) { const double wj = 0.5 - 0.5 * tw[i].x; sw = fma(wj, wj, sw); }
-    sw = warp_sum(sw);
-    if (lane == 0) *s_sw = sw;
-  }
-  const long long sig0 = (long long)blockIdx.x * TC_M;
-  // ---- prologue: warp wid prepares rows wid*8 .. wid*8+7
-  const unsigned lt = (1u << lane) - 1u;
-  for (int q = 0; q < TC_M / (WTC_THREADS / 32); ++q) {
-    const int row = wid * (TC_M / (WTC_THREADS / 32)) + q;
-    const long long sig = sig0 + row;
-    double xr[WTC_REG], yr[WTC_REG];
-    if (sig < nsig) {
-      const double* px = proc_x + sig * W;
-      const double* py = proc_y + sig * W;
-#pragma unroll
-      for (int u = 0; u < WTC_REG; ++u) {
-        const int k = lane + 32 * u;
-        xr[u] = k < W ? px[k] : nan_f64();
-        yr[u] = k < W ? py[k] : nan_f64();
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < WTC_REG; ++u) { xr[u] = nan_f64(); yr[u] = nan_f64(); }
-    }
-    int n = 0, m = 0, ci[WTC_REG];
-    double xfirst = 0.0, xlast = 0.0;
-#pragma unroll
-    for (int u = 0; u < WTC_REG; ++u) {
-      const bool fx = isfinite(xr[u]), fy = isfinite(yr[u]);
-      const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
-      if (bx) {
-        const double xf = __shfl_sync(0xffffffffu, xr[u], __ffs(bx) - 1), xl = __shfl_sync(0xffffffffu, xr[u], 31 - __clz(bx));
-        if (m == 0) xfirst = xf;
-        xlast = xl;
-      }
-      ci[u] = fy ? n + __popc(by & lt) : -1;            // compacted index of this sample
-      n += __popc(by); m += __popc(bx);
-    }
-    const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
-    const bool guard = n >= 2 && isfinite(fs);          // signal_processor.py:252
-    const bool ok = guard && n >= 256 && sig < nsig;    // one 256-sample segment (n < 384 by the host's W <= 383)
-    double a = 0.0;
-#pragma unroll
-    for (int u = 0; u < WTC_REG; ++u) if (ci[u] >= 0 && ci[u] < 256) a += yr[u];
-    const double mean = warp_sum(a) / 256.0;
-#pragma unroll
-    for (int u = 0; u < WTC_REG; ++u) {
-      const int j = ci[u];
-      if (ok && j >= 0 && j < 256) Z[(j >> 2) * (TC_M * 4) + row * 4 + (j & 3)] = (float)((yr[u] - mean) * (0.5 - 0.5 * tw[j].x));
-    }
-    if (!ok) {                                          // the tensor core still reads the row: zeros
-      for (int j = lane; j < 256; j += 32) Z[(j >> 2) * (TC_M * 4) + row * 4 + (j & 3)] = 0.f;
-      if (lane == 0 && sig < nsig) {
-        if (guard) num_bins[sig] = -2;                  // short window: welch_warp_kernel takes it
-        else { num_bins[sig] = 0; peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
-      }
-    }
-    if (lane == 0) { s_mean[row] = mean; s_fs[row] = fs; s_ok[row] = ok ? 1 : 0; }
-  }
-  __syncthreads();
-  // ---- contraction on the tensor cores
-  tc_dft256<WTC_THREADS, false>(smem, tmem);
-  // ---- epilogue: thread = signal row (warps 0..3 <-> TMEM lanes 0..127)
-  if (tid < TC_M) {
-    const int row = tid;
-    const bool ok = s_ok[row] != 0;
-    const double fs = s_fs[row];
-    const float scale = ok ? (float)(1.0 / (fs * *s_sw)) : 0.f;
-    // pass 1: fp32 maximum of the one-sided density
-    float pmax = -INFINITY;
-    for (int c = 0; c < 4; ++c) {
-      float re[32], im[32];
-      tc_load32(tmem, 32 * c, re);
-      tc_load32(tmem, 128 + 32 * c, im);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = 32 * c + i;
-        float pw = k == 0 ? re[i] * re[i] * scale : 2.f * (re[i] * re[i] + im[i] * im[i]) * scale;
-        pmax = fmaxf(pmax, pw);
-        if (k == 0) pmax = fmaxf(pmax, im[0] * im[0] * scale);       // column 128 = Re X[128]
-      }
-    }
-    // pass 2: list the candidate bins (within WELCH_TC_BAND of the fp32 maximum) of this row in shared memory (the chunk
-    // buffers are free now).  tcgen05.ld is warp-collective: every lane executes the loads, uniform control flow.
-    const float thr = pmax - WELCH_TC_BAND * fabsf(pmax);
-    int nc = 0;
-    int* clist = reinterpret_cast<int*>(smem + TC_OFF_CHUNK) + row * (WTC_MAXC + 1);
-    for (int c = 0; c < 5; ++c) {
-      float re[32], im[32];
-      unsigned cand = 0;
-      __syncwarp();
-      if (c < 4) {
-        tc_load32(tmem, 32 * c, re);
-        tc_load32(tmem, 128 + 32 * c, im);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = 32 * c + i;
-          const float pw = k == 0 ? re[i] * re[i] * scale : 2.f * (re[i] * re[i] + im[i] * im[i]) * scale;
-          if (pw >= thr) cand |= 1u << i;
-        }
-      } else {
-        tc_load32(tmem, 128, im);                                 // bin 128
-        if (im[0] * im[0] * scale >= thr) cand = 1u;
-      }
-      if (!ok) cand = 0;
-      while (cand) {
-        const int i = __ffs(cand) - 1;
-        cand &= cand - 1;
-        if (nc < WTC_MAXC) clist[1 + nc] = c < 4 ? 32 * c + i : 128;
-        ++nc;
-      }
-    }
-    clist[0] = ok ? nc : 0;
-  }
-  __syncthreads();
-  // ---- float64 decision: warp wid re-reads its 8 windows (coalesced), rebuilds the compaction and evaluates the
-  // candidate bins of each as float64 dot products against the table; first-max rule.  A window with more than
-  // WTC_MAXC candidates (flat spectrum) is handed to the float64 kernel (num_bins = -2).
-  for (int q = 0; q < TC_M / (WTC_THREADS / 32); ++q) {
-    const int row = wid * (TC_M / (WTC_THREADS / 32)) + q;
-    const long long sig = sig0 + row;
-    const int* clist = reinterpret_cast<const int*>(smem + TC_OFF_CHUNK) + row * (WTC_MAXC + 1);
-    const int nc = clist[0];
-    if (nc == 0) continue;                                        // not a tensor-core row (warp uniform)
-    if (nc > WTC_MAXC) { if (lane == 0) num_bins[sig] = -2; continue; }
-    const double* py = proc_y + sig * W;
-    double yr[WTC_REG];
-#pragma unroll
-    for (int u = 0; u < WTC_REG; ++u) { const int k = lane + 32 * u; yr[u] = k < W ? py[k] : nan_f64(); }
-    const double mean = s_mean[row], fs = s_fs[row];
-    double zr[WTC_REG]; int ci[WTC_REG];
-    int n = 0;
-#pragma unroll
-    for (int u = 0; u < WTC_REG; ++u) {
-      const bool fy = isfinite(yr[u]);
-      const unsigned by = __ballot_sync(0xffffffffu, fy);
-      const int j = n + __popc(by & lt);
-      ci[u] = fy && j < 256 ? j : -1;
-      zr[u] = ci[u] >= 0 ? (yr[u] - mean) * (0.5 - 0.5 * tw[ci[u]].x) : 0.0;
-      n += __popc(by);
-    }
-    const double scale64 = 1.0 / (fs * *s_sw);
-    double best = -INFINITY; int bi = 0x7fffffff;
-    for (int e = 0; e < nc; ++e) {
-      const int k = clist[1 + e];
-      double sre = 0.0, sim = 0.0;
-#pragma unroll
-      for (int u = 0; u < WTC_REG; ++u) {
-        if (ci[u] >= 0) { const double2 t = tw[(ci[u] * k) & 255]; sre = fma(zr[u], t.x, sre); sim = fma(zr[u], t.y, sim); }
-      }
-      sre = warp_sum(sre); sim = warp_sum(sim);
-      double pw = (sre * sre + sim * sim) * scale64;
-      if (k >= 1 && k < 128) pw *= 2.0;
-      if (isfinite(pw) && (pw > best || (pw == best && k < bi))) { best = pw; bi = k; }
-    }
-    if (lane == 0) {
-      const double fval = 1.0 / (256.0 * (1.0 / fs));             // rfftfreq(256, d=1/fs)[k] = k * (1/(256*d))
-      num_bins[sig] = 129;
-      if (bi != 0x7fffffff) { peak_idx[sig] = bi; peak_freq[sig] = (double)bi * fval; peak_mag[sig] = best; }
-      else { peak_idx[sig] = -1; peak_freq[sig] = nan_f64(); peak_mag[sig] = nan_f64(); }
-    }
-  }
-  tc_teardown(tmem);
-}
-
-int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
-                    double* peak_freq, double* peak_mag, cudaStream_t st) {
-  if (int rc = ensure_dyn_smem((const void*)welch_tc_kernel, WTC_SMEM)) return rc;
-  welch_tc_kernel<<<(unsigned)((nsig + TC_M - 1) / TC_M), WTC_THREADS, WTC_SMEM, st>>>(proc_x, proc_y, W, nsig, num_bins, peak_idx,
-                                                                                      peak_freq, peak_mag);
-  return check_launch("welch_tc_kernel");
-}
-
+// (A Welch periodogram on this block — single-pass tf32 candidates + float64 decision, `welch_tc_kernel` — was built in
+// round 1 and measured at 82 + 8 us against 76 us for the float64 shared-memory FFT kernel per 16 384 windows: the
+// contraction is 23 % of it, the per-window front end and the float64 decision are the same scalar work the FFT kernel
+// does.  It did not win and was removed in round 2; profiles/r1i_welch_tc_summary.md keeps the measurement.)
 
 // ---------------------------------------------------------------------------------------------
 // DFT_RFFT on the tensor cores (signal_processor.py:254-258: mags = 2 |rfft(y)| / n) for windows whose n valid samples

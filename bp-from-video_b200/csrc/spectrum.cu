@@ -20,8 +20,6 @@ namespace bpv {
 long long dft_tc_image_bytes(int W);
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
                   int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, cudaStream_t st);
-int launch_welch_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int32_t* num_bins, int32_t* peak_idx,
-                    double* peak_freq, double* peak_mag, cudaStream_t st);
 
 constexpr float LS_DELTA = 1.0e-4f;     // candidate band below the fp32 maximum (PSD is in [0, 1])
 constexpr int LS_SMALL_N = 24;          // below this every bin is evaluated in float64
@@ -302,7 +300,8 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const dou
   const int W = p.window, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double2* tw = reinterpret_cast<double2*>(sm);                 // [256] exp(+2*pi*i*k/256) as (cos, sin)
   const long long sig = (long long)blockIdx.x * WELCH_WPB + wid;
-  // only_flagged: second pass behind welch_tc_kernel, which marks the windows it does not take with num_bins = -2
+  // only_flagged: second pass behind a kernel that marks the windows it does not take with num_bins = -2 (unused since the
+  // Welch tensor-core path was removed; kept for the DFT path's twin in spectrum_dense_kernel)
   const bool mine = sig < nsig && (!only_flagged || num_bins[sig] == -2);
   if (!__syncthreads_or(mine)) return;
   for (int i = tid; i < 256; i += blockDim.x) { double s_, c_; sincospi((double)i / 128.0, &s_, &c_); tw[i] = make_double2(c_, s_); }
@@ -805,17 +804,7 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
     if (p->transform == BPV_PGRAM_WELCH && W <= 512) {   // warp per signal (x staging needs W <= 512 doubles)
       const size_t smw = (size_t)(512 + WELCH_WPB * welch_warp_doubles(W)) * sizeof(double);
       if (int rc = ensure_dyn_smem((const void*)welch_warp_kernel, smw)) return rc;
-      // BPV_WELCH_TC=1: peak-only calls on one-segment windows run the 256-point DFT on the tensor cores (dft_tc.cu:
-      // tcgen05 candidates + float64 decision, same peaks bit for bit); the warp kernel then only takes the windows that
-      // kernel flagged (warm-up, n < 256).  Opt-in: measured 82 + 8 us against 76 us for the float64 FFT kernel per
-      // 16 384 windows — the contraction is 19 us of that, the per-window front end (gather, compaction, detrend, window)
-      // and the float64 decision dominate both kernels (profiles/README.md).
-      int only_flagged = 0;
-      const char* tc_env = getenv("BPV_WELCH_TC");
-      if (!spec_mag && W >= 256 && W <= 383 && tc_env && tc_env[0] == '1') {
-        if (int rc = launch_welch_tc(proc_x, proc_y, W, nsig, num_bins, peak_idx, peak_freq, peak_mag, st)) return rc;
-        only_flagged = 1;
-      }
+      const int only_flagged = 0;
       welch_warp_kernel<<<(unsigned)((nsig + WELCH_WPB - 1) / WELCH_WPB), 32 * WELCH_WPB, smw, st>>>(
           proc_x, proc_y, *p, max_bins, nsig, only_flagged, spec_f, spec_mag, num_bins, peak_idx, peak_freq, peak_mag);
       return check_launch("welch_warp_kernel");

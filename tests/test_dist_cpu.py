@@ -49,3 +49,48 @@ def test_gather_equals_single_rank_result(S, ragged):
         p.join(60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def _worker_async(rank, world, port, J, q):
+    """RecordGather over gloo: the gather launched at step k is handed over at step k + 1 (int32 24-byte records)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(here, 'bp-from-video_b200'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from bpv import dist as bd
+    bd.init_from_env('gloo')
+    rg = bd.RecordGather()
+    ok = rg.collect() is None and rg.flush() is None
+    expect = lambda k: torch.cat([torch.full((J, 6), 1000 * r + k, dtype=torch.int32) for r in range(world)])
+    for k in range(5):
+        rg.launch(torch.full((J, 6), 1000 * rank + k, dtype=torch.int32))
+        prev = rg.collect()
+        ok &= (prev is None) if k == 0 else bool(torch.equal(prev, expect(k - 1)))
+    ok &= bool(torch.equal(rg.flush(), expect(4)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_record_gather_hands_results_over_one_step_later():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_worker_async, args=(r, 2, port, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
+
+def test_record_gather_passes_through_without_a_process_group():
+    from bpv.dist import RecordGather, _parse_cpulist
+    rg = RecordGather()
+    a, b = torch.arange(12).reshape(2, 6), torch.arange(12, 24).reshape(2, 6)
+    rg.launch(a)
+    assert rg.collect() is None
+    rg.launch(b)
+    assert torch.equal(rg.collect(), a) and torch.equal(rg.flush(), b)
+    assert _parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11} and _parse_cpulist('') == set()

@@ -107,35 +107,6 @@ def test_dft256_tensor_core_block_matches_numpy():
         assert err.max() < 1e-5, (rows, err.max())
 
 
-def test_welch_tensor_core_path_equals_float64_path(monkeypatch):
-    """BPV_WELCH_TC=1: peak-only Welch calls on one-segment windows (256 <= n < 384) run the 256-point DFT on the tensor
-    cores (tcgen05, tf32) to select candidate bins and decide among them in float64: the reported peak bin must equal the
-    all-float64 kernel's on every window, the peak value to float64 rounding; shorter windows fall through to the float64
-    kernel."""
-    from bpv import ops
-    monkeypatch.setenv('BPV_WELCH_TC', '1')
-    S, R, W = 700, 2, 300
-    fill = [W, W - 1, W - 7, 290, 270, 257, 256, 255, 200, 64, 3, 2, 1, 0]
-    fill = [fill[i % len(fill)] for i in range(S)]
-    t, y = make_windows(4242, S, W, R, fps=30.0, fill=fill)
-    with np.errstate(all='ignore'):
-        t0 = np.where(np.isfinite(t).any(axis=1), np.nanmin(np.where(np.isfinite(t), t, np.inf), axis=1), 0.0)
-    y = y + 0.8 * np.sin(2 * np.pi * (0.9 + 2.5 * np.arange(S)[:, None, None] / S) * (t - t0[:, None])[:, None, :])
-    px = np.repeat(t[:, None, :], R, axis=1)            # x stays finite where y is NaN (dropped detection)
-    p = params(S, R, W, [], orc.PGRAM_WELCH)
-    dx, dy = torch.from_numpy(px.copy()).cuda(), torch.from_numpy(y.copy()).cuda()
-    ref = {k: (v.clone() if v is not None else None) for k, v in ops.window_spectrum(dx, dy, p, store=True).items()}
-    got = ops.window_spectrum(dx, dy, p, store=False)
-    torch.cuda.synchronize()
-    assert torch.equal(got['num_bins'], ref['num_bins'])
-    assert torch.equal(got['peak_idx'], ref['peak_idx'])
-    assert torch.equal(torch.isnan(got['peak_freq']), torch.isnan(ref['peak_freq']))
-    okm = ~torch.isnan(ref['peak_freq'])
-    assert torch.equal(got['peak_freq'][okm], ref['peak_freq'][okm])
-    assert torch.allclose(got['peak_mag'][okm], ref['peak_mag'][okm], rtol=1e-12, atol=0)
-    assert int((ref['num_bins'] == 129).sum()) > S // 2  # windows with n >= 256 took the tensor-core path
-
-
 METHOD_SETS = [
     [], [orc.DIFF_1], [orc.DIFF_2], [orc.DETREND_CONST], [orc.DETREND_LINEAR], [orc.INTERP_LINEAR], [orc.INTERP_CUBIC],
     [orc.FILTER_BUTTER], [orc.FILTER_FIR],
