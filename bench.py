@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload at N=1 = BASELINE.json configs[1] ("c2"): 256 streams x 1080p, CHROM_GREEN ROI sampling,
-[DETREND_LINEAR, FILTER_FIR], Welch HR, W=300, T=32 frames per stream resident in HBM per step (51 GB,
-far larger than the 126 MB L2, so nothing is cached between steps).  One step = the whole hot path over
+[DETREND_LINEAR, FILTER_FIR], Welch HR, W=300, T=64 frames per stream resident in HBM per step (102 GB of the
+180 GB, far larger than the 126 MB L2, so nothing is cached between steps; `--frames-per-step 32` = the round-1 depth:
+the launch ramp / tail and ~80 MB of dirty window scratch left in L2 cost F1 0.64 of the HBM peak there against 0.74 at 64,
+profiles/r2q_discard_depth_ab.txt).  One step = the whole hot path over
 one batch: ROI-sample S*T frames, push, and evaluate the sliding window after EVERY frame, as the
 reference's process() does (S*T window jobs -> R bpm + P ptt each).  metric = ROI-sampled frames/s.
 N>1: every rank owns S streams (weak scaling, no data-path collective); the 24-byte per-job records are
@@ -38,7 +40,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: S, H, W, T, window, channel, methods, transform, fps, kwargs
-    'c2': dict(S=256, H=1080, W=1920, T=32, window=300, channel='CHROM_GREEN', methods=['DETREND_LINEAR', 'FILTER_FIR'],
+    'c2': dict(S=256, H=1080, W=1920, T=64, window=300, channel='CHROM_GREEN', methods=['DETREND_LINEAR', 'FILTER_FIR'],
                transform='PGRAM_WELCH', fps=30.0, kw={},
                desc='BASELINE configs[1]: 256 streams 1080p 30 fps, chrom-green ROI + detrend + FIR + Welch HR'),
     'c2small': dict(S=32, H=1080, W=1920, T=8, window=300, channel='CHROM_GREEN', methods=['DETREND_LINEAR', 'FILTER_FIR'],
@@ -80,7 +82,7 @@ def shape_config(name, wl, world=1, windows='every_frame'):
     return {'workload': name, 'desc': wl['desc'], 'streams_per_gpu': S, 'frames_per_stream_per_step': T,
             'frame': f"{wl['W']}x{wl['H']}x3 u8 BGR", 'window': wl['window'], 'rois': 2, 'windows': windows,
             'window_jobs_per_step': jobs * world,
-            'l2_policy': 'inputs (51 GB of frames per GPU) larger than the 126 MB L2' if name == 'c2' else 'inputs larger than L2',
+            'l2_policy': f"inputs ({S * T * wl['H'] * wl['W'] * 3 / 1e9:.0f} GB of frames per GPU) larger than the 126 MB L2",
             'parallelism': f'streams sharded x{world}, NCCL all-gather of per-stream records' if world > 1 else 'single GPU'}
 
 
@@ -800,6 +802,7 @@ def main():
     ap.add_argument('--impl', default='bpv', choices=['bpv', 'reference'])
     ap.add_argument('--workload', default='c2', choices=list(WORKLOADS))
     ap.add_argument('--windows', default='every_frame', choices=['every_frame', 'last'])
+    ap.add_argument('--frames-per-step', type=int, default=0, help='frames per stream per step (batch depth T); 0 = the workload default')
     ap.add_argument('--ref-frames', type=int, default=64, help='reference arm: at most this many frames per core per step')
     ap.add_argument('--ref-budget-s', type=float, default=90.0, help='reference arm: CPU seconds per core for all steps')
     ap.add_argument('--cpu-frames', type=int, default=400, help='cpu_baseline of the GPU arm: frames per core')
@@ -809,7 +812,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-other', action='store_true', help='skip the other_shapes / latency blocks')
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames_per_step > 0:
+        wl['T'] = args.frames_per_step
     if args.impl == 'reference':
         run_reference(args, wl)
     else:

@@ -119,8 +119,7 @@ class BatchedSignalProcessor:
         self._samples = [torch.empty((self.S, self.Tmax, self.R), dtype=f64, device=dev) for _ in range(self._nbuf)]
         # the processed windows are results only when the arrays are stored; otherwise scratch between F2 and F3 / F4
         nproc = self._nbuf if self.store_arrays else 1
-        self._proc = [(torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev),
-                       torch.empty((Jmax, self.R, self.W), dtype=f64, device=dev)) for _ in range(nproc)]
+        self._proc = [torch.empty((2, Jmax, self.R, self.W), dtype=f64, device=dev) for _ in range(nproc)]   # [x | y]
         self._status = [torch.empty((Jmax, self.R), dtype=torch.int32, device=dev) for _ in range(self._nbuf)]
         self._spec = [None] * self._nbuf
         self._xc = [None] * self._nbuf
@@ -138,6 +137,9 @@ class BatchedSignalProcessor:
             design_cache = os.environ.get('BPV_DESIGN_CACHE', '1') != '0'
         self._dcache = ops.new_design_cache(dev) if design_cache else None
         self._dcache_sig = None
+        # measured (profiles/r2q_discard_depth_ab.txt): at 8192 jobs per step the discard saves 2.2 us of F1 and costs 4 us itself; at
+        # 16 384 jobs the scratch (157 MB) no longer fits L2 and has been written back before F1 starts -> off by default
+        self.discard_scratch = os.environ.get('BPV_DISCARD', '0') == '1'
         self._side = None
         self._ev = None
         # sg_bpm / sg_ptt histories and their running means on the device (0 = off)
@@ -298,8 +300,8 @@ class BatchedSignalProcessor:
         head0 = g0 if self.windows == EVERY_FRAME else g0 + T - 1
         p = self._params(head0, 1, jobs)
         J = S * jobs
-        pxb, pyb = self._proc[turn % len(self._proc)]
-        px, py, st = pxb[:J], pyb[:J], self._status[turn][:J]
+        proc = self._proc[turn % len(self._proc)]
+        px, py, st = proc[0, :J], proc[1, :J], self._status[turn][:J]
         has_filter = any(m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR) for m in self.methods)
         if _designed:
             main.wait_event(self._ev['design'])
@@ -330,6 +332,13 @@ class BatchedSignalProcessor:
             sp = ops.window_spectrum(px, py, p, store=self.store_arrays, workspace=self._ws_spec, out=spo)
             xc = ops.window_xcorr(px, py, p, store=self.store_arrays, out=xco)
         self._spec[turn], self._xc[turn] = sp, xc
+        if not self.store_arrays and self.discard_scratch:
+            # the processed windows are dead now: drop their dirty L2 lines instead of letting the next step's ROI sampling
+            # push them out to DRAM (F1 64.5 -> 69.7 us with 80 MB of dirty scratch in L2, profiles/r2p_f1_dirty.txt)
+            if J == self._Jmax:
+                ops.scratch_discard(proc)
+            else:
+                ops.scratch_discard(px, py)
         n_design = sum(1 for m in set(self.methods) if m in (_cabi.FILTER_BUTTER, _cabi.FILTER_FIR))
         n_pre = 1 + n_design + (1 if n_design and self._dcache is not None else 0)     # filter + designs (+ cache probe)
         n_spec = 2 if self.transform == _cabi.PGRAM_LS else 1
@@ -340,6 +349,8 @@ class BatchedSignalProcessor:
                 n_spec = 5              # dft_image + seal + dft_tc_tma + dft_peak kernels + spectrum_dense_kernel for the flagged windows
         n_push = 2 if _designed else 1
         self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P else 0)
+        if not self.store_arrays and self.discard_scratch:
+            self.launches_per_step += 1 if J == self._Jmax else 2
         arrays = {}
         if self.store_arrays:
             arrays = dict(proc_x=px, proc_y=py, freqs=sp['freqs'], mags=sp['mags'], num_bins=sp['num_bins'],

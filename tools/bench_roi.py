@@ -19,6 +19,7 @@ ap.add_argument('--hint', type=int, default=0)
 ap.add_argument('--mode', type=int, default=1)
 ap.add_argument('--l2gran', type=int, default=0)
 ap.add_argument('--host', action='store_true', help='frames in pinned host memory (zero-copy reads over PCIe)')
+ap.add_argument('--dirty', type=int, default=0, help='MB of an L2-resident scratch buffer rewritten (left dirty in L2) before every timed launch')
 ap.add_argument('--box', default='', help='w,h: fixed-size boxes at random positions instead of the synthetic forehead/palm boxes')
 a = ap.parse_args()
 N, H, W = a.frames, a.H, a.W
@@ -67,13 +68,25 @@ for _ in range(3):
     ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
 torch.cuda.synchronize()
 print('checksum', repr(float(out.nan_to_num().double().sum().item())), int(out.isnan().sum().item()))
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
-ev[0].record()
-for i in range(a.iters):
-    ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
-    ev[i + 1].record()
-torch.cuda.synchronize()
-ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
+if a.dirty:
+    scratch = torch.zeros(a.dirty << 20, dtype=torch.uint8, device='cuda')
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters)]
+    for i in range(a.iters):
+        scratch.add_(1)                      # read-modify-write: the whole buffer is dirty in L2 when F1 starts
+        e0[i].record()
+        ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
+        e1[i].record()
+    torch.cuda.synchronize()
+    ts = [e0[i].elapsed_time(e1[i]) for i in range(a.iters)]
+else:
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
+    ev[0].record()
+    for i in range(a.iters):
+        ops.roi_sample(frames, boxes, a.mode, roi_pixels_hint=hint, out_value=out)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)]
 t = float(np.median(ts))
 print(f'frames={N} {W}x{H} hint={hint} roi_bytes={nbytes/1e6:.1f} MB  median {t*1e3:.1f} us  min {min(ts)*1e3:.1f} us '
       f'-> {nbytes/t/1e6:.1f} GB/s median, {nbytes/min(ts)/1e6:.1f} GB/s best, {N/t*1e3:.0f} frames/s')
