@@ -38,4 +38,37 @@ __device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c,
   }
 }
 
+// Circular variant for the full cross-correlation (F4): X holds the PERIODIC extension of the n-sample operand, so one
+// sweep over the K taps visits, for output r of tile q, first the taps of lag li = RT*q - 1 + r (operand indices li - k >= 0)
+// and — after the operand index wraps below zero, i.e. before tap k = RT*q + r — the taps of lag li + n.  The two lag
+// ranges are complementary (li + 1 and n - 1 - li taps), so every lane does exactly K taps whatever its lags are: a
+// linear sweep gives the centre lanes n taps and the outer lanes almost none, and the warp pays for the longest.
+// At the wrap the accumulator of output r is moved to first[r] and cleared; on return acc[r] holds lag li + n.
+// Same ascending tap order per lag as the linear form.  j0 % RT == 0, j0 - K >= 0, q < K / RT.
+// LDC != 0: the leading dimension as a compile-time constant (the operand loads then use immediate offsets from one base
+// register instead of an address computation per load).
+template <int RT, int LDC, typename T>
+__device__ __forceinline__ void corr_tile_wrap(T (&acc)[RT], T (&first)[RT], const T* __restrict__ c, int K,
+                                               const T* __restrict__ XT, int LD_rt, int j0, int q) {
+  const int LD = LDC ? LDC : LD_rt;
+  const int col0 = j0 / RT;
+  T w[RT];
+#pragma unroll
+  for (int s = 0; s < RT; ++s) w[s] = XT[s * LD + col0];
+  const int nb = K / RT;
+  for (int kb = 0; kb < nb; ++kb) {
+    const T* cc = c + kb * RT;
+    const T* xn = XT + (col0 - kb - 1);
+    const bool wrap = kb == q;
+#pragma unroll
+    for (int kk = 0; kk < RT; ++kk) {
+      if (wrap) { first[kk] = acc[kk]; acc[kk] = (T)0; }      // output kk wraps before tap RT*q + kk
+      const T ck = cc[kk];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r] = fma(ck, w[(r - kk + RT) % RT], acc[r]);
+      w[RT - 1 - kk] = xn[(RT - 1 - kk) * LD];
+    }
+  }
+}
+
 }  // namespace bpv

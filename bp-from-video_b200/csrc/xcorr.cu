@@ -180,17 +180,18 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
 // ---------------------------------------------------------------------------------------------
 // Warp-per-pair version (default): the CTA-per-pair kernel above spends most of its time in __syncthreads between short
 // phases (staging, single-warp compaction, five block reductions, peak search: the tile phase is 18 % of its samples).
-// Here one warp owns a (job, pair): every phase is warp-local (ballot compaction, shuffle reductions), each lane owns ONE
-// tile of XW_RT = 20 consecutive lags so a 300-sample window (599 lags) is a single round of the register-tiled sliding
-// dot product (2 LDS per 20 FFMA), and the float64 re-evaluation of the candidate lags is a warp-cooperative dot product.
+// Here one warp owns a (job, pair): every phase is warp-local (ballot compaction, shuffle reductions), each lane owns the
+// XW_RT = 10 lag pairs (li, li + n) of one tile, so a 300-sample window (599 lags) is a single round of the register-tiled
+// circular sliding dot product (2 LDS + 2 predicated moves per 10 FFMA, n taps per lane), and the float64 re-evaluation of
+// the candidate lags is a warp-cooperative dot product.
 // smem per warp: doubles a64[W] | b64[W]; u16 pos[W]; floats cv[2W] | c[K] | XT[RT * LD]
 // ---------------------------------------------------------------------------------------------
-constexpr int XW_RT = 20;
+constexpr int XW_RT = 10;
 struct XwLayout { int b64, pos, cv, c, xt, total, K, LD; };
 __host__ __device__ inline XwLayout xw_layout(int W) {
   XwLayout L;
-  L.K = (W + XW_RT - 1) / XW_RT * XW_RT;
-  L.LD = (L.K + 2 * W + XW_RT) / XW_RT + 2;
+  L.K = (W + XW_RT - 1) / XW_RT * XW_RT;                 // taps, padded to the tile
+  L.LD = (2 * (L.K / XW_RT) + 2) | 1;                    // columns of the de-interleaved periodic operand (odd: no bank conflicts)
   int o = W * 8;
   L.b64 = o; o += W * 8;
   L.pos = o; o += (W * 2 + 15) / 16 * 16;
@@ -201,6 +202,13 @@ __host__ __device__ inline XwLayout xw_layout(int W) {
   return L;
 }
 
+// COARSE pass layout (corr_tile.cuh, corr_tile_wrap):  corr[li] = sum_m c[m] a[li - m]  (c[m] = b[n-1-m], 0 <= li - m < n).
+// Lags li and li + n use complementary tap ranges, so a lane owns the lag PAIRS li = RT*tile - 1 + r, r = 0..RT-1 and sweeps the
+// K taps once over the periodic extension AA[t] = a[t mod n], t in [-n, n), stored at X[t + K + RT + 1]: n multiply-adds per
+// output pair for every lane (a 300-sample window: 30 lanes x 10 pairs, one round), where one tile of consecutive lags per
+// lane made the warp wait for the centre lanes' n taps per lag.
+// LDC = the operand buffer's leading dimension when it is one of the specialised window sizes (0 = run-time value)
+template <int LDC>
 __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                          const bpv_window_params p, const XwLayout Lw, long long npairs,
                                                          float* __restrict__ corr_lag, float* __restrict__ corr_val,
@@ -228,11 +236,9 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   float* cv = reinterpret_cast<float*>(sm + Lw.cv);
   float* c = reinterpret_cast<float*>(sm + Lw.c);
   float* XT = reinterpret_cast<float*>(sm + Lw.xt);
-  const int Kw = Lw.K, LD = Lw.LD;
-  // stage both windows (independent coalesced loads), clear the fp32 operand buffers
+  const int LD = LDC ? LDC : Lw.LD;
+  // stage both windows (independent coalesced loads)
   for (int k = lane; k < W; k += 32) { a64[k] = ya_g[k]; b64[k] = yb_g[k]; }
-  for (int i = lane; i < Kw; i += 32) c[i] = 0.f;
-  for (int i = lane; i < RT * LD; i += 32) XT[i] = 0.f;
   __syncwarp();
   // jointly valid samples (valid = a.w & b.w), compacted in place
   int n = 0;
@@ -252,7 +258,8 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
     if (lane == 0) { num_lags[jp] = 0; lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
     return;
   }
-  const int K = (n + RT - 1) / RT * RT;
+  const int K = (n + RT - 1) / RT * RT;         // <= Lw.K
+  const int OFF = K + RT + 1;                   // storage index of AA[0]
   double daa = 0, dbb = 0, dab = 0, amax = 0, bmax = 0;
   for (int i = lane; i < n; i += 32) {
     const double va = a64[i], vb = b64[i];
@@ -262,40 +269,46 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   daa = warp_sum(daa); dbb = warp_sum(dbb); dab = warp_sum(dab);
   for (int o = 16; o > 0; o >>= 1) { amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o)); bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o)); }
   const double den = fmax(fmax(daa, dbb), dab);
-  // fp32 operands scaled to O(1) so tiny band-passed signals neither underflow nor lose bits
+  // fp32 operands scaled to O(1) so tiny band-passed signals neither underflow nor lose bits.  The operand buffer is
+  // written completely (every storage index a tile can touch): periodic extension inside [-n, n), zeros outside.
   const double sa = amax > 0 ? 1.0 / amax : 1.0, sb = bmax > 0 ? 1.0 / bmax : 1.0;
-  for (int i = lane; i < n; i += 32) {
-    XT[xt_index<RT>(i + n - 1 + K, LD)] = (float)(a64[i] * sa);     // storage index = u + K
-    c[n - 1 - i] = (float)(b64[i] * sb);
+  const int jtot = 2 * K + 2 * RT;              // storage indices [0, jtot): t = j - OFF in [-K - RT - 1, K + RT - 2]
+  for (int j = lane; j < jtot; j += 32) {
+    const int t = j - OFF;
+    float v = 0.f;
+    if (t >= -n && t < n) v = (float)(a64[t < 0 ? t + n : t] * sa);
+    XT[xt_index<RT>(j, LD)] = v;
   }
+  for (int m = lane; m < K; m += 32) c[m] = m < n ? (float)(b64[n - 1 - m] * sb) : 0.f;
   __syncwarp();
   const float unscale = (float)(1.0 / (sa * sb * den));
   const int L = 2 * n - 1;
   const long long ob = jp * (2LL * W - 1);
   const double x_last = xa_g[pos[n - 1]];
-  // COARSE pass in fp32:  corr[li] = sum_l a[l + k] b[l], k = li - (n-1)  ==  sum_m c[m] X[j - m] with j = li + n - 1
-  const int jbase = (n - 1 + K) / RT * RT;      // storage index of the tile that holds li = 0
   float cmax = -INFINITY; int cnt = 0;          // coarse maximum / finite count, gathered while the tiles are written
-  for (int J0 = jbase + RT * lane; J0 <= (L - 1) + (n - 1) + K; J0 += RT * 32) {
-    float acc[RT];
+  const int tiles = K / RT;
+  for (int tile = lane; tile < tiles; tile += 32) {
+    float acc[RT], first[RT];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = 0.f;
-    const int u0 = J0 - K;                       // logical index of the tile's first output operand
-    int kb_lo = (u0 - (2 * n - 2)) / RT; if (kb_lo < 0) kb_lo = 0;
-    int kb_hi = (u0 + RT - 1 - (n - 1)) / RT + 1; if (kb_hi < 0) kb_hi = 0;
-    corr_tile<RT, float>(acc, c, K, XT, LD, J0, kb_lo, kb_hi);
+    for (int r = 0; r < RT; ++r) { acc[r] = 0.f; first[r] = 0.f; }
+    corr_tile_wrap<RT, LDC, float>(acc, first, c, K, XT, LD, RT * tile + K + RT, tile);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      const int li = u0 + r - (n - 1);
-      if (li >= 0 && li < L) {
-        const float cc = acc[r] * unscale;
-        cv[li] = cc;
-        if (isfinite(cc)) { ++cnt; cmax = fmaxf(cmax, cc); }
-        if (corr_val) {
-          const int k = li - (n - 1), ak = k < 0 ? -k : k;
-          const double lag = (x_last - xa_g[pos[n - 1 - ak]]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
-          corr_lag[ob + li] = (float)lag;
-          corr_val[ob + li] = cc;
+      const int la = RT * tile - 1 + r;          // first lag of the pair; the second is la + n
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int li = h ? la + n : la;
+        const bool ok = h ? (la <= n - 2) : (la >= 0 && la <= n - 2);
+        if (ok) {
+          const float cc = (h ? acc[r] : first[r]) * unscale;
+          cv[li] = cc;
+          if (isfinite(cc)) { ++cnt; cmax = fmaxf(cmax, cc); }
+          if (corr_val) {
+            const int k = li - (n - 1), ak = k < 0 ? -k : k;
+            const double lag = (x_last - xa_g[pos[n - 1 - ak]]) * (k > 0 ? 1.0 : (k < 0 ? -1.0 : 0.0));
+            corr_lag[ob + li] = (float)lag;
+            corr_val[ob + li] = cc;
+          }
         }
       }
     }
@@ -363,9 +376,17 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
     if (wpb > 4) wpb = 4;
     if (wpb >= 1) {
       const size_t smw = (size_t)wpb * Lw.total;
-      if (int rc = ensure_dyn_smem((const void*)xcorr_warp_kernel, smw)) return rc;
-      xcorr_warp_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smw, (cudaStream_t)stream>>>(
-          proc_x, proc_y, *p, Lw, n, corr_lag, corr_val, num_lags, lag_idx, lag_sec, lag_corr);
+      const unsigned grid = (unsigned)((n + wpb - 1) / wpb);
+#define BPV_XW(LDC)                                                                                                   \
+  do {                                                                                                                \
+    if (int rc = ensure_dyn_smem((const void*)xcorr_warp_kernel<LDC>, smw)) return rc;                                \
+    xcorr_warp_kernel<LDC><<<grid, wpb * 32, smw, (cudaStream_t)stream>>>(proc_x, proc_y, *p, Lw, n, corr_lag,       \
+                                                                         corr_val, num_lags, lag_idx, lag_sec, lag_corr); \
+  } while (0)
+      if (Lw.LD == 63) BPV_XW(63);            // windows of 291..300 samples (the 10 s window at 30 fps)
+      else if (Lw.LD == 53) BPV_XW(53);       // 241..250 (the reference's default signal_max_samples)
+      else BPV_XW(0);
+#undef BPV_XW
       return check_launch("bpv_window_xcorr");
     }
   }
