@@ -52,6 +52,12 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
 }
+// same, with the N of the instruction chosen at run time (bin chunks narrower than 128 bins): n_dim = N >> 3 @17
+__device__ __forceinline__ void tc_mma_tf32_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
@@ -469,33 +475,40 @@ __global__ void __launch_bounds__(128) dft_peak_kernel(const double* __restrict_
 //                 fullA / fullB, issues the 6 tcgen05.mma of the block and commits them to emptyA / emptyB
 // Waits are bounded: a barrier that never completes traps instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------
-constexpr int DTM_NSA = 3, DTM_NSB = 5;                     // ring stages of the A / B operands
+// Ring stages of the A / B operands inside one 208 KB ring area: the B ring takes DTM_NSB images of this launch's size (32 KB at
+// 128 bins per CTA, 18 KB at 72), the A ring (16 KB per k block) everything that is left — 3 stages at 128 bins, 7 at 72.
+// The A stages are what hides the producer <-> tensor-core round trip (commit -> producers wake -> convert -> proxy fence ->
+// arrive -> issue): with 3 stages a k block costs ~1 us however narrow the MMA is.
+constexpr int DTM_NSB = 5, DTM_NSA_MIN = 3, DTM_NSA_MAX = 8;
 constexpr int DTM_A_BYTES = 16 * 1024, DTM_B_BYTES = 32 * 1024;
-constexpr int DTM_OFF_B = DTM_NSA * DTM_A_BYTES;            // B ring behind the A ring
-constexpr int DTM_OFF_BAD = DTM_OFF_B + DTM_NSB * DTM_B_BYTES;   // int [128]
-constexpr int DTM_OFF_BAR = DTM_OFF_BAD + 512;              // fullA[3] emptyA[3] fullB[5] emptyB[5] (u64 each) | tmem slot (u32)
-constexpr int DTM_NBAR = 2 * DTM_NSA + 2 * DTM_NSB;
+constexpr int DTM_RING = DTM_NSA_MIN * DTM_A_BYTES + DTM_NSB * DTM_B_BYTES;
+constexpr int DTM_OFF_BAD = DTM_RING;                       // int [128]
+constexpr int DTM_OFF_BAR = DTM_OFF_BAD + 512;              // fullA[8] emptyA[8] fullB[5] emptyB[5] (u64 each) | tmem slot (u32)
+constexpr int DTM_NBAR = 2 * DTM_NSA_MAX + 2 * DTM_NSB;
 constexpr int DTM_SMEM = DTM_OFF_BAR + 8 * DTM_NBAR + 16;
 constexpr int DTM_THREADS = DTC_THREADS + 32;               // 16 producer warps + the control warp
-constexpr int DTM_PREFETCH = DTM_NSB - 2;                   // B images in flight ahead of the MMAs
+constexpr int DTM_PF = 4;                                   // A operand: k blocks of float64 samples held in registers
 constexpr unsigned long long DTM_MAGIC = 0x62707644465431ULL;   // "bpvDFT1"
 
+// Bin chunk width BC (bins per CTA, multiple of 8, <= 128): the MMA is M 128 x N 2*BC, the image of one (bin chunk, k block)
+// is [B hi | B lo] = 2 x (4 k-chunks x 2*BC columns x 16 B) = 256 * BC bytes.  Whatever BC a launch picks, the chunks cover
+// fewer than F + 128 bins.
 __host__ __device__ inline long long dtc_image_bytes(int W) {
-  const long long NB = (W + DTC_KB - 1) / DTC_KB, nbc = (W / 2 + 1 + 127) / 128;
-  return 256 + nbc * NB * DTM_B_BYTES;                      // header (magic, n) + images
+  const long long NB = (W + DTC_KB - 1) / DTC_KB, F = W / 2 + 1;
+  return 256 + NB * 256 * (F + 128);                        // header (magic, n, BC) + images
 }
 
 // One CTA per (k block, bin chunk): 1024 operand items (chunk c, column col) of 4 consecutive samples each.
-__global__ void __launch_bounds__(256) dft_image_kernel(int n, unsigned char* __restrict__ ws) {
+__global__ void __launch_bounds__(256) dft_image_kernel(int n, int BC, unsigned char* __restrict__ ws) {
   const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(ws);
-  if (hdr[0] == DTM_MAGIC && hdr[1] == (unsigned long long)n) return;          // built for this n by an earlier launch
-  const int F = n / 2 + 1, NB = (n + DTC_KB - 1) / DTC_KB;
+  if (hdr[0] == DTM_MAGIC && hdr[1] == (unsigned long long)n && hdr[2] == (unsigned long long)BC) return;   // built by an earlier launch
+  const int F = n / 2 + 1, NB = (n + DTC_KB - 1) / DTC_KB, N = 2 * BC;
   const int kb = blockIdx.x, bc = blockIdx.y;
-  float4* Bhi = reinterpret_cast<float4*>(ws + 256 + ((long long)bc * NB + kb) * DTM_B_BYTES);
-  float4* Blo = Bhi + 4 * TC_N;
-  for (int it = threadIdx.x; it < 4 * TC_N; it += blockDim.x) {
-    const int c = it / TC_N, col = it % TC_N;
-    const int kcol = bc * 128 + (col & 127);
+  float4* Bhi = reinterpret_cast<float4*>(ws + 256 + ((long long)bc * NB + kb) * (256LL * BC));
+  float4* Blo = Bhi + 4 * N;
+  for (int it = threadIdx.x; it < 4 * N; it += blockDim.x) {
+    const int c = it / N, col = it % N;
+    const int kcol = bc * BC + (col < BC ? col : col - BC);
     float hv[4], lv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(256) dft_image_kernel(int n, unsigned char* __
         const long long idx = ((long long)j * kcol) % n;
         double s_, c_;
         sincospi(2.0 * (double)idx / (double)n, &s_, &c_);
-        v = col < 128 ? c_ : s_;
+        v = col < BC ? c_ : s_;
       }
       hv[e] = tc_hi((float)v);
       lv[e] = (float)(v - (double)hv[e]);
@@ -514,9 +527,9 @@ __global__ void __launch_bounds__(256) dft_image_kernel(int n, unsigned char* __
     Blo[it] = make_float4(lv[0], lv[1], lv[2], lv[3]);
   }
 }
-__global__ void dft_image_seal_kernel(int n, unsigned char* __restrict__ ws) {
+__global__ void dft_image_seal_kernel(int n, int BC, unsigned char* __restrict__ ws) {
   unsigned long long* hdr = reinterpret_cast<unsigned long long*>(ws);
-  hdr[0] = DTM_MAGIC; hdr[1] = (unsigned long long)n;
+  hdr[0] = DTM_MAGIC; hdr[1] = (unsigned long long)n; hdr[2] = (unsigned long long)BC;
 }
 
 __device__ __forceinline__ void tc_wait_bounded(uint32_t bar, uint32_t parity) {
@@ -538,7 +551,7 @@ __device__ __forceinline__ void tc_arrive(uint32_t bar) {
 }
 
 __global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double* __restrict__ proc_y, int W, long long nsig, int max_bins,
-                                                                    const unsigned char* __restrict__ img,
+                                                                    int BC, const unsigned char* __restrict__ img,
                                                                     float* __restrict__ mags, int32_t* __restrict__ num_bins) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -546,13 +559,19 @@ __global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double
   int* bad = reinterpret_cast<int*>(smem + DTM_OFF_BAD);
   uint8_t* barp = smem + DTM_OFF_BAR;
   const uint32_t bar = tc_smem_u32(barp), slot = bar + 8 * DTM_NBAR;
-  const uint32_t fullA = bar, emptyA = bar + 8 * DTM_NSA, fullB = bar + 16 * DTM_NSA, emptyB = fullB + 8 * DTM_NSB;
+  const uint32_t fullA = bar, emptyA = bar + 8 * DTM_NSA_MAX, fullB = bar + 16 * DTM_NSA_MAX, emptyB = fullB + 8 * DTM_NSB;
+  const uint32_t b_stride = (256u * (uint32_t)BC + 1023u) & ~1023u;        // one B image (256 BC bytes), 1 KB aligned
+  constexpr int NSB = DTM_NSB;
+  int NSA = (DTM_RING - NSB * (int)b_stride) / DTM_A_BYTES;
+  if (NSA > DTM_NSA_MAX) NSA = DTM_NSA_MAX;
+  const int PREF = NSB - 2;
+  const uint32_t off_b = (uint32_t)NSA * DTM_A_BYTES;                       // B ring behind the A ring
   if (tid < 128) bad[tid] = 0;
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (tid == 0) {
-      for (int s_ = 0; s_ < DTM_NSA; ++s_) {
+      for (int s_ = 0; s_ < DTM_NSA_MAX; ++s_) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fullA + 8u * s_), "r"(DTC_THREADS / 32) : "memory");   // one arrive per producer warp
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(emptyA + 8u * s_) : "memory");
       }
@@ -569,48 +588,53 @@ __global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 8 * DTM_NBAR);
 
   const long long sig0 = (long long)blockIdx.x * TC_M;
-  const int k0 = blockIdx.y * 128;
+  const int k0 = blockIdx.y * BC;
   const int NB = (n + DTC_KB - 1) / DTC_KB;
   const uint32_t smem0 = tc_smem_u32(smem);
   if (wid == DTC_THREADS / 32) {
     // ---- control warp: TMA producer + MMA issuer (one thread)
     if (lane == 0) {
-      const unsigned char* my_img = img + 256 + (long long)blockIdx.y * NB * DTM_B_BYTES;
-      for (int kb = 0; kb < DTM_PREFETCH && kb < NB; ++kb)
-        tc_bulk_load(smem0 + DTM_OFF_B + (uint32_t)(kb % DTM_NSB) * DTM_B_BYTES, my_img + (long long)kb * DTM_B_BYTES, DTM_B_BYTES,
-                     fullB + 8u * (kb % DTM_NSB));
+      const uint32_t img_bytes = 256u * (uint32_t)BC, b_lbo = 32u * (uint32_t)BC, b_lo_off = 128u * (uint32_t)BC;   // N = 2 BC columns
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BC) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const unsigned char* my_img = img + 256 + (long long)blockIdx.y * NB * img_bytes;
+      for (int kb = 0; kb < PREF && kb < NB; ++kb)
+        tc_bulk_load(smem0 + off_b + (uint32_t)(kb % NSB) * b_stride, my_img + (long long)kb * img_bytes, img_bytes,
+                     fullB + 8u * (kb % NSB));
       for (int kb = 0; kb < NB; ++kb) {
-        const int k2 = kb + DTM_PREFETCH;
+        const int k2 = kb + PREF;
         if (k2 < NB) {
-          const int s2 = k2 % DTM_NSB;
-          if (k2 >= DTM_NSB) tc_wait_bounded(emptyB + 8u * s2, (uint32_t)((k2 / DTM_NSB - 1) & 1));    // its previous image has been consumed
-          tc_bulk_load(smem0 + DTM_OFF_B + (uint32_t)s2 * DTM_B_BYTES, my_img + (long long)k2 * DTM_B_BYTES, DTM_B_BYTES, fullB + 8u * s2);
+          const int s2 = k2 % NSB;
+          if (k2 >= NSB) tc_wait_bounded(emptyB + 8u * s2, (uint32_t)((k2 / NSB - 1) & 1));    // its previous image has been consumed
+          tc_bulk_load(smem0 + off_b + (uint32_t)s2 * b_stride, my_img + (long long)k2 * img_bytes, img_bytes, fullB + 8u * s2);
         }
-        const int sa_ = kb % DTM_NSA, sb_ = kb % DTM_NSB;
-        tc_wait_bounded(fullA + 8u * sa_, (uint32_t)((kb / DTM_NSA) & 1));
-        tc_wait_bounded(fullB + 8u * sb_, (uint32_t)((kb / DTM_NSB) & 1));
+        const int sa_ = kb % NSA, sb_ = kb % NSB;
+        tc_wait_bounded(fullA + 8u * sa_, (uint32_t)((kb / NSA) & 1));
+        tc_wait_bounded(fullB + 8u * sb_, (uint32_t)((kb / NSB) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem0 + (uint32_t)sa_ * DTM_A_BYTES, sb = smem0 + DTM_OFF_B + (uint32_t)sb_ * DTM_B_BYTES;
+        const uint32_t sa = smem0 + (uint32_t)sa_ * DTM_A_BYTES, sb = smem0 + off_b + (uint32_t)sb_ * b_stride;
 #pragma unroll
         for (int ks = 0; ks < DTC_KB / 8; ++ks) {
           const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
-          const uint64_t dbh = tc_desc(sb + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), dbl = tc_desc(sb + 16384 + ks * 2 * TC_B_LBO, TC_B_LBO, TC_SBO);
-          tc_mma_tf32(tmem, dah, dbh, (kb | ks) != 0);
-          tc_mma_tf32(tmem, dal, dbh, 1);
-          tc_mma_tf32(tmem, dah, dbl, 1);
+          const uint64_t dbh = tc_desc(sb + ks * 2 * b_lbo, b_lbo, TC_SBO), dbl = tc_desc(sb + b_lo_off + ks * 2 * b_lbo, b_lbo, TC_SBO);
+          tc_mma_tf32_n(tmem, dah, dbh, idesc, (kb | ks) != 0);
+          tc_mma_tf32_n(tmem, dal, dbh, idesc, 1);
+          tc_mma_tf32_n(tmem, dah, dbl, idesc, 1);
         }
         tc_commit(emptyA + 8u * sa_);
         tc_commit(emptyB + 8u * sb_);
       }
     }
   } else {
-    // ---- producer warps: the A operand
+    // ---- producer warps: the A operand.  The float64 samples of the next DTM_PF - 1 k blocks are in flight in registers
+    // while a block is converted.  (Measured alternatives, profiles/r2w_dft_tc.txt: one block ahead 78 us, four ahead 72 us;
+    // deeper A or B rings change nothing; one signal row per thread with the warps taking k blocks in turn — fewer proxy
+    // fences per warp, but one 128-byte line per thread instead of 64 bytes per 4 lanes — 93 us.)
     const int arow = tid >> 2, aq = tid & 3;
     const long long asig = sig0 + arow;
     const double* ay = proc_y + (asig < nsig ? asig : 0) * W;
     const bool vec_ok = (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0;
     int mybad = 0;
-    double cur[4], nxt[4];
+    double buf[DTM_PF][4];
     auto fetch = [&](int kb, double (&dst)[4]) {
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
@@ -624,51 +648,57 @@ __global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double
         }
       }
     };
-    fetch(0, cur);
-    for (int kb = 0; kb < NB; ++kb) {
-      const int st = kb % DTM_NSA;
-      uint8_t* stage = smem + st * DTM_A_BYTES;
-      if (kb + 1 < NB) fetch(kb + 1, nxt);
-      if (kb >= DTM_NSA) tc_wait_bounded(emptyA + 8u * st, (uint32_t)((kb / DTM_NSA - 1) & 1));      // block kb-3 has been consumed
-      float hv[4], lv[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double v = cur[e];
-        if (!isfinite(v)) mybad = 1;
-        hv[e] = tc_hi((float)v);
-        lv[e] = (float)(v - (double)hv[e]);
+    for (int u = 0; u < DTM_PF - 1; ++u)
+      if (u < NB) fetch(u, buf[u]);
+    for (int kb0 = 0; kb0 < NB; kb0 += DTM_PF) {
+#pragma unroll
+      for (int u = 0; u < DTM_PF; ++u) {
+        const int kb = kb0 + u;
+        if (kb < NB) {
+          if (kb + DTM_PF - 1 < NB) fetch(kb + DTM_PF - 1, buf[(u + DTM_PF - 1) % DTM_PF]);
+          const int st = kb % NSA;
+          uint8_t* stage = smem + st * DTM_A_BYTES;
+          if (kb >= NSA) tc_wait_bounded(emptyA + 8u * st, (uint32_t)((kb / NSA - 1) & 1));      // block kb - NSA has been consumed
+          float hv[4], lv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const double v = buf[u][e];
+            if (!isfinite(v)) mybad = 1;
+            hv[e] = tc_hi((float)v);
+            lv[e] = (float)(v - (double)hv[e]);
+          }
+          float2* Ah2 = reinterpret_cast<float2*>(stage);
+          float2* Al2 = reinterpret_cast<float2*>(stage + 8192);
+          const int o0 = (((aq >> 1) * TC_M + arow) << 1) + (aq & 1), o1 = (((2 + (aq >> 1)) * TC_M + arow) << 1) + (aq & 1);
+          Ah2[o0] = make_float2(hv[0], hv[1]); Al2[o0] = make_float2(lv[0], lv[1]);
+          Ah2[o1] = make_float2(hv[2], hv[3]); Al2[o1] = make_float2(lv[2], lv[3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) tc_arrive(fullA + 8u * st);
+        }
       }
-      float2* Ah2 = reinterpret_cast<float2*>(stage);
-      float2* Al2 = reinterpret_cast<float2*>(stage + 8192);
-      const int o0 = (((aq >> 1) * TC_M + arow) << 1) + (aq & 1), o1 = (((2 + (aq >> 1)) * TC_M + arow) << 1) + (aq & 1);
-      Ah2[o0] = make_float2(hv[0], hv[1]); Al2[o0] = make_float2(lv[0], lv[1]);
-      Ah2[o1] = make_float2(hv[2], hv[3]); Al2[o1] = make_float2(lv[2], lv[3]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) tc_arrive(fullA + 8u * st);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
     }
     if (mybad) bad[arow] = 1;
   }
   // the commit of the last block completes when every MMA has: the accumulator is final
-  tc_wait_bounded(emptyA + 8u * ((NB - 1) % DTM_NSA), (uint32_t)(((NB - 1) / DTM_NSA) & 1));
+  tc_wait_bounded(emptyA + 8u * ((NB - 1) % NSA), (uint32_t)(((NB - 1) / NSA) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();                                         // bad[] complete
   if (tid < TC_M) {
     const long long sig = sig0 + tid;
     const bool rowbad = bad[tid] != 0;
     const float sc = 2.f / (float)n;
-    for (int c32 = 0; c32 < 4; ++c32) {
+    for (int c32 = 0; 32 * c32 < BC; ++c32) {              // re columns [0, BC), im columns [BC, 2 BC); 256 columns are allocated
       float re[32], im[32];
       __syncwarp();
       tc_load32(tmem, 32 * c32, re);
-      tc_load32(tmem, 128 + 32 * c32, im);
+      tc_load32(tmem, BC + 32 * c32, im);
       if (sig < nsig && !rowbad) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int k = k0 + 32 * c32 + i;
-          if (k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(re[i] * re[i] + im[i] * im[i]);
+          if (32 * c32 + i < BC && k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(re[i] * re[i] + im[i] * im[i]);
         }
       }
     }
@@ -692,11 +722,32 @@ int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long n
   if (image_ws && !(env && env[0] == '0')) {
     if (int rc = ensure_dyn_smem((const void*)dft_tc_tma_kernel, DTM_SMEM)) return rc;
     const int NB = (W + DTC_KB - 1) / DTC_KB;
-    dft_image_kernel<<<dim3((unsigned)NB, grid.y), 256, 0, st>>>(W, (unsigned char*)image_ws);
+    // bins per CTA: one CTA per SM (209 KB of shared memory), so the launch costs waves x (MMA time ~ 2 BC columns + the
+    // per-block operand conversion, ~64 columns' worth).  2048 signals x 601 bins: 16 x 5 CTAs of 128 bins leave 68 SMs idle,
+    // 16 x 9 CTAs of 72 bins fill 144 of the 148 (BPV_DFT_BC overrides: measurement switch).
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    int BC = 128;
+    {
+      long long best = -1;
+      for (int bc = 16; bc <= 128; bc += 8) {
+        const long long ctas = (long long)grid.x * ((F + bc - 1) / bc);
+        const long long cost = ((ctas + sms - 1) / sms) * (2 * bc + 64);
+        if (best < 0 || cost < best || (cost == best && bc > BC)) { best = cost; BC = bc; }
+      }
+      const char* ebc = getenv("BPV_DFT_BC");
+      if (ebc && atoi(ebc) >= 16 && atoi(ebc) <= 128 && atoi(ebc) % 8 == 0) BC = atoi(ebc);
+    }
+    grid.y = (unsigned)((F + BC - 1) / BC);
+    dft_image_kernel<<<dim3((unsigned)NB, grid.y), 256, 0, st>>>(W, BC, (unsigned char*)image_ws);
     if (int rc = check_launch("dft_image_kernel")) return rc;
-    dft_image_seal_kernel<<<1, 1, 0, st>>>(W, (unsigned char*)image_ws);
+    dft_image_seal_kernel<<<1, 1, 0, st>>>(W, BC, (unsigned char*)image_ws);
     if (int rc = check_launch("dft_image_seal_kernel")) return rc;
-    dft_tc_tma_kernel<<<grid, DTM_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, (const unsigned char*)image_ws, mags, num_bins);
+    dft_tc_tma_kernel<<<grid, DTM_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, BC, (const unsigned char*)image_ws, mags, num_bins);
     if (int rc = check_launch("dft_tc_tma_kernel")) return rc;
   } else {
     if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
