@@ -118,6 +118,7 @@ struct Warp {
   double xfirst, xlast;
   bool grid;           // x[block] has been replaced by the uniform grid (after an INTERP_*)
   int fir_c, fir_gt, fir_b;   // FIR sub-plan inside buf0 (PreLayout)
+  int W;               // window length of the launch (fixes the merged FIR's operand layout for every n <= W)
 };
 
 __device__ void diff1(Warp& w) {  // np.diff(y, n=1, prepend=y[0])  (signal_processor.py:203)
@@ -645,14 +646,16 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
 // 253 x n multiply-adds instead of 127 x (2n + 126), one staged operand buffer instead of two, no intermediate signal;
 // agrees with the two-pass form to rounding (1e-15 relative).  RT consecutive outputs per lane (corr_tile.cuh): RT = 10
 // makes a 300-sample window ONE round of 30 lanes, RT = 8 a 250-sample window one round of 32.
-template <int RT>
+// LDC / KC: the operand buffer's leading dimension and the padded tap count as compile-time constants for the common
+// (taps, window) pairs (corr_tile.cuh); the leading dimension is the launch's (window length W), not the signal's.
+template <int RT, int LDC = 0, int KC = 0>
 __device__ void fir_merged(Warp& w, const double* __restrict__ ac_g, int T) {
   const int M = T - 1;
-  const int K = fir_merged_k(T, RT);
+  const int K = KC ? KC : fir_merged_k(T, RT);
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;      // signal_processor.py:233-234
   const int L = n + 2 * p;
   const int tiles = (n + RT - 1) / RT;
-  const int LD = (K / RT + tiles) | 1;
+  const int LD = LDC ? LDC : fir_merged_ld(w.W, T, RT);
   double* XT = w.buf0;              // X[j] = ext[j + xbase], de-interleaved by RT; output m sits at j = m + K
   double* c = w.buf0 + w.fir_c;     // c[k] = ac[|k - M|], k = 0 .. 2M; zero up to K
   for (int k = w.lane; k < K; k += 32) {
@@ -678,7 +681,7 @@ __device__ void fir_merged(Warp& w, const double* __restrict__ ac_g, int T) {
     double acc[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-    corr_tile<RT, double>(acc, c, K, XT, LD, K + RT * t);
+    corr_tile<RT, double, LDC, KC>(acc, c, K, XT, LD, K + RT * t);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int m = RT * t + r;
@@ -694,8 +697,15 @@ __device__ __forceinline__ void fir_apply(Warp& w, const double* __restrict__ tg
     // the cheaper tiling for this window length: rounds x RT x padded taps
     const int c8 = ((n + 7) / 8 + 31) / 32 * 8 * fir_merged_k(T, 8);
     const int c10 = ((n + 9) / 10 + 31) / 32 * 10 * fir_merged_k(T, 10);
-    if (c10 < c8) fir_merged<10>(w, tg + 256, T);
-    else fir_merged<8>(w, tg + 256, T);
+    const bool t127 = T == 127;                       // the reference's default filter (fir_taps = 127): K = 260 / 256
+    if (c10 < c8) {
+      if (t127 && w.W == 300) fir_merged<10, 57, 260>(w, tg + 256, T);       // fir_merged_ld(300, 127, 10)
+      else fir_merged<10>(w, tg + 256, T);
+    } else {
+      if (t127 && w.W == 300) fir_merged<8, 71, 256>(w, tg + 256, T);        // fir_merged_ld(300, 127, 8)
+      else if (t127 && w.W == 250) fir_merged<8, 65, 256>(w, tg + 256, T);   // fir_merged_ld(250, 127, 8)
+      else fir_merged<8>(w, tg + 256, T);
+    }
   } else {
     fir_filtfilt(w, tg, T);
   }
@@ -726,6 +736,7 @@ __device__ int gather_window(Warp& w, unsigned char* sm, const PreLayout& L, con
   w.posv = reinterpret_cast<unsigned short*>(sm + L.posv);
   w.posb = reinterpret_cast<unsigned short*>(sm + L.posb);
   w.grid = false;
+  w.W = p.window;
   w.fir_c = L.fir_c; w.fir_gt = L.fir_gt; w.fir_b = L.fir_b;
   const long long job = sig / p.R;
   const int r = (int)(sig % p.R);
