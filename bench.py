@@ -63,8 +63,9 @@ OTHER_SHAPES = {
                desc='configs[4]: 65536 streams x 10 s windows over all GPUs, ROI -> Butterworth -> Lomb-Scargle -> HR -> PTT + NCCL record gather'),
 }
 METRIC, UNIT = 'roi_sampled_frames_per_s', 'frames/s'
-# dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch (ncu --set full; profiles/r2l_c2_summary.md: 331.6 + 5.6 MB, same boxes)
-ROI_NCU_TRAFFIC_BYTES = 337.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one c2 F1 launch of 16 384 frames (ncu --set full; profiles/r2y_c2_summary.md:
+# 664.3 + 4.0 and 664.4 + 5.9 MB for the two captured launches, same boxes); 337.2 MB for the 8192-frame launch of round 1
+ROI_NCU_TRAFFIC_BYTES = 669.3e6
 FRAME_PERIOD_MS = 1000.0 / 30.0
 
 
@@ -556,6 +557,7 @@ def run_gpu(args, wl):
     for k, fn in orig.items():
         setattr(ops, k, fn)
     ms = start.elapsed_time(stop)
+    launches_per_step = eng.launches_per_step + 1            # of the timed steps: the engine's own count + pack_records32
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -641,7 +643,6 @@ def run_gpu(args, wl):
     del host_frames
     fma = measure_fma_peaks(torch, dev) if rank == 0 else None
     pcie = measure_pcie(torch, dev) if rank == 0 else None
-    launches_per_step = eng.launches_per_step + 1            # + pack_records32
     sched = {'overlap_mask': eng.overlap, 'design_cache': eng._dcache is not None}
     del frames, eng
     torch.cuda.empty_cache()
@@ -737,7 +738,7 @@ def run_gpu(args, wl):
         # F1 is the HBM-bound kernel the metric is quoted on ("ROI-sampled frames/s (%HBM peak)") and moves most of the
         # step's DRAM traffic; the dominant family BY TIME is FP64-bound filter work (roofline_by_time, FP64 peak).
         'roofline': {'kernel': 'roi (roi_staged_kernel)', 'bound': 'hbm', 'achieved': kernels['roi']['gbs'], 'peak': peak,
-                     'unit': 'GB/s', 'frac': kernels['roi']['frac_hbm'], 'traffic': ROI_NCU_TRAFFIC_BYTES,
+                     'unit': 'GB/s', 'frac': kernels['roi']['frac_hbm'], 'traffic': (ROI_NCU_TRAFFIC_BYTES * T / 64.0) if args.workload == 'c2' else None,
                      'peak_source': peak_src, 'alg_bytes': alg['roi'],
                      'granule64_bytes': g64, 'granule32_bytes': g32,
                      'note': 'achieved = algorithmic bytes (sum of 3*w*h over the ROIs of a launch + boxes + outputs) / mean '

@@ -12,8 +12,9 @@ python bench.py --impl reference --steps 5 --warmup 1 --ref-budget-s 20 > gpurun
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KF" -c 400 --csv --log-file gpurun_out/${tag}_launches_bench_c2.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-other > gpurun_out/${tag}_ncu.log 2>&1; echo "ncu rc=$?"
 if [ -n "$full" ]; then
-  # ring prefill = 10 step_signals x 5 kernels; each warm-up step = 7 kernels -> skip past the warm-up, capture one full step
-  ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 90 --launch-count 10 -f -o gpurun_out/${tag}_c2 \
+  # ring prefill = 5 step_signals x 5 kernels; each step = 9 kernels -> skip past the prefill and two warm-up steps, capture
+  # two whole steps
+  ncu --set full --clock-control none --import-source on -k "$KF" --launch-skip 43 --launch-count 18 -f -o gpurun_out/${tag}_c2 \
       python bench.py --steps 1 --warmup 3 --no-cpu --no-other > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 python - <<PY
