@@ -899,6 +899,122 @@ __global__ void __launch_bounds__(128) roi_nv12_kernel(const uint8_t* __restrict
   }
 }
 
+// Branch-free body for aligned planes (frame base, frame stride and pitch multiples of 16: every decoder surface).  The
+// kernel above tests the ROI's edges per pixel (914 instructions per 32 pixels, ~120 of them branches and predicates); here
+//   * the column mask of a thread's 16-pixel group is loop invariant and is folded into the accumulation as a 0 / 1
+//     multiplier (sum = value * m + sum is one IMAD, the same cost as the plain add),
+//   * the two luma rows of a chroma row accumulate into row-local partial sums that enter the totals with a 0 / 1 row weight
+//     (only the first / last chroma row of a ROI can have a luma row outside it), so nothing in the loop branches,
+//   * the constant offsets (Y - 16, U - 128, V - 128) are folded into the per-pair chroma terms:
+//       c = max(Y, 16) * CY + [2^19 - 16 CY + k_u (U - 128) + k_v (V - 128)]        (one IMAD per channel and pixel)
+// Same integer arithmetic as OpenCV's (20-bit fixed point, >> 20, saturate), bit for bit.
+// d = { c[15:0], sat_u8(a), sat_u8(b) }: two saturating conversions and the packing in ONE instruction (I2IP.U8.S32.SAT)
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <bool WANT_SUMS, bool ALL>
+__global__ void __launch_bounds__(128) roi_nv12_vec_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long pitch,
+                                                           int H, int W, int R, int mode, long long num_rois,
+                                                           const int32_t* __restrict__ boxes,
+                                                           unsigned long long* __restrict__ out_sums, double* __restrict__ out_value) {
+  constexpr int THREADS = 128, WARPS = THREADS / 32;
+  constexpr int CY = 1220542, CVR = 1673527, CVG = -852492, CUG = -409993, CUB = 2116026;
+  const int gt = threadIdx.x;
+  const long long roi = blockIdx.x;
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  bool has_box = false;
+  const int4 b = __ldg(reinterpret_cast<const int4*>(boxes) + roi);
+  has_box = b.x != BPV_NO_BOX;
+  if (has_box) { py_slice(b.x, b.z, W, xs, xe); py_slice(b.y, b.w, H, ys, ye); }
+  const uint8_t* yp = frames + (roi / R) * frame_stride;
+  const uint8_t* uvp = yp + (long long)H * pitch;
+  const int nrows = ye - ys, ncols = xe - xs;
+  uint32_t sB = 0, sG = 0, sR = 0;                           // !WANT_SUMS: sB carries B + R (all the chrominance formula needs)
+  if (nrows > 0 && ncols > 0) {
+    const int x0 = xs & ~15;
+    const int vpr = (xe - x0 + 15) >> 4;
+    const int c_lo = ys >> 1, c_hi = (ye - 1) >> 1, ncr = c_hi - c_lo + 1;
+    int rps, r0, v0;
+    if (vpr >= THREADS) { rps = 1; r0 = 0; v0 = gt; }
+    else { rps = THREADS / vpr; r0 = gt / vpr; v0 = gt - r0 * vpr; if (r0 >= rps) v0 = vpr; }
+    for (int v = v0; v < vpr; v += THREADS) {
+      const int xv = x0 + 16 * v;
+      // per pixel PAIR (2 pr, 2 pr + 1): byte selectors for the packed saturated values — the values of a pair are summed by
+      // one dp4a against the pair's 0 / 1 byte mask, so the ROI's left / right edge costs nothing in the loop
+      uint32_t m2[8], m4[8];                                   // {e0, e1} in bytes {1, 0} / {e0, e0, e1, e1} in bytes {3, 2, 1, 0}
+#pragma unroll
+      for (int pr = 0; pr < 8; ++pr) {
+        const uint32_t a0 = (xv + 2 * pr >= xs && xv + 2 * pr < xe) ? 1u : 0u, a1 = (xv + 2 * pr + 1 >= xs && xv + 2 * pr + 1 < xe) ? 1u : 0u;
+        m2[pr] = a0 << 8 | a1;
+        m4[pr] = a0 * 0x01010000u | a1 * 0x00000101u;
+        asm volatile("" : "+r"(m2[pr]), "+r"(m4[pr]));         // opaque registers: the compiler must not re-derive them per row
+      }
+      for (int r = r0; r < ncr; r += rps) {
+        const int cy = c_lo + r;
+        uint32_t w0 = 2 * cy >= ys ? 1u : 0u, w1 = 2 * cy + 1 < ye ? 1u : 0u;
+        asm volatile("" : "+r"(w0), "+r"(w1));
+        const uint8_t* yrow = yp + (long long)(2 * cy) * pitch + xv;
+        // both luma rows of a chroma row exist in the frame (H even), bytes beyond the row's last pixel lie inside the pitch.
+        // (Requesting the thread's next chroma row before converting the current one was measured: 92.2 us again for the
+        // chrominance mode, 70.2 instead of 61.4 us for green only — 80 registers cost more occupancy than the overlap gains.)
+        const uint4 c4 = ld_stream_v4(uvp + (long long)cy * pitch + xv);
+        const uint4 a4 = ld_stream_v4(yrow), b4 = ld_stream_v4(yrow + pitch);
+        const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+        const uint32_t yw[2][4] = {{a4.x, a4.y, a4.z, a4.w}, {b4.x, b4.y, b4.z, b4.w}};
+        uint32_t pG[2] = {0, 0}, pR[2] = {0, 0}, pB[2] = {0, 0};
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+          const int uu = (int)__byte_perm(cw[pr >> 1], 0, 0x4440 + 2 * (pr & 1));
+          const int vv = (int)__byte_perm(cw[pr >> 1], 0, 0x4441 + 2 * (pr & 1));
+          const int guv = ((1 << 19) - 16 * CY - 128 * (CVG + CUG)) + CVG * vv + CUG * uu;
+          const int ruv = ((1 << 19) - 16 * CY - 128 * CVR) + CVR * vv;
+          const int buv = ((1 << 19) - 16 * CY - 128 * CUB) + CUB * uu;
+#pragma unroll
+          for (int ro = 0; ro < 2; ++ro) {
+            const int y0 = max((int)__byte_perm(yw[ro][pr >> 1], 0, 0x4440 + 2 * (pr & 1)), 16);
+            const int y1 = max((int)__byte_perm(yw[ro][pr >> 1], 0, 0x4441 + 2 * (pr & 1)), 16);
+            pG[ro] = __dp4a(pack_sat_u8((y0 * CY + guv) >> 20, (y1 * CY + guv) >> 20, 0u), m2[pr], pG[ro]);
+            if (ALL) {
+              if (WANT_SUMS) {
+                pR[ro] = __dp4a(pack_sat_u8((y0 * CY + ruv) >> 20, (y1 * CY + ruv) >> 20, 0u), m2[pr], pR[ro]);
+                pB[ro] = __dp4a(pack_sat_u8((y0 * CY + buv) >> 20, (y1 * CY + buv) >> 20, 0u), m2[pr], pB[ro]);
+              } else {                                        // {R0, B0, R1, B1}: both channels of both pixels in one dp4a
+                const uint32_t q0 = pack_sat_u8((y0 * CY + ruv) >> 20, (y0 * CY + buv) >> 20, 0u);
+                pB[ro] = __dp4a(pack_sat_u8((y1 * CY + ruv) >> 20, (y1 * CY + buv) >> 20, q0), m4[pr], pB[ro]);
+              }
+            }
+          }
+        }
+        sG += pG[0] * w0 + pG[1] * w1;
+        if (ALL) { sB += pB[0] * w0 + pB[1] * w1; if (WANT_SUMS) sR += pR[0] * w0 + pR[1] * w1; }
+      }
+    }
+  }
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(ncols > 0 ? ncols : 0);
+  unsigned long long tB = warp_sum_u64(sB), tG = warp_sum_u64(sG), tR = warp_sum_u64(sR);
+  __shared__ unsigned long long part[WARPS][3];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { part[wid][0] = tB; part[wid][1] = tG; part[wid][2] = tR; }
+  __syncthreads();
+  if (gt == 0) {
+    tB = tG = tR = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { tB += part[w][0]; tG += part[w][1]; tR += part[w][2]; }
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tR; o.w = N;
+      *reinterpret_cast<ulonglong4*>(out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(2 * (long long)tG - (long long)tB - (long long)tR + 2 * (long long)N) / (double)(4 * N);   // tR = 0 when tB carries B + R
+    out_value[roi] = val;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // F1 on a frame the reference would first have resized: VideoReader runs
 // cv2.resize(frame, target_res[::-1]) on file input (video_reader.py:95-96) and the ROI boxes live in the resized
@@ -1057,10 +1173,20 @@ extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_b
   const bool all = mode != BPV_GREEN;
 #define BPV_NV12(S, V, A) roi_nv12_kernel<S, V, A><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, \
                                                                               (unsigned long long*)out_sums, out_value)
-  if (out_sums) { if (vec) BPV_NV12(true, true, true); else BPV_NV12(true, false, true); }
+#define BPV_NV12V(S, A) roi_nv12_vec_kernel<S, A><<<(unsigned)n, 128, 0, st>>>(frames, frame_stride_bytes, pitch_bytes, H, W, R, mode, n, boxes, \
+                                                                             (unsigned long long*)out_sums, out_value)
+  // BPV_NV12_OLD=1: the per-pixel-predicate kernel on aligned planes too (measurement switch)
+  static const bool old_body = [] { const char* e = getenv("BPV_NV12_OLD"); return e && e[0] == '1'; }();
+  if (vec && !old_body) {
+    if (out_sums) BPV_NV12V(true, true);
+    else if (all) BPV_NV12V(false, true);
+    else BPV_NV12V(false, false);
+  }
+  else if (out_sums) { if (vec) BPV_NV12(true, true, true); else BPV_NV12(true, false, true); }
   else if (all) { if (vec) BPV_NV12(false, true, true); else BPV_NV12(false, false, true); }
   else { if (vec) BPV_NV12(false, true, false); else BPV_NV12(false, false, false); }
 #undef BPV_NV12
+#undef BPV_NV12V
   return check_launch("bpv_roi_sample_nv12");
 }
 
