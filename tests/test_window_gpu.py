@@ -118,7 +118,7 @@ METHOD_SETS = [
 ]
 
 
-@pytest.mark.parametrize('W,fps', [(64, 30.0), (300, 30.0), (500, 120.0)])
+@pytest.mark.parametrize('W,fps', [(64, 30.0), (250, 30.0), (300, 30.0), (500, 120.0)])   # 250 / 300: the specialised FIR tiles
 @pytest.mark.parametrize('methods', METHOD_SETS, ids=lambda m: '-'.join(map(str, m)) or 'none')
 def test_preprocess_matches_oracle(methods, W, fps):
     from bpv import ops
@@ -295,7 +295,7 @@ def test_dft_tensor_core_path_matches_oracle(methods, force, W, fps, monkeypatch
                     np.testing.assert_allclose(pm[s, r], ey, rtol=1e-7, atol=1e-9 * max(1.0, abs(ey)))
 
 
-@pytest.mark.parametrize('W,fps', [(64, 30.0), (300, 30.0), (600, 120.0)])
+@pytest.mark.parametrize('W,fps', [(64, 30.0), (250, 30.0), (300, 30.0), (600, 120.0)])   # 250 / 300: specialised xcorr leading dimensions
 @pytest.mark.parametrize('methods', [[orc.FILTER_BUTTER], [orc.DETREND_LINEAR, orc.FILTER_FIR], [orc.INTERP_CUBIC, orc.FILTER_BUTTER], []],
                          ids=lambda m: '-'.join(map(str, m)) or 'none')
 def test_xcorr_matches_oracle(methods, W, fps):
