@@ -346,7 +346,7 @@ class BatchedSignalProcessor:
             env = os.environ.get('BPV_DFT_TC')
             interp = any(m in (_cabi.INTERP_LINEAR, _cabi.INTERP_CUBIC) for m in self.methods)
             if (env[:1] == '1') if env is not None else interp:
-                n_spec = 5              # dft_image + seal + dft_tc_tma + dft_peak kernels + spectrum_dense_kernel for the flagged windows
+                n_spec = 6              # dft_image + seal + dft_split + dft_tc_tma2 + dft_peak kernels + spectrum_dense_kernel for the flagged windows
         n_push = 2 if _designed else 1
         self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P else 0)
         if not self.store_arrays and self.discard_scratch:

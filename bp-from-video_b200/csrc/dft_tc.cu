@@ -708,12 +708,171 @@ __global__ void __launch_bounds__(DTM_THREADS, 1) dft_tc_tma_kernel(const double
   tc_teardown(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Both operands by TMA (round 2, last step).  In dft_tc_tma_kernel the 16 producer warps convert the float64 samples of every
+// k block into the hi / lo tf32 A operand while the tensor core waits: wait for the stage, convert, store, proxy fence, arrive
+// — ~0.95 us per 16-sample block whatever the ring depths are (profiles/README.md), against 0.23 us of MMAs.  The split does
+// not depend on the bin chunk, so it is done ONCE per launch by dft_split_kernel into ready-made A images (one 16 KB image
+// per (128-signal tile, k block), the same canonical layout) in the caller's workspace; every CTA of a signal tile then
+// fetches them with cp.async.bulk exactly like the twiddle images.  The CTA is three roles and no conversion:
+//   warp 4, lane 0   TMA producer: A image + B image of k block kb into stage kb % NST (one mbarrier, expect_tx of both)
+//   warp 5, lane 0   MMA issuer: waits the stage, 6 tcgen05.mma (3xTF32), tcgen05.commit releases the stage
+//   warps 0-3        epilogue: tcgen05.ld of the 128 accumulator rows once the last commit has landed
+// ---------------------------------------------------------------------------------------------
+constexpr int DT2_THREADS = 192;
+constexpr int DT2_NST_MAX = 8;
+constexpr int DT2_RING = 208 * 1024;
+constexpr int DT2_OFF_BAR = DT2_RING;                        // full[8] empty[8] done (u64 each) | tmem slot (u32)
+constexpr int DT2_NBAR = 2 * DT2_NST_MAX + 1;
+constexpr int DT2_SMEM = DT2_OFF_BAR + 8 * DT2_NBAR + 16;
+
+__host__ __device__ inline long long dtc_split_bytes(int W, long long nsig) {
+  const long long NB = (W + DTC_KB - 1) / DTC_KB, mt = (nsig + TC_M - 1) / TC_M;
+  return mt * NB * DTM_A_BYTES + ((mt * TC_M * 4 + 255) / 256) * 256;      // A images | int bad[rows]
+}
+
+// thread = (signal row, chunk of 4 consecutive samples): the lanes of a warp take 32 consecutive rows of one chunk, so the
+// image stores are coalesced (512 contiguous bytes per warp) and every lane reads exactly one 32-byte sector of its row
+__global__ void __launch_bounds__(256) dft_split_kernel(const double* __restrict__ proc_y, int W, long long nsig,
+                                                        unsigned char* __restrict__ a_img, int* __restrict__ bad) {
+  const int NB = (W + DTC_KB - 1) / DTC_KB, NC = NB * 4;
+  const long long rows = ((nsig + TC_M - 1) / TC_M) * TC_M;
+  const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long rblk = item / (32LL * NC);
+  const int within = (int)(item - rblk * (32LL * NC));
+  const int g = within >> 5, lr = within & 31;
+  const long long row = rblk * 32 + lr;
+  if (row >= rows) return;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  if (row < nsig) {
+    const double* y = proc_y + row * W;
+    const int j = 4 * g;
+    if (j + 3 < W && (W & 1) == 0 && (reinterpret_cast<uintptr_t>(proc_y) & 15) == 0) {
+      const double2 p0 = *reinterpret_cast<const double2*>(y + j), p1 = *reinterpret_cast<const double2*>(y + j + 2);
+      v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (j + e < W) v[e] = y[j + e];
+    }
+  }
+  float hv[4], lv[4];
+  bool isbad = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    isbad |= !isfinite(v[e]);
+    hv[e] = tc_hi((float)v[e]);
+    lv[e] = (float)(v[e] - (double)hv[e]);
+  }
+  const long long mt = row / TC_M;
+  const int r = (int)(row % TC_M), kb = g >> 2, c = g & 3;
+  float4* img = reinterpret_cast<float4*>(a_img + (mt * NB + kb) * DTM_A_BYTES);
+  img[c * TC_M + r] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+  img[4 * TC_M + c * TC_M + r] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+  if (isbad) bad[row] = 1;                                   // zeroed by the launcher (cudaMemsetAsync) before this kernel
+}
+
+__global__ void __launch_bounds__(DT2_THREADS, 1) dft_tc_tma2_kernel(int W, long long nsig, int max_bins, int BC,
+                                                                     const unsigned char* __restrict__ a_img, const int* __restrict__ bad,
+                                                                     const unsigned char* __restrict__ img,
+                                                                     float* __restrict__ mags, int32_t* __restrict__ num_bins) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int n = W, F = n / 2 + 1;
+  uint8_t* barp = smem + DT2_OFF_BAR;
+  const uint32_t bar = tc_smem_u32(barp), slot = bar + 8 * DT2_NBAR;
+  const uint32_t full = bar, empty = bar + 8 * DT2_NST_MAX, done = bar + 16 * DT2_NST_MAX;
+  const uint32_t img_bytes = 256u * (uint32_t)BC;
+  const uint32_t stage_bytes = DTM_A_BYTES + ((img_bytes + 1023u) & ~1023u);
+  int NST = DT2_RING / (int)stage_bytes;
+  if (NST > DT2_NST_MAX) NST = DT2_NST_MAX;
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "n"(TC_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (tid == 0) {
+      for (int s_ = 0; s_ < 2 * DT2_NST_MAX + 1; ++s_)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u * s_) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(barp + 8 * DT2_NBAR);
+
+  const long long sig0 = (long long)blockIdx.x * TC_M;
+  const int k0 = blockIdx.y * BC;
+  const int NB = (n + DTC_KB - 1) / DTC_KB;
+  const uint32_t smem0 = tc_smem_u32(smem);
+  if (wid == 4) {
+    if (lane == 0) {                                         // ---- TMA producer
+      const unsigned char* my_a = a_img + (long long)blockIdx.x * NB * DTM_A_BYTES;
+      const unsigned char* my_b = img + 256 + (long long)blockIdx.y * NB * img_bytes;
+      for (int kb = 0; kb < NB; ++kb) {
+        const int s_ = kb % NST;
+        if (kb >= NST) tc_wait_bounded(empty + 8u * s_, (uint32_t)((kb / NST - 1) & 1));       // the MMAs of block kb - NST have read the stage
+        const uint32_t dst = smem0 + (uint32_t)s_ * stage_bytes, fb = full + 8u * s_;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"((uint32_t)DTM_A_BYTES + img_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(my_a + (long long)kb * DTM_A_BYTES), "r"((uint32_t)DTM_A_BYTES), "r"(fb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst + (uint32_t)DTM_A_BYTES), "l"(my_b + (long long)kb * img_bytes), "r"(img_bytes), "r"(fb) : "memory");
+      }
+    }
+  } else if (wid == 5) {
+    if (lane == 0) {                                         // ---- MMA issuer
+      const uint32_t b_lbo = 32u * (uint32_t)BC, b_lo_off = 128u * (uint32_t)BC;   // N = 2 BC columns
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BC) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      for (int kb = 0; kb < NB; ++kb) {
+        const int s_ = kb % NST;
+        tc_wait_bounded(full + 8u * s_, (uint32_t)((kb / NST) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem0 + (uint32_t)s_ * stage_bytes, sb = sa + (uint32_t)DTM_A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < DTC_KB / 8; ++ks) {
+          const uint64_t dah = tc_desc(sa + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), dal = tc_desc(sa + 8192 + ks * 2 * TC_A_LBO, TC_A_LBO, TC_SBO);
+          const uint64_t dbh = tc_desc(sb + ks * 2 * b_lbo, b_lbo, TC_SBO), dbl = tc_desc(sb + b_lo_off + ks * 2 * b_lbo, b_lbo, TC_SBO);
+          tc_mma_tf32_n(tmem, dah, dbh, idesc, (kb | ks) != 0);
+          tc_mma_tf32_n(tmem, dal, dbh, idesc, 1);
+          tc_mma_tf32_n(tmem, dah, dbl, idesc, 1);
+        }
+        tc_commit(empty + 8u * s_);
+      }
+      tc_commit(done);                                       // arrives when every MMA issued so far has completed
+    }
+  }
+  tc_wait_bounded(done, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid < TC_M) {
+    const long long sig = sig0 + tid;
+    const bool rowbad = bad[sig] != 0;                       // bad[] covers the padded rows of the last tile
+    const float sc = 2.f / (float)n;
+    for (int c32 = 0; 32 * c32 < BC; ++c32) {
+      float re[32], im[32];
+      __syncwarp();
+      tc_load32(tmem, 32 * c32, re);
+      tc_load32(tmem, BC + 32 * c32, im);
+      if (sig < nsig && !rowbad) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + 32 * c32 + i;
+          if (32 * c32 + i < BC && k < F && k < max_bins) mags[sig * max_bins + k] = sc * sqrtf(re[i] * re[i] + im[i] * im[i]);
+        }
+      }
+    }
+    if (sig < nsig && rowbad && blockIdx.y == 0) num_bins[sig] = -2;     // the float64 kernel takes this window
+    if (sig < nsig && !rowbad && blockIdx.y == 0) num_bins[sig] = -1;    // marker: coarse spectrum ready for dft_peak_kernel
+  }
+  tc_teardown(tmem);
+}
+
+long long dft_tc_split_bytes(int W, long long nsig) { return dtc_split_bytes(W, nsig); }
 long long dft_tc_image_bytes(int W) { return dtc_image_bytes(W); }
 
 // image_ws: caller-owned, persistent device memory of dft_tc_image_bytes(W) bytes (zero-initialised once) for the TMA-fed
 // kernel, or NULL for the kernel that generates its operands itself.  BPV_DFT_TMA=0 forces the latter (measurement switch).
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
-                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, cudaStream_t st) {
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, void* split_ws,
+                  cudaStream_t st) {
   const int smem = dtc_smem(W), smem_p = W * 16;
   if (int rc = ensure_dyn_smem((const void*)dft_peak_kernel, smem_p)) return rc;
   const int F = W / 2 + 1;
@@ -747,8 +906,23 @@ int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long n
     if (int rc = check_launch("dft_image_kernel")) return rc;
     dft_image_seal_kernel<<<1, 1, 0, st>>>(W, BC, (unsigned char*)image_ws);
     if (int rc = check_launch("dft_image_seal_kernel")) return rc;
-    dft_tc_tma_kernel<<<grid, DTM_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, BC, (const unsigned char*)image_ws, mags, num_bins);
-    if (int rc = check_launch("dft_tc_tma_kernel")) return rc;
+    const char* esp = getenv("BPV_DFT_SPLIT");               // BPV_DFT_SPLIT=0: convert the samples inside the kernel (measurement switch)
+    if (split_ws && !(esp && esp[0] == '0')) {
+      if (int rc = ensure_dyn_smem((const void*)dft_tc_tma2_kernel, DT2_SMEM)) return rc;
+      const long long mt = (nsig + TC_M - 1) / TC_M, rows = mt * TC_M;
+      unsigned char* a_img = (unsigned char*)split_ws;
+      int* bad = (int*)(a_img + mt * NB * DTM_A_BYTES);
+      cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)rows * sizeof(int), st);
+      if (e != cudaSuccess) { set_error("dft split: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+      const long long items = rows * NB * 4;
+      dft_split_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(proc_y, W, nsig, a_img, bad);
+      if (int rc = check_launch("dft_split_kernel")) return rc;
+      dft_tc_tma2_kernel<<<grid, DT2_THREADS, DT2_SMEM, st>>>(W, nsig, max_bins, BC, a_img, bad, (const unsigned char*)image_ws, mags, num_bins);
+      if (int rc = check_launch("dft_tc_tma2_kernel")) return rc;
+    } else {
+      dft_tc_tma_kernel<<<grid, DTM_THREADS, DTM_SMEM, st>>>(proc_y, W, nsig, max_bins, BC, (const unsigned char*)image_ws, mags, num_bins);
+      if (int rc = check_launch("dft_tc_tma_kernel")) return rc;
+    }
   } else {
     if (int rc = ensure_dyn_smem((const void*)dft_tc_kernel, smem)) return rc;
     dft_tc_kernel<<<grid, DTC_THREADS, smem, st>>>(proc_y, W, nsig, max_bins, mags, num_bins);

@@ -18,8 +18,10 @@
 namespace bpv {
 
 long long dft_tc_image_bytes(int W);
+long long dft_tc_split_bytes(int W, long long nsig);
 int launch_dft_tc(const double* proc_x, const double* proc_y, int W, long long nsig, int max_bins, float* spec_f, float* mags,
-                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, cudaStream_t st);
+                  int32_t* num_bins, int32_t* peak_idx, double* peak_freq, double* peak_mag, void* image_ws, void* split_ws,
+                  cudaStream_t st);
 
 constexpr float LS_DELTA = 1.0e-4f;     // candidate band below the fp32 maximum (PSD is in [0, 1])
 constexpr int LS_SMALL_N = 24;          // below this every bin is evaluated in float64
@@ -780,7 +782,8 @@ static int64_t spectrum_coarse_bytes(const bpv_window_params* p, int32_t max_bin
 extern "C" int64_t bpv_spectrum_workspace_bytes(const bpv_window_params* p, int32_t max_bins) {
   if (!p) return -1;
   int64_t b = spectrum_coarse_bytes(p, max_bins);
-  if (p->transform == BPV_DFT_RFFT && p->window >= 16 && p->window <= 2048) b += bpv::dft_tc_image_bytes(p->window);
+  if (p->transform == BPV_DFT_RFFT && p->window >= 16 && p->window <= 2048)
+    b += (bpv::dft_tc_image_bytes(p->window) + 255) / 256 * 256 + bpv::dft_tc_split_bytes(p->window, (long long)p->S * p->jobs_per_stream * p->R);
   return b;
 }
 
@@ -830,8 +833,11 @@ extern "C" int bpv_window_spectrum(const double* proc_x, const double* proc_y, c
           coarse = (float*)workspace;
         }
         // the twiddle operand images live behind the coarse area when the caller's workspace has room for them
-        void* images = (workspace && workspace_bytes >= cb + dft_tc_image_bytes(W)) ? (void*)((unsigned char*)workspace + cb) : nullptr;
-        if (int rc = launch_dft_tc(proc_x, proc_y, W, nsig, max_bins, spec_f, coarse, num_bins, peak_idx, peak_freq, peak_mag, images, st)) return rc;
+        // and behind them the hi / lo images of this launch's samples (A operand), when there is room for those too
+        const int64_t ib = (dft_tc_image_bytes(W) + 255) / 256 * 256;
+        void* images = (workspace && workspace_bytes >= cb + ib) ? (void*)((unsigned char*)workspace + cb) : nullptr;
+        void* split = (images && workspace_bytes >= cb + ib + dft_tc_split_bytes(W, nsig)) ? (void*)((unsigned char*)workspace + cb + ib) : nullptr;
+        if (int rc = launch_dft_tc(proc_x, proc_y, W, nsig, max_bins, spec_f, coarse, num_bins, peak_idx, peak_freq, peak_mag, images, split, st)) return rc;
         only_flagged = 1;
       }
     }
