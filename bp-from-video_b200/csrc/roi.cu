@@ -1151,6 +1151,166 @@ __global__ void __launch_bounds__(128) roi_resized_kernel(const uint8_t* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused resize, staged variant (aligned frames, bilinear case): the ROI's SOURCE footprint is staged in shared memory with
+// 16-byte cp.async vectors exactly as the BGR kernel stages its tile (the byte-load kernel above issues 12 byte loads and ~90
+// instructions per output pixel), and the bilinear arithmetic is regrouped without changing a single intermediate value:
+//   * a thread owns one output column and a contiguous run of output rows; its column's two source pixels are 6 adjacent
+//     bytes at a loop-invariant offset, so two PRMTs with per-thread selectors turn four aligned 32-bit shared-memory loads
+//     into {B0 B1 G0 G1} and {R0 R1 . .}, and the horizontal pass  h = s0 * a0 + s1 * a1  is ONE dp2a per channel against the
+//     packed 11-bit weights (a0 | a1 << 16);
+//   * consecutive output rows share source rows (scale 1.5: every other one), so the horizontal result of the previous
+//     row's lower source row is kept in registers;
+//   * the vertical pass ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2 is two IMAD.HI with the weights pre-shifted
+//     by 16 (all operands are non-negative), >> 2 and the saturation come from one packed convert.
+// Output rows are processed in bands whose source rows fit the stage.
+// ---------------------------------------------------------------------------------------------
+struct RowTap4 { int i0, i1; uint32_t w0s, w1s; };          // source rows + 11-bit weights << 16
+struct ColTap2 { int i0; uint32_t wpair; };                 // left source column + (a0 | a1 << 16); the right one is i0 + 1 (a1 = 0 at the border)
+
+template <bool WANT_SUMS, bool ALL>
+__global__ void __launch_bounds__(128) roi_resized_staged_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+                                                                 int sh, int sw, int dh, int dw, int R, int mode, long long num_rois,
+                                                                 const int32_t* __restrict__ boxes,
+                                                                 unsigned long long* __restrict__ out_sums, double* __restrict__ out_value,
+                                                                 int smem_total, double scale_x, double scale_y) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  constexpr int THREADS = 128, WARPS = THREADS / 32;
+  const int gt = threadIdx.x;
+  const long long roi = blockIdx.x;
+  int xs = 0, xe = 0, ys = 0, ye = 0;
+  const int4 b = __ldg(reinterpret_cast<const int4*>(boxes) + roi);
+  const bool has_box = b.x != BPV_NO_BOX;
+  if (has_box) { py_slice(b.x, b.z, dw, xs, xe); py_slice(b.y, b.w, dh, ys, ye); }   // box lives in the RESIZED frame
+  const int nrows = ye - ys, ncols = xe - xs;
+  // dynamic shared memory (smem_total bytes): stage from the front, the ROI's row taps [nrows] at the back; the column tap is
+  // per thread (loop invariant), so the tables do not grow with the frame width
+  unsigned char* stage = rsm;
+  RowTap4* rtap = reinterpret_cast<RowTap4*>(rsm + smem_total) - (nrows > 0 ? nrows : 0);
+  const int stage_bytes = smem_total - (nrows > 0 ? nrows : 0) * (int)sizeof(RowTap4);
+  const uint8_t* fp = frames + (roi / R) * frame_stride;
+  uint32_t sB = 0, sG = 0, sR = 0;                           // !WANT_SUMS: sB carries B + R
+  __shared__ int s_xrange[2];
+  if (nrows > 0 && ncols > 0) {
+    // scale_x / scale_y = 1 / (dst / src) as cv::resize computes them: IEEE double divisions, done once on the host
+    for (int r = gt; r < nrows; r += THREADS) {
+      const ResizeTap t = resize_tap(ys + r, scale_y, sh, false);
+      rtap[r].i0 = t.i0; rtap[r].i1 = t.i1; rtap[r].w0s = (uint32_t)(unsigned short)t.w0 << 16; rtap[r].w1s = (uint32_t)(unsigned short)t.w1 << 16;
+    }
+    if (gt >= THREADS - 2) s_xrange[gt - (THREADS - 2)] = resize_tap(gt == THREADS - 2 ? xs : xe - 1, scale_x, sw, true).i0;
+    __syncthreads();
+    const int xmin = s_xrange[0], xlast = s_xrange[1];
+    const int xmax = xlast + 1 < sw ? xlast + 1 : sw - 1;
+    const int tile_x0 = (3 * xmin) & ~15;                     // staged bytes [tile_x0, tile_x0 + rowb) of every source row
+    const int rowb = (3 * xmax + 3 - tile_x0 + 15) & ~15;
+    const int rowb_s = rowb + 16;                             // row slot: the border column's don't-care bytes stay inside it
+    const int vpr = rowb >> 4;
+    const uint32_t sbase = smem_u32(stage);
+    const unsigned long long pol = l2_evict_first_policy();
+    // this thread's column(s) and row run inside a band
+    int rps, r0, c0;
+    if (ncols >= THREADS) { rps = 1; r0 = 0; c0 = gt; }
+    else { rps = THREADS / ncols; r0 = gt / ncols; c0 = gt - r0 * ncols; if (r0 >= rps) c0 = ncols; }
+    int rb = 0;
+    while (rb < nrows) {
+      const int src0 = rtap[rb].i0;
+      int re = nrows;                                         // the usual case: the whole footprint fits the stage
+      if ((rtap[nrows - 1].i1 - src0 + 1) * rowb_s > stage_bytes) {
+        re = rb + 1;
+        while (re < nrows && (rtap[re].i1 - src0 + 1) * rowb_s <= stage_bytes) ++re;   // rtap is monotone: uniform scan
+      }
+      const int nsrc = rtap[re - 1].i1 - src0 + 1;
+      {                                                       // (row, vector) walked without a division per vector
+        const int dr = THREADS / vpr, dv = THREADS - dr * vpr;
+        int rr = gt / vpr, v = gt - rr * vpr;
+        const uint8_t* g = fp + (long long)(src0 + rr) * row_stride + tile_x0 + 16 * v;
+        uint32_t d = sbase + (uint32_t)(rr * rowb_s + 16 * v);
+        const long long gstep = (long long)dr * row_stride + 16 * dv;
+        const uint32_t dstep = (uint32_t)(dr * rowb_s + 16 * dv);
+        const long long gwrap = row_stride - 16ll * vpr;
+        const uint32_t dwrap = (uint32_t)(rowb_s - 16 * vpr);
+        while (rr < nsrc) {
+          cp_async16_64B(d, g, pol);
+          rr += dr; v += dv; g += gstep; d += dstep;
+          if (v >= vpr) { v -= vpr; ++rr; g += gwrap; d += dwrap; }
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      const int band = re - rb, run = (band + rps - 1) / rps;
+      const int my0 = rb + r0 * run, my1 = my0 + run < re ? my0 + run : re;
+      for (int c = c0; c < ncols; c += THREADS) {
+        ColTap2 ct;
+        {
+          const ResizeTap t = resize_tap(xs + c, scale_x, sw, true);
+          ct.i0 = t.i0; ct.wpair = (uint32_t)(unsigned short)t.w0 | (uint32_t)(unsigned short)t.w1 << 16;
+        }
+        const int off = 3 * ct.i0 - tile_x0, shb = off & 3;
+        const uint32_t a1 = (uint32_t)(off & ~3), a2 = a1 + (shb == 3 ? 4u : 0u);
+        const int s2 = shb == 3 ? 1 : shb + 2;
+        const uint32_t sel1 = (uint32_t)(shb | (shb + 3) << 4 | (shb + 1) << 8 | (shb + 4) << 12);   // {B0 B1 G0 G1}
+        const uint32_t sel2 = (uint32_t)(s2 | (s2 + 3) << 4);                                       // {R0 R1 . .}
+        // branch-free row loop: both source rows of every output row go through the horizontal pass (keeping the previous
+        // row's result for the rows that share a source row — every other one at scale 1.5 — was measured slower: the two
+        // tests and the divergent copies cost more issue slots than the 12-instruction pass they save)
+        auto hpass = [&](int srow, uint32_t& hB, uint32_t& hG, uint32_t& hR) {
+          const uint32_t base = sbase + (uint32_t)((srow - src0) * rowb_s);
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(base + a1));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(base + a1 + 4u));
+          const uint32_t p1 = __byte_perm(w0, w1, sel1);
+          hG = __dp2a_hi(ct.wpair, p1, 0u) >> 4;
+          if (ALL) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(base + a2));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(base + a2 + 4u));
+            const uint32_t p2 = __byte_perm(w2, w3, sel2);
+            hB = __dp2a_lo(ct.wpair, p1, 0u) >> 4;
+            hR = __dp2a_lo(ct.wpair, p2, 0u) >> 4;
+          }
+        };
+#pragma unroll 2
+        for (int r = my0; r < my1; ++r) {
+          const RowTap4 tr = rtap[r];
+          uint32_t hB0 = 0, hG0 = 0, hR0 = 0, hB1 = 0, hG1 = 0, hR1 = 0;
+          hpass(tr.i0, hB0, hG0, hR0);
+          hpass(tr.i1, hB1, hG1, hR1);
+          const uint32_t g = (__umulhi(hG0, tr.w0s) + __umulhi(hG1, tr.w1s) + 2u) >> 2;
+          sG += g < 255u ? g : 255u;
+          if (ALL) {
+            const uint32_t bb = (__umulhi(hB0, tr.w0s) + __umulhi(hB1, tr.w1s) + 2u) >> 2;
+            const uint32_t rr = (__umulhi(hR0, tr.w0s) + __umulhi(hR1, tr.w1s) + 2u) >> 2;
+            if (WANT_SUMS) { sB += bb < 255u ? bb : 255u; sR += rr < 255u ? rr : 255u; }
+            else sB = __dp4a(pack_sat_u8((int)bb, (int)rr, 0u), 0x00000101u, sB);
+          }
+        }
+      }
+      rb = re;
+      if (rb < nrows) __syncthreads();                        // band consumed before the next one overwrites the stage
+    }
+  }
+  const unsigned long long N = (unsigned long long)(nrows > 0 ? nrows : 0) * (unsigned long long)(ncols > 0 ? ncols : 0);
+  unsigned long long tB = warp_sum_u64(sB), tG = warp_sum_u64(sG), tR = warp_sum_u64(sR);
+  __shared__ unsigned long long part[WARPS][3];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { part[wid][0] = tB; part[wid][1] = tG; part[wid][2] = tR; }
+  __syncthreads();
+  if (gt == 0) {
+    tB = tG = tR = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { tB += part[w][0]; tG += part[w][1]; tR += part[w][2]; }
+    if (WANT_SUMS) {
+      ulonglong4 o; o.x = tB; o.y = tG; o.z = tR; o.w = N;
+      *reinterpret_cast<ulonglong4*>(out_sums + 4 * roi) = o;
+    }
+    double val;
+    if (!has_box || N == 0) val = nan_f64();
+    else if (mode == BPV_GREEN) val = (double)tG / (double)N;
+    else val = (double)(2 * (long long)tG - (long long)tB - (long long)tR + 2 * (long long)N) / (double)(4 * N);   // tR = 0 when tB carries B + R
+    out_value[roi] = val;
+  }
+}
+
 }  // namespace bpv
 
 extern "C" int bpv_roi_sample_nv12(const uint8_t* frames, int64_t frame_stride_bytes, int64_t pitch_bytes,
@@ -1215,6 +1375,29 @@ extern "C" int bpv_roi_sample_resized_u8(const uint8_t* frames, int64_t frame_st
                                                                 dst_h, dst_w, R, mode, n, boxes,                             \
                                                                 (unsigned long long*)out_sums, out_value);                   \
   } while (0)
+  // staged variant: aligned frames, bilinear case (the exact 2x decimation keeps the byte-load kernel), and a stage that holds
+  // the two source rows of one output row at the frame's full width.  BPV_RESIZE_OLD=1: measurement switch.
+  static const bool old_body = [] { const char* e = getenv("BPV_RESIZE_OLD"); return e && e[0] == '1'; }();
+  const bool aligned = (((uintptr_t)frames | (uintptr_t)frame_stride_bytes | (uintptr_t)row_stride_bytes) & 15) == 0;
+  const bool area2 = src_w == 2 * dst_w && src_h == 2 * dst_h;
+  const int smem2 = 26 * 1024;                                        // 8 CTAs per SM
+  const long long rowslot = ((3ll * src_w + 15) & ~15ll) + 32;
+  if (aligned && !area2 && !old_body && 2 * rowslot + (long long)dst_h * (long long)sizeof(RowTap4) <= smem2) {
+#define BPV_RSZ2(S, A)                                                                                                      \
+  do {                                                                                                                      \
+    if (int rc = ensure_dyn_smem((const void*)roi_resized_staged_kernel<S, A>, smem2)) return rc;                            \
+    roi_resized_staged_kernel<S, A><<<(unsigned)n, 128, smem2, st>>>(frames, frame_stride_bytes, row_stride_bytes, src_h,    \
+                                                                     src_w, dst_h, dst_w, R, mode, n, boxes,                 \
+                                                                     (unsigned long long*)out_sums, out_value, smem2,        \
+                                                                     1.0 / ((double)dst_w / (double)src_w),                  \
+                                                                     1.0 / ((double)dst_h / (double)src_h));                 \
+  } while (0)
+    if (out_sums) BPV_RSZ2(true, true);
+    else if (mode != BPV_GREEN) BPV_RSZ2(false, true);
+    else BPV_RSZ2(false, false);
+#undef BPV_RSZ2
+    return check_launch("bpv_roi_sample_resized_u8");
+  }
   if (out_sums) BPV_RSZ(true, true);
   else if (mode != BPV_GREEN) BPV_RSZ(false, true);
   else BPV_RSZ(false, false);
