@@ -387,6 +387,53 @@ def time_family_wrappers(torch, ops, fam, only=None):
     return orig
 
 
+def _time_launches(torch, fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]))
+
+
+def run_ingest_resized(torch, frames, boxes_np, channel, peak):
+    """SURVEY 8f row 2 beside the headline: F1 with the VideoReader resize fused in front (1080p frames in HBM sampled as if
+    cv2.resize had produced 720p; boxes scaled to the 720p frame).  Same frames / launch size as the timed region."""
+    from bpv import ops, synth
+    S, T, H, W = frames.shape[:4]
+    dh, dw = H * 2 // 3, W * 2 // 3
+    b = boxes_np.reshape(S * T, 2, 4).copy()
+    ok = b[..., 0] != synth.NO_BOX
+    b[ok] = np.rint(b[ok] * (dw / W)).astype(np.int32)
+    bd = torch.from_numpy(b).to(frames.device)
+    fr = frames.view(S * T, H, W, 3)
+    ms = _time_launches(torch, lambda: ops.roi_sample_resized(fr, dh, dw, bd, channel))
+    src_bytes = roi_bytes(boxes_np, H, W)                     # the source footprint of the scaled boxes ~ the original boxes
+    return {'resized_720p': {'us_per_launch': ms * 1e3, 'frames_per_s': S * T / ms * 1e3, 'alg_bytes': int(src_bytes),
+                             'gbs': src_bytes / ms / 1e6, 'frac_hbm': src_bytes / ms / 1e6 / peak,
+                             'desc': f'{S * T} frames {W}x{H} BGR in HBM, boxes in the {dw}x{dh} frame cv2.resize would produce; 3 B per source pixel'}}
+
+
+def run_ingest_nv12(torch, dev, boxes_np, S, T, H, W, channel, peak):
+    """F1 straight from NV12 decoder surfaces (1.5 B/px) in HBM, same boxes and launch size as the timed region."""
+    from bpv import ops
+    nv = torch.empty((S * T, H * 3 // 2, W), dtype=torch.uint8, device=dev)
+    for i in range(0, S * T, 256):
+        nv[i:i + 256].random_(0, 256)
+    bd = torch.from_numpy(boxes_np.reshape(S * T, 2, 4).copy()).to(dev)
+    ms = _time_launches(torch, lambda: ops.roi_sample_nv12(nv, H, W, bd, channel))
+    alg = roi_bytes(boxes_np, H, W) / 2                       # 1.5 B/px instead of 3
+    del nv
+    torch.cuda.empty_cache()
+    return {'nv12': {'us_per_launch': ms * 1e3, 'frames_per_s': S * T / ms * 1e3, 'alg_bytes': int(alg), 'gbs': alg / ms / 1e6,
+                     'frac_hbm': alg / ms / 1e6 / peak,
+                     'desc': f'{S * T} NV12 surfaces {W}x{H} (Y plane + interleaved UV plane) in HBM; 1.5 B per ROI pixel'}}
+
+
 def run_other_shape(torch, name, wl, dev, world, steps=6, with_frames=True):
     """One of the other BASELINE shapes on this rank's GPU: prefill the rings, then `steps` timed steps of one new frame per
     stream (F1 when the shape has frames, push, F2, F3, F4; window evaluated once per step per stream); N > 1: + gather."""
@@ -644,8 +691,20 @@ def run_gpu(args, wl):
     fma = measure_fma_peaks(torch, dev) if rank == 0 else None
     pcie = measure_pcie(torch, dev) if rank == 0 else None
     sched = {'overlap_mask': eng.overlap, 'design_cache': eng._dcache is not None}
+    # ---- ingest variants of F1, informational: same launch size, frames / surfaces resident in HBM
+    ingest = {}
+    if rank == 0 and world == 1 and not args.no_other:
+        try:
+            ingest.update(run_ingest_resized(torch, frames, boxes_np, getattr(_cabi, wl['channel']), peaks()[0]))
+        except Exception as e:
+            ingest['resized_720p'] = {'error': f'{type(e).__name__}: {e}'[:300]}
     del frames, eng
     torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_other:
+        try:
+            ingest.update(run_ingest_nv12(torch, dev, boxes_np, S, T, H, W, getattr(_cabi, wl['channel']), peaks()[0]))
+        except Exception as e:
+            ingest['nv12'] = {'error': f'{type(e).__name__}: {e}'[:300]}
 
     # ---- the other named shapes (every rank takes part when N > 1: c5 is sharded over the ranks)
     other = {}
@@ -779,6 +838,8 @@ def run_gpu(args, wl):
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    if ingest:
+        line['ingest'] = ingest
     if other:
         line['other_shapes'] = other
     if lat is not None:
