@@ -19,10 +19,12 @@ __device__ __forceinline__ int xt_index(int j, int LD) { return (j % RT) * LD + 
 // LDC / KC != 0: leading dimension / padded tap count as compile-time constants.  With run-time values every tap block opens
 // with a dependent chain (constant-bank load -> two IMADs -> LDS -> first FMA) and every operand load needs its own address
 // computation: 29 integer instructions and ~17 % of the stall samples of the FIR loop (profiles/r2l_c2 source view).
-template <int RT, typename T, int LDC = 0, int KC = 0>
+// CVALID > 0 (run-time c_valid): c holds only c_valid coefficients (e.g. the taps as the design kernel left them in global
+// memory) and the padding up to K is supplied as zeros here instead of by a zero-padded copy.
+template <int RT, typename T, int LDC = 0, int KC = 0, bool CGUARD = false>
 __device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c, int K_rt,
                                           const T* __restrict__ XT, int LD_rt, int j0,
-                                          int kb_begin = 0, int kb_end = 0x7fffffff) {
+                                          int kb_begin = 0, int kb_end = 0x7fffffff, int c_valid = 0) {
   const int LD = LDC ? LDC : LD_rt;
   const int K = KC ? KC : K_rt;
   const int col0 = j0 / RT;
@@ -36,7 +38,7 @@ __device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c,
   for (int kb = kb_begin; kb < kb_end; ++kb) {
 #pragma unroll
     for (int kk = 0; kk < RT; ++kk) {
-      const T ck = cc[kk];
+      const T ck = (!CGUARD || kb * RT + kk < c_valid) ? cc[kk] : (T)0;
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r] = fma(ck, w[(r - kk + RT) % RT], acc[r]);
       w[RT - 1 - kk] = xn[(RT - 1 - kk) * LD];      // X[j0 - k - 1] replaces X[j0 - k + RT - 1]

@@ -48,7 +48,7 @@ struct PreLayout {        // per-warp shared-memory plan, in bytes
   int yv, xv, posv, posb, buf0, buf1, coef, total;
   int buf_len;            // doubles in buf0
   // FIR sub-plan inside buf0 (doubles): merged path  XT [0, fir_c) | c [fir_c, fir_c + Kmax)
-  //                                     two-pass path XT [0, fir_gt) | GT [fir_gt, fir_b) | b [fir_b, +136) | zi [+136, +264)
+  //                                     two-pass path XT [0, fir_gt) | GT [fir_gt, fir_b)
   int fir_c, fir_gt, fir_b;
 };
 
@@ -84,7 +84,7 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p) {
     const int T = p.fir_taps, nf = W < T - 1 ? W : T - 1;          // the two-pass path only sees windows of n < T samples
     L.fir_gt = 8 * fir_ld_fwd(nf, T);
     L.fir_b = L.fir_gt + 10 * fir_ld_bwd(nf, T);
-    int need = L.fir_b + 136 + 128;
+    int need = L.fir_b;                                              // taps / zi stay in global memory (fir_filtfilt)
     if (W >= T) {
       const int x8 = 8 * fir_merged_ld(W, T, 8), x10 = 10 * fir_merged_ld(W, T, 10);
       L.fir_c = x8 > x10 ? x8 : x10;
@@ -560,19 +560,11 @@ constexpr int FIR_RTB = 10;   // backward pass: n outputs (300) = ONE round of 3
 __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) {
   const int Kp = (T + FIR_RT - 1) / FIR_RT * FIR_RT;
   const int KpB = (T + FIR_RTB - 1) / FIR_RTB * FIR_RTB;
-  double* b = w.buf0 + w.fir_b;   // [max(Kp, KpB)] zero padded
-  double* zi = b + 136;           // [T-1]
-  {   // all nine global loads of the lane in flight before the first store (taps 0..135 zero padded | lfilter_zi from the design kernel)
-    double tb[5], tz[4];
-#pragma unroll
-    for (int u = 0; u < 5; ++u) { const int i = w.lane + 32 * u; tb[u] = i < T ? taps_g[i] : 0.0; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = w.lane + 32 * u; tz[u] = i < T - 1 ? taps_g[128 + i] : 0.0; }
-#pragma unroll
-    for (int u = 0; u < 5; ++u) { const int i = w.lane + 32 * u; if (i < 136) b[i] = tb[u]; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = w.lane + 32 * u; if (i < T - 1) zi[i] = tz[u]; }
-  }
+  // Taps and lfilter_zi are read where the design kernel left them (global memory, L1 / L2 resident): this two-pass form only
+  // serves windows shorter than the filter (a stream's first T - 1 frames), and a zero-padded shared-memory copy of both cost
+  // every warp of the launch 2 KB — the difference between 18 and 21 resident warps per SM for the steady-state windows.
+  const double* __restrict__ b = taps_g;          // [T] (corr_tile supplies the zero padding up to Kp / KpB)
+  const double* __restrict__ zi = taps_g + 128;   // [T-1]
   const int n = w.n, dpl = 3 * T, p = n <= dpl ? n - 1 : dpl;  // signal_processor.py:233-234
   const int L = n + 2 * p;
   const int fa = p, fb = (p + n - 1 + T - 1) < (L - 1) ? (p + n - 1 + T - 1) : (L - 1);   // forward outputs needed
@@ -607,7 +599,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
       double acc[FIR_RT];
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) acc[r] = 0.0;
-      corr_tile<FIR_RT, double>(acc, b, Kp, XT, LD, j0);
+      corr_tile<FIR_RT, double, 0, 0, true>(acc, b, Kp, XT, LD, j0, 0, 0x7fffffff, T);
 #pragma unroll
       for (int r = 0; r < FIR_RT; ++r) {
         const int i = i0 + r;
@@ -628,7 +620,7 @@ __device__ void fir_filtfilt(Warp& w, const double* __restrict__ taps_g, int T) 
       double acc[FIR_RTB];
 #pragma unroll
       for (int r = 0; r < FIR_RTB; ++r) acc[r] = 0.0;
-      corr_tile<FIR_RTB, double>(acc, b, KpB, GT, LDB, j0);
+      corr_tile<FIR_RTB, double, 0, 0, true>(acc, b, KpB, GT, LDB, j0, 0, 0x7fffffff, T);
 #pragma unroll
       for (int r = 0; r < FIR_RTB; ++r) {
         const int i = i0 + r;
@@ -918,7 +910,9 @@ static int launch_preprocess(const double* ring_t, const double* ring_y, const b
   BPV_REQUIRE(per_warp <= max_smem, BPV_E_TOO_LARGE, "bpv_window_preprocess: window %d needs %d B of shared memory per signal",
               p.window, L.total);
   // warps per CTA: the value in 1..4 (__launch_bounds__(128)) that keeps the most warps resident per SM
-  const int reg_warps = 4 * MINB;                                // what the register budget of this instantiation allows
+  // what the register budget of this instantiation allows: 4 MINB warps by the launch bound; one-warp CTAs of a 96-register
+  // instantiation fit 21 (65536 / (96 * 32))
+  const int reg_warps = MINB >= 5 ? 21 : 4 * MINB;
   int wpb = 1, best = 0;
   for (int c = 1; c <= 4; ++c) {
     const int per_block = c * per_warp + 1024;                   // + per-CTA reservation
