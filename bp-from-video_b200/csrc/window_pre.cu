@@ -658,16 +658,17 @@ __device__ void fir_merged(Warp& w, const double* __restrict__ ac_g, int T) {
   const double y_first = w.yv[0], y_last = w.yv[n - 1];
   // odd extension (scipy.signal._arraytools.odd_ext): head 2*y[0] - y[p-i], body y[i-p], tail 2*y[n-1] - y[2n-2+p-i];
   // indices outside [0, L) only meet the zero taps k > 2M
+  // storage index jj = i - xbase, written segment by segment (zeros | head | body | tail | zeros): one select-free loop per
+  // segment instead of five selects per element (the single loop was 9 % of the kernel's instructions)
   const int total = RT * (K / RT + tiles);
-#pragma unroll 3
-  for (int jj = w.lane; jj < total; jj += 32) {
-    const int i = jj + xbase;
-    const bool inside = i >= 0 && i < L, hd = i < p, tl = i >= p + n;
-    const int src = hd ? p - i : (tl ? 2 * n - 2 + p - i : i - p);
-    const double y = w.yv[inside ? src : 0];
-    const double v = hd ? 2.0 * y_first - y : (tl ? 2.0 * y_last - y : y);
-    XT[xt_index<RT>(jj, LD)] = inside ? v : 0.0;
-  }
+  const int j_h = xbase < 0 ? -xbase : 0;                         // first element of the extension (i = 0)
+  const int j_b = p - xbase, j_t = p + n - xbase;                  // body / tail start
+  const int j_e = L - xbase < total ? L - xbase : total;           // end of the extension inside the buffer
+  for (int jj = w.lane; jj < j_h; jj += 32) XT[xt_index<RT>(jj, LD)] = 0.0;
+  for (int jj = j_h + w.lane; jj < j_b; jj += 32) XT[xt_index<RT>(jj, LD)] = 2.0 * y_first - w.yv[j_b - jj];           // p - i
+  for (int jj = j_b + w.lane; jj < j_t && jj < total; jj += 32) XT[xt_index<RT>(jj, LD)] = w.yv[jj - j_b];           // i - p
+  for (int jj = j_t + w.lane; jj < j_e; jj += 32) XT[xt_index<RT>(jj, LD)] = 2.0 * y_last - w.yv[2 * n - 2 - (jj - j_b)];   // 2n-2+p-i
+  for (int jj = (j_e > j_t ? j_e : j_t) + w.lane; jj < total; jj += 32) XT[xt_index<RT>(jj, LD)] = 0.0;
   __syncwarp();
   for (int t = w.lane; t < tiles; t += 32) {
     double acc[RT];
