@@ -246,10 +246,13 @@ __global__ void __launch_bounds__(128) spectrum_dense_kernel(const double* __res
 // __syncwarp between stages); shorter windows (warm-up) use a warp-level direct DFT with their own twiddles.
 // The CTA-per-signal version spent its time in ~25 __syncthreads with little work between them (197 us per
 // 16 384 signals); this one is ~1 k warp instructions per signal.
-// smem: CTA table tw[256] (cos, sin) | per warp: ys[W] | buf[512] | mags[130] | z[256]
+// smem: CTA table tw[256] (cos, sin) | per warp: ys[W] | buf[576]   (windows shorter than 256 samples are ONE segment of
+// nperseg = n: their windowed segment overwrites ys in place and their <= 128 bins stay in registers)
 // ---------------------------------------------------------------------------------------------
 constexpr int WELCH_WPB = 4;
-__host__ __device__ inline int welch_warp_doubles(int W) { return W + 576 + 130 + 256; }
+constexpr int WELCH_MINB = 5;          // 96 registers; 6 CTAs per SM (80 registers, small spills) measured no faster: the kernel
+                                       // is bound by shared-memory wavefronts (64 % of peak), not by occupancy
+__host__ __device__ inline int welch_warp_doubles(int W) { return W + 576; }
 // FFT buffer index padding: one spare complex slot per 8 keeps the strided accesses of the late passes and the
 // 4-element groups of the last pass on distinct banks
 __device__ __forceinline__ int wpad(int e) { return e + (e >> 3); }
@@ -263,10 +266,10 @@ __device__ __forceinline__ double2 cmulc(double2 d, double2 t) {
 // each lane owns two groups of four elements i, i+Q, i+2Q, i+3Q (i mod 4Q < Q).  Natural-order input, after the four
 // passes Q = 64, 16, 4, 1 the output is in bit-reversed order.  Twiddles: A = W_4Q^p, -iA = W_4Q^(p+Q), C = W_2Q^p with
 // p = i mod Q, read from the CTA's table tw[k] = exp(+2 pi i k / 256).
-template <int Q>
+template <int Q, int GROUPS = 2>      // GROUPS x 32 groups of four elements: 2 for 256 points, 1 for 128
 __device__ __forceinline__ void welch_fft_pass(double2* __restrict__ fz, const double2* __restrict__ tw, int lane) {
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < GROUPS; ++j) {
     const int g = lane + 32 * j;
     const int pq = g & (Q - 1);
     const int i = (g / Q) * (4 * Q) + pq;
@@ -292,7 +295,7 @@ __device__ __forceinline__ void welch_fft_pass(double2* __restrict__ fz, const d
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const double* __restrict__ proc_x,
+__global__ void __launch_bounds__(32 * WELCH_WPB, WELCH_MINB) welch_warp_kernel(const double* __restrict__ proc_x,
                                                                     const double* __restrict__ proc_y,
                                                                     const bpv_window_params p, int max_bins, long long nsig,
                                                                     int only_flagged, float* __restrict__ spec_f, float* __restrict__ spec_mag,
@@ -311,8 +314,6 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const dou
   if (!mine) return;
   double* ys = sm + 512 + (size_t)wid * welch_warp_doubles(W);
   double* buf = ys + W;            // FFT: 256 complex (re, im interleaved); direct DFT: cos[256] | sin[256]
-  double* mags = buf + 576;
-  double* z = mags + 130;
   const double* px = proc_x + sig * W;
   const double* py = proc_y + sig * W;
 
@@ -351,58 +352,77 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const dou
   if (!fft) {
     for (int i = lane; i < N; i += 32) sincospi(2.0 * (double)i / (double)N, &ds[i], &dc[i]);
   }
-  for (int k = lane; k < F; k += 32) mags[k] = 0.0;
-  __syncwarp();
   double sw = 0.0;
   for (int i = lane; i < N; i += 32) { const double wj = 0.5 - 0.5 * (fft ? tw[i].x : dc[i]); sw = fma(wj, wj, sw); }
   const double scale = 1.0 / (fs * warp_sum(sw));
-  double facc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // FFT path: power sums of the bins this lane owns (positions lane + 32 j)
+  double facc[5] = {0, 0, 0, 0, 0};               // FFT path: power sums of the bins this lane owns (lane + 32 j; lane 0: bin 128)
+  double dm[4] = {0, 0, 0, 0};                    // direct path: bins lane + 32 j (F <= 128)
   for (int sg = 0; sg < nseg; ++sg) {
     const double* seg = ys + sg * hop;
     double a = 0.0;
     for (int i = lane; i < N; i += 32) a += seg[i];
     const double mean = warp_sum(a) / (double)N;
     if (fft) {
+      // The segment is real: its 256-point transform comes from ONE 128-point complex FFT of z[m] = x[2m] + i x[2m+1]
+      // (half the butterflies and — what bounds this kernel — half the shared-memory wavefronts of the complex 256-point FFT):
+      //   E[k] = (Z[k] + conj Z[128-k]) / 2,  O[k] = (Z[k] - conj Z[128-k]) / 2i,  X[k] = E[k] + exp(-2 pi i k / 256) O[k],  k = 0..128
       double2* fz = reinterpret_cast<double2*>(buf);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = lane + 32 * j;
-        fz[wpad(i)] = make_double2((seg[i] - mean) * (0.5 - 0.5 * tw[i].x), 0.0);
+      for (int j = 0; j < 4; ++j) {
+        const int m = lane + 32 * j;
+        const double2 sv = *reinterpret_cast<const double2*>(seg + 2 * m);
+        fz[wpad(m)] = make_double2((sv.x - mean) * (0.5 - 0.5 * tw[2 * m].x), (sv.y - mean) * (0.5 - 0.5 * tw[2 * m + 1].x));
       }
       __syncwarp();
-      welch_fft_pass<64>(fz, tw, lane);
-      welch_fft_pass<16>(fz, tw, lane);
-      welch_fft_pass<4>(fz, tw, lane);
-      welch_fft_pass<1>(fz, tw, lane);
-      // bin k sits at position brev8(k): every lane takes the contiguous positions lane + 32 j and keeps its own bins
+      welch_fft_pass<32, 1>(fz, tw, lane);         // 128-point radix-2 DIF: spans 64 + 32, 16 + 8, 4 + 2, then the last stage
+      welch_fft_pass<8, 1>(fz, tw, lane);
+      welch_fft_pass<2, 1>(fz, tw, lane);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int pos = lane + 32 * j;
-        const int k = (int)(__brev((unsigned)pos) >> 24);
-        if (k < F) {
-          const double2 v = fz[wpad(pos)];
-          double pw = (v.x * v.x + v.y * v.y) * scale;
+      for (int j = 0; j < 2; ++j) {
+        const int i = 2 * (lane + 32 * j);
+        const double2 e0 = fz[wpad(i)], e1 = fz[wpad(i + 1)];
+        fz[wpad(i)] = cadd(e0, e1);
+        fz[wpad(i + 1)] = csub(e0, e1);
+      }
+      __syncwarp();
+      // Z[k] sits at position brev7(k); lane owns the bins k = lane + 32 j (j < 4), lane 0 also bin 128
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int k = j < 4 ? lane + 32 * j : 128;
+        if (j < 4 || lane == 0) {
+          const double2 A = fz[wpad((int)(__brev((unsigned)(k & 127)) >> 25))];
+          const double2 B = fz[wpad((int)(__brev((unsigned)((128 - k) & 127)) >> 25))];
+          const double er = 0.5 * (A.x + B.x), ei = 0.5 * (A.y - B.y);
+          const double orr = 0.5 * (A.y + B.y), oi = -0.5 * (A.x - B.x);
+          const double2 t = tw[k];                                  // exp(+2 pi i k / 256): X = E + conj(t) O
+          const double xr = er + (t.x * orr + t.y * oi), xi = ei + (t.x * oi - t.y * orr);
+          double pw = (xr * xr + xi * xi) * scale;
           if (k >= 1 && k < F - 1) pw *= 2.0;
           facc[j] += pw;
         }
       }
       __syncwarp();
     } else {
-      for (int i = lane; i < N; i += 32) z[i] = (seg[i] - mean) * (0.5 - 0.5 * dc[i]);
+      // n < 256: nperseg = n, exactly one segment (sg == 0, seg == ys): windowed in place
+      for (int i = lane; i < N; i += 32) ys[i] = (seg[i] - mean) * (0.5 - 0.5 * dc[i]);
       __syncwarp();
-      for (int k = lane; k < F; k += 32) {
-        double re = 0.0, im = 0.0;
-        int idx = 0;
-        for (int j = 0; j < N; ++j) {
-          const double v = z[j];
-          re = fma(v, dc[idx], re);
-          im = fma(-v, ds[idx], im);
-          idx += k; if (idx >= N) idx -= N;
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        const int k = lane + 32 * jb;
+        if (k < F) {
+          double re = 0.0, im = 0.0;
+          int idx = 0;
+          for (int j = 0; j < N; ++j) {
+            const double v = ys[j];
+            re = fma(v, dc[idx], re);
+            im = fma(-v, ds[idx], im);
+            idx += k; if (idx >= N) idx -= N;
+          }
+          double pw = (re * re + im * im) * scale;
+          const bool dbl = (N % 2 == 0) ? (k >= 1 && k < F - 1) : (k >= 1);
+          if (dbl) pw *= 2.0;
+          dm[jb] += pw;
         }
-        double pw = (re * re + im * im) * scale;
-        const bool dbl = (N % 2 == 0) ? (k >= 1 && k < F - 1) : (k >= 1);
-        if (dbl) pw *= 2.0;
-        mags[k] += pw;
       }
       __syncwarp();
     }
@@ -412,9 +432,9 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const dou
   double bv = -INFINITY; int bi = 0x7fffffff, cnt = 0;
   if (fft) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = (int)(__brev((unsigned)(lane + 32 * j)) >> 24);
-      if (k < F) {
+    for (int j = 0; j < 5; ++j) {
+      const int k = j < 4 ? lane + 32 * j : 128;
+      if (j < 4 || lane == 0) {
         const double v = facc[j] / (double)nseg;
         if (spec_mag && k < max_bins) {
           spec_f[sig * max_bins + k] = (float)((double)k * fval);
@@ -424,13 +444,17 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, 5) welch_warp_kernel(const dou
       }
     }
   } else {
-    for (int k = lane; k < F; k += 32) {
-      const double v = mags[k] / (double)nseg;
-      if (spec_mag && k < max_bins) {
-        spec_f[sig * max_bins + k] = (float)((double)k * fval);
-        spec_mag[sig * max_bins + k] = (float)v;
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      const int k = lane + 32 * jb;
+      if (k < F) {
+        const double v = dm[jb] / (double)nseg;
+        if (spec_mag && k < max_bins) {
+          spec_f[sig * max_bins + k] = (float)((double)k * fval);
+          spec_mag[sig * max_bins + k] = (float)v;
+        }
+        if (isfinite(v)) { ++cnt; if (v > bv) { bv = v; bi = k; } }
       }
-      if (isfinite(v)) { ++cnt; if (v > bv) { bv = v; bi = k; } }
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
