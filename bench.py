@@ -364,6 +364,29 @@ def measure_pcie(torch, dev):
     return best
 
 
+def measure_pcie_concurrent(torch, dev, tdist, world):
+    """N > 1: every rank copies 256 MiB of pinned memory to its GPU AT THE SAME TIME, 8 times back to back; returns
+    (sum over ranks, slowest rank) in GB/s — the host-side ceiling the N-GPU e2e number lives under (the GPUs' PCIe links share
+    host bridges / memory channels), measured with nothing of this repo's kernels involved."""
+    h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    tdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(8):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    mine = 8 * h.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([mine, -mine], dtype=torch.float64, device=dev)
+    tot = t.clone()
+    tdist.all_reduce(tot, op=tdist.ReduceOp.SUM)
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    return float(tot[0].item()), float(-t[1].item())
+
+
 def time_family_wrappers(torch, ops, fam, only=None):
     """Wrap the ops launchers (all, or those named in `only`) so every call is bracketed by CUDA events on the stream it
     launches on."""
@@ -689,6 +712,7 @@ def run_gpu(args, wl):
         e2e_s = float(tt.item())
     del host_frames
     fma = measure_fma_peaks(torch, dev) if rank == 0 else None
+    pcie_conc = measure_pcie_concurrent(torch, dev, tdist, world) if world > 1 else None
     pcie = measure_pcie(torch, dev) if rank == 0 else None
     sched = {'overlap_mask': eng.overlap, 'design_cache': eng._dcache is not None}
     # ---- ingest variants of F1, informational: same launch size, frames / surfaces resident in HBM
@@ -828,6 +852,9 @@ def run_gpu(args, wl):
                 'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': int(host_out.numel() * 8),
                 'frames_per_stream_per_step': Te, 'pcie_gbs_measured': pcie,
                 'pcie_frac': (e2e_h2d / e2e_s / 1e9) / pcie if pcie else None,
+                'pcie_gbs_concurrent_sum': pcie_conc[0] if pcie_conc else None,
+                'pcie_gbs_concurrent_slowest_rank': pcie_conc[1] if pcie_conc else None,
+                'pcie_frac_concurrent': (world * e2e_h2d / e2e_s / 1e9) / pcie_conc[0] if pcie_conc else None,
                 'how': 'BatchedSignalProcessor.roi_samples + step_signals on pinned HOST frames/boxes/timestamps; F1 reads the '
                        'ROI rows zero-copy over PCIe (the other 99.5 % of each frame never crosses the bus, so h2d_bytes_per_step '
                        'counts the ROI bytes + boxes + timestamps) on a side stream, overlapped with the previous batch\'s window '
