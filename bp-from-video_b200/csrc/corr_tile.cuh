@@ -81,4 +81,53 @@ __device__ __forceinline__ void corr_tile_wrap(T (&acc)[RT], T (&first)[RT], con
   }
 }
 
+// Packed-FMA form of corr_tile_wrap for float operands (sm_100a `fma.rn.f32x2`, SASS FFMA2: two float FMAs per issued
+// instruction with a scalar-broadcast first operand and a per-operand half swap).  The RT outputs of a lane are held as
+// RT/2 register pairs (acc[i], acc[i + RT/2]) and its RT operand samples as pairs (w[s], w[s + RT/2]): under tap kk
+// output i needs w[(i - kk) mod RT] and output i + RT/2 needs the sample RT/2 further on — the two halves of ONE pair,
+// swapped when (i - kk) mod RT >= RT/2.  Every lane-level FMA is the one corr_tile_wrap issues, in the same order, so the
+// results are identical bit for bit; the loop body is RT/2 FFMA2 per tap instead of RT FFMA (the kernel is issue bound).
+// c must be 8-byte aligned; RT even.
+template <int RT, int LDC>
+__device__ __forceinline__ void corr_tile_wrap_f32x2(float (&acc)[RT], float (&first)[RT], const float* __restrict__ c, int K,
+                                                     const float* __restrict__ XT, int LD_rt, int j0, int q) {
+  static_assert(RT % 2 == 0, "pairs of outputs");
+  constexpr int H = RT / 2;
+  const int LD = LDC ? LDC : LD_rt;
+  const int col0 = j0 / RT;
+  float2 A[H], P[H];
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    A[i] = make_float2(acc[i], acc[i + H]);
+    P[i] = make_float2(XT[i * LD + col0], XT[(i + H) * LD + col0]);
+  }
+  const int nb = K / RT;
+  for (int kb = 0; kb < nb; ++kb) {
+    const float2* cc = reinterpret_cast<const float2*>(c + kb * RT);
+    const float* xn = XT + (col0 - kb - 1);
+    const bool wrap = kb == q;
+#pragma unroll
+    for (int kk = 0; kk < RT; ++kk) {
+      if (wrap) {                                             // output kk wraps before tap RT*q + kk
+        if (kk < H) { first[kk] = A[kk].x; A[kk].x = 0.f; }
+        else { first[kk] = A[kk - H].y; A[kk - H].y = 0.f; }
+      }
+      const float2 cp = cc[kk / 2];
+      const float ck = (kk & 1) ? cp.y : cp.x;
+      const float2 cb = make_float2(ck, ck);
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const int lo = (i - kk + RT) % RT;                    // sample under output i; output i + H sees (lo + H) % RT
+        const float2 op = lo < H ? P[lo] : make_float2(P[lo - H].y, P[lo - H].x);
+        A[i] = __ffma2_rn(cb, op, A[i]);
+      }
+      const int t = RT - 1 - kk;                              // X[j0 - k - 1] replaces X[j0 - k + RT - 1]
+      const float xv = xn[t * LD];
+      if (t < H) P[t].x = xv; else P[t - H].y = xv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < H; ++i) { acc[i] = A[i].x; acc[i + H] = A[i].y; }
+}
+
 }  // namespace bpv

@@ -258,8 +258,16 @@ __device__ void firls_design_group(double fs, bool live, int taps, double min_fr
       }
     }
     if (live) {
+      // written out as the symmetric filter itself, c[k] = ac[|k - Mt|] for k = 0 .. 2 Mt (Mt = taps - 1), zero up to
+      // FIR_MERGED_LEN: the preprocessing kernel's tiles read c[] straight from here (no per-signal copy into shared memory)
+      const int Mt = n - 1;
 #pragma unroll
-      for (int e = 0; e < E; ++e) ac_out[d0 + e] = ok ? acc[e] : nan_f64();
+      for (int e = 0; e < E; ++e) {
+        const int d = d0 + e;
+        const double v = ok ? acc[e] : nan_f64();
+        if (d <= Mt) { ac_out[Mt - d] = v; ac_out[Mt + d] = v; }
+      }
+      for (int k = 2 * Mt + 1 + sub; k < FIR_MERGED_LEN; k += FIRLS_LPD) ac_out[k] = 0.0;
     }
   }
 }
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(FIRLS_THREADS) job_firls_kernel(const double* 
   const bool live = job < p.S * p.jobs_per_stream;
   // padding groups shadow job 0 (warp-uniform control flow), write nothing
   const double fs = group_job_fs(ring_t, p, live ? job : 0, sub);
-  double* o = out + (long long)(live ? job : 0) * FIR_WS_STRIDE;      // taps [128] | lfilter_zi [128] | autocorrelation [128]
+  double* o = out + (long long)(live ? job : 0) * FIR_WS_STRIDE;      // taps [128] | lfilter_zi [128] | merged taps [FIR_MERGED_LEN]
   firls_design_group(fs, live, p.fir_taps, p.min_freq, p.max_freq, p.fir_df, o, o + 128, o + 256, smem + firls_smem_offset(d));
 }
 

@@ -7,11 +7,12 @@ namespace bpv {
 
 constexpr int MAX_SOS = 16;     // butter_order <= 16 -> <= 16 second-order sections
 constexpr int MAX_TAPS = 127;   // fir_taps <= 127 (odd)
-// design cache (filters.cu): DC_SLOTS entries of [sos 16x6 | taps | zi | autocorrelation], keyed by the bits of fs
+// design cache (filters.cu): DC_SLOTS entries of [sos 16x6 | taps | zi | merged taps], keyed by the bits of fs
 constexpr int DC_SLOTS = 256, DC_PROBES = 8, DC_HDR_BYTES = 16;
-constexpr int DC_STRIDE = MAX_SOS * 6 + 384;
+constexpr int FIR_MERGED_LEN = 264;  // merged filtfilt taps c[k] = ac[|k - (T-1)|], k = 0 .. 2T-2, zero padded (2T-1 <= 255; tiles read up to 260)
+constexpr int FIR_WS_STRIDE = 256 + FIR_MERGED_LEN;   // doubles of filter workspace per window job: taps [128] | lfilter_zi [128] | merged taps [264]
+constexpr int DC_STRIDE = MAX_SOS * 6 + FIR_WS_STRIDE;
 constexpr long long DC_BYTES = DC_HDR_BYTES + (long long)DC_SLOTS * 8 + (long long)DC_SLOTS * DC_STRIDE * 8;
-constexpr int FIR_WS_STRIDE = 384;   // doubles of filter workspace per window job: taps [128] | lfilter_zi [128] | tap autocorrelation [128]
 
 // status codes written to the per-signal status array
 constexpr int ST_OK = 0, ST_GUARD = 1, ST_CUBIC_X = 2, ST_BAD_BANDS = 3;

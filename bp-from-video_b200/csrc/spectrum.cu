@@ -319,25 +319,35 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, WELCH_MINB) welch_warp_kernel(
 
   // ---- gather: stage (independent loads), then ballot-compact finite y in place; fs from the finite-x mask
   double* xst = buf;               // x staging (W <= 512 checked by the host)
-  for (int k = lane; k < W; k += 32) { xst[k] = px[k]; ys[k] = py[k]; }
+  bool allf = true;
+  for (int k = lane; k < W; k += 32) {
+    const double x = px[k], y = py[k];
+    xst[k] = x; ys[k] = y;
+    allf &= isfinite(x) && isfinite(y);
+  }
   __syncwarp();
   int n = 0, m = 0;
   double xfirst = 0.0, xlast = 0.0;
-  const unsigned lt = (1u << lane) - 1u;
-  for (int k0 = 0; k0 < W; k0 += 32) {
-    const int k = k0 + lane;
-    double x = nan_f64(), y = nan_f64();
-    if (k < W) { x = xst[k]; y = ys[k]; }
-    const bool fx = isfinite(x), fy = isfinite(y);
-    const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
-    if (bx) {
-      if (m == 0) xfirst = shfl_dd(x, __ffs(bx) - 1);
-      xlast = shfl_dd(x, 31 - __clz(bx));
+  if (__all_sync(0xffffffffu, allf)) {     // a window without holes is its own compaction (one vote instead of W / 32 ballot rounds)
+    n = m = W;
+    xfirst = xst[0]; xlast = xst[W - 1];
+  } else {
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k0 = 0; k0 < W; k0 += 32) {
+      const int k = k0 + lane;
+      double x = nan_f64(), y = nan_f64();
+      if (k < W) { x = xst[k]; y = ys[k]; }
+      const bool fx = isfinite(x), fy = isfinite(y);
+      const unsigned bx = __ballot_sync(0xffffffffu, fx), by = __ballot_sync(0xffffffffu, fy);
+      if (bx) {
+        if (m == 0) xfirst = shfl_dd(x, __ffs(bx) - 1);
+        xlast = shfl_dd(x, 31 - __clz(bx));
+      }
+      __syncwarp();
+      if (fy) ys[n + __popc(by & lt)] = y;
+      __syncwarp();
+      n += __popc(by); m += __popc(bx);
     }
-    __syncwarp();
-    if (fy) ys[n + __popc(by & lt)] = y;
-    __syncwarp();
-    n += __popc(by); m += __popc(bx);
   }
   const double fs = m >= 2 ? 1.0 / ((xlast - xfirst) / (double)(m - 1)) : nan_f64();
   if (!(n >= 2 && isfinite(fs))) {        // guard signal_processor.py:252 -> empty spectrum
@@ -569,6 +579,9 @@ __global__ void __launch_bounds__(128) ls_coarse_kernel(const double* __restrict
   const int k0 = kbase + tid;
   const double f = ls_freq(k0 < F ? k0 : F - 1, F, p.min_freq, p.max_freq);
   const float fh = (float)f, fl = (float)(f - (double)fh);
+  // (Packed float instructions — FADD2 / FMUL2 / FFMA2 on (c, s) pairs, 5 instead of 10 instructions per (sample, frequency)
+  // slot, bit-identical results — were measured on B200 and are slower here: config 3 2.24 -> 2.28 ms, config 5 8.94 -> 9.10 ms
+  // per step (profiles/r4a): a packed instruction holds the FP32 pipe for two issue slots, and the pairs cost registers.)
   float C[LS_NF], S[LS_NF], CC[LS_NF], CS[LS_NF], YC[LS_NF], YS[LS_NF];
 #pragma unroll
   for (int m = 0; m < LS_NF; ++m) { C[m] = S[m] = CC[m] = CS[m] = YC[m] = YS[m] = 0.f; }

@@ -238,21 +238,31 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   float* XT = reinterpret_cast<float*>(sm + Lw.xt);
   const int LD = LDC ? LDC : Lw.LD;
   // stage both windows (independent coalesced loads)
-  for (int k = lane; k < W; k += 32) { a64[k] = ya_g[k]; b64[k] = yb_g[k]; }
+  bool allf = true;
+  for (int k = lane; k < W; k += 32) {
+    const double va = ya_g[k], vb = yb_g[k];
+    a64[k] = va; b64[k] = vb; pos[k] = (unsigned short)k;
+    allf &= isfinite(va) && isfinite(vb);
+  }
   __syncwarp();
-  // jointly valid samples (valid = a.w & b.w), compacted in place
+  // jointly valid samples (valid = a.w & b.w), compacted in place; a pair of windows without holes already is (one vote
+  // instead of W / 32 ballot rounds, positions = identity)
   int n = 0;
-  const unsigned lt = (1u << lane) - 1u;
-  for (int k0 = 0; k0 < W; k0 += 32) {
-    const int k = k0 + lane;
-    double va = nan_f64(), vb = nan_f64();
-    if (k < W) { va = a64[k]; vb = b64[k]; }
-    const bool ok = isfinite(va) && isfinite(vb);
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    __syncwarp();
-    if (ok) { const int i = n + __popc(bal & lt); a64[i] = va; b64[i] = vb; pos[i] = (unsigned short)k; }
-    __syncwarp();
-    n += __popc(bal);
+  if (__all_sync(0xffffffffu, allf)) {
+    n = W;
+  } else {
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k0 = 0; k0 < W; k0 += 32) {
+      const int k = k0 + lane;
+      double va = nan_f64(), vb = nan_f64();
+      if (k < W) { va = a64[k]; vb = b64[k]; }
+      const bool ok = isfinite(va) && isfinite(vb);
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();
+      if (ok) { const int i = n + __popc(bal & lt); a64[i] = va; b64[i] = vb; pos[i] = (unsigned short)k; }
+      __syncwarp();
+      n += __popc(bal);
+    }
   }
   if (n < 2) {                                  // guard signal_processor.py:284 -> empty
     if (lane == 0) { num_lags[jp] = 0; lag_idx[jp] = -1; lag_sec[jp] = nan_f64(); lag_corr[jp] = nan_f64(); }
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
     float acc[RT], first[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) { acc[r] = 0.f; first[r] = 0.f; }
-    corr_tile_wrap<RT, LDC, float>(acc, first, c, K, XT, LD, RT * tile + K + RT, tile);
+    corr_tile_wrap_f32x2<RT, LDC>(acc, first, c, K, XT, LD, RT * tile + K + RT, tile);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int la = RT * tile - 1 + r;          // first lag of the pair; the second is la + n

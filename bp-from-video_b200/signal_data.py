@@ -10,6 +10,7 @@ ndarrays (convertible by np.array, iterable, picklable), sized like the referenc
 from __future__ import annotations
 
 import collections.abc
+import math
 import warnings
 
 import numpy as np
@@ -34,12 +35,12 @@ def _initial(value, maxlen):
 
 
 def _span(values, mask):
-    """(nanmin, nanmax) when at least two entries are usable, else (nan, nan) (signal_data.py:47-49)."""
-    if int(np.sum(mask)) < 2:
+    """(nanmin, nanmax) when at least two entries are usable, else (nan, nan) (signal_data.py:47-49).
+    fmin / fmax reductions ignore NaN like nanmin / nanmax (all-NaN -> nan) without their warning machinery: this runs
+    twice per Signal on every appended sample."""
+    if np.count_nonzero(mask) < 2:
         return (np.nan, np.nan)
-    with warnings.catch_warnings():
-        warnings.simplefilter('ignore', RuntimeWarning)
-        return (np.nanmin(values), np.nanmax(values))
+    return (np.fmin.reduce(values, axis=None), np.fmax.reduce(values, axis=None))
 
 
 class Signal:
@@ -64,9 +65,7 @@ class Signal:
         if self.maxlen is not None and len(arr) >= self.maxlen:
             if self.maxlen == 0:
                 return arr
-            arr = np.roll(arr, -1, axis=0)
-            arr[-1] = value
-            return arr
+            return np.concatenate([arr[1:], value[None, ...]], axis=0)      # deque(maxlen).append: the oldest sample falls out
         return np.concatenate([arr, value[None, ...]], axis=0)
 
     def add_sample(self, xp: XType, yp: YType) -> None:
@@ -157,10 +156,11 @@ class SignalGroup:
 
     @staticmethod
     def _union(pairs):
+        """(nanmin of the lows, nanmax of the highs) when both sides have a finite entry, else (nan, nan)."""
         lows, highs = zip(*pairs) if pairs else ((), ())
-        if not pairs or not (np.isfinite(lows).any() and np.isfinite(highs).any()):
+        if not (any(math.isfinite(v) for v in lows) and any(math.isfinite(v) for v in highs)):
             return (np.nan, np.nan)
-        return (np.nanmin(lows), np.nanmax(highs))
+        return (np.float64(min(v for v in lows if v == v)), np.float64(max(v for v in highs if v == v)))
 
     def reset_ranges(self) -> None:
         # NB (reference behaviour, signal_data.py:100-102): wrapping signals in a group re-derives every

@@ -153,6 +153,7 @@ class SignalProcessor:
         self._engine = None
         self._engine_key = None
         self._staging = None
+        self._host_bufs = {}
 
     # ------------------------------------------------------------------------------------------
     # device plumbing
@@ -352,12 +353,12 @@ class SignalProcessor:
         return x, y
 
     def _spectrum_signal(self, freqs, mags):
-        sig = signal_data.Signal(list(freqs), list(mags), s_maxlen=len(freqs))
+        sig = signal_data.Signal(np.asarray(freqs, dtype=float), np.asarray(mags, dtype=float), s_maxlen=len(freqs))
         sig.set_range((self.min_freq, self.max_freq), (self.min_mag, self.max_mag))
         return sig
 
     def _corr_signal(self, lags, corr):
-        sig = signal_data.Signal(list(lags), list(corr), s_maxlen=len(lags))
+        sig = signal_data.Signal(np.asarray(lags, dtype=float), np.asarray(corr, dtype=float), s_maxlen=len(lags))
         sig.set_range((self.min_lag, self.max_lag), (self.min_corr, self.max_corr))
         return sig
 
@@ -402,6 +403,23 @@ class SignalProcessor:
         return signal_data.SignalGroup(signals=[self.correlate_signal_pair(a, b)
                                                 for a, b in itertools.combinations(list(signals_proc), 2)])
 
+    def _to_host(self, named: dict) -> dict:
+        """Device tensors -> numpy arrays with ONE synchronisation: every tensor is copied asynchronously into its own
+        pinned staging buffer on the stream the step ran on (sixteen blocking .cpu() calls were a quarter of the per-frame
+        time of process())."""
+        import torch
+        bufs = self._host_bufs
+        staged = {}
+        with torch.cuda.device(self.device):
+            for k, t in named.items():
+                b = bufs.get(k)
+                if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                    b = bufs[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                b.copy_(t, non_blocking=True)
+                staged[k] = b
+            torch.cuda.current_stream(self.device).synchronize()
+        return {k: b.numpy().copy() for k, b in staged.items()}     # the staging buffers are reused by the next frame
+
     @profiler.timeit
     def process(self, frame_data: 'video_reader.FrameData', model_results: 'inference_runner.InferenceResults') -> SignalStore:
         """One frame through the whole path (signal_processor.py:302-313) as ONE batched-engine step (S=1, T=1)."""
@@ -413,23 +431,23 @@ class SignalProcessor:
         boxes = torch.from_numpy(self._boxes(rois)[None, None]).to(self.device)
         tst = torch.tensor([[ts]], dtype=torch.float64, device=self.device)
         res = eng.step(self._stage_frame(frame_data.frame), boxes, tst)
-        host = {k: v.cpu().numpy() for k, v in res.arrays.items()}
-        samples = res.samples.cpu().numpy()[0, 0]
-        status = res.status.cpu().numpy()
-        peak_f, lag_s = res.peak_freq.cpu().numpy()[0], res.lag_sec.cpu().numpy()[0]
+        host = self._to_host(dict(res.arrays, samples=res.samples, status=res.status, peak_freq=res.peak_freq, lag_sec=res.lag_sec,
+                                  peak_idx=res.peak_idx, peak_mag=res.peak_mag, lag_idx=res.lag_idx, lag_corr=res.lag_corr))
+        samples, status = host['samples'][0, 0], host['status']
+        peak_f, lag_s = host['peak_freq'][0], host['lag_sec'][0]
         R, W = self.num_signals, self.signal_max_samples
         st.sg_raw.add_samples(ts, [np.float64(v) for v in samples])     # before any raise, as the reference (:307-308)
         self._raise_status(status)
         st.sg_proc = signal_data.SignalGroup(signals=[signal_data.Signal(host['proc_x'][0, r], host['proc_y'][0, r], W) for r in range(R)])
         nb = host['num_bins'][0]
-        pidx, pmag = res.peak_idx.cpu().numpy()[0], res.peak_mag.cpu().numpy()[0]
+        pidx, pmag = host['peak_idx'][0], host['peak_mag'][0]
         st.sg_spec = signal_data.SignalGroup(signals=[
             self._spectrum_signal(*self._decided(host['freqs'][0, r, :nb[r]], host['mags'][0, r, :nb[r]], pidx[r], peak_f[r], pmag[r]))
             for r in range(R)])
         st.sg_bpm.add_samples(ts, [f * 60 for f in peak_f])             # peak decided in float64 on the device
         pairs = math.comb(R, 2)
         nl = host['num_lags'][0] if pairs else []
-        lidx, lcorr = res.lag_idx.cpu().numpy()[0], res.lag_corr.cpu().numpy()[0]
+        lidx, lcorr = host['lag_idx'][0], host['lag_corr'][0]
         st.sg_corr = signal_data.SignalGroup(signals=[
             self._corr_signal(*self._decided(host['lags'][0, k, :nl[k]], host['corr'][0, k, :nl[k]], lidx[k], lag_s[k], lcorr[k]))
             for k in range(pairs)])
@@ -441,3 +459,4 @@ class SignalProcessor:
     def cleanup(self):
         self._engine = None
         self._staging = None
+        self._host_bufs = {}

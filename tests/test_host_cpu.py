@@ -250,7 +250,7 @@ def test_cabi_rejects_bad_arguments_before_touching_the_gpu():
     assert pre(params([_cabi.FILTER_FIR])) == -1                    # filter design needs the caller's workspace
     assert b'workspace' in lib.bpv_last_error()
     need = lib.bpv_window_workspace_bytes(C.byref(params([_cabi.FILTER_FIR])))
-    assert need == 1 * ((16 * 6 + 384) * 8 + 8 + 16)            # per job: sos | taps | zi | tap autocorrelation | cache ref | miss entry
+    assert need == 1 * ((16 * 6 + 520) * 8 + 8 + 16)            # per job: sos | taps [128] | zi [128] | merged taps [264] | cache ref | miss entry
     assert pre(params([_cabi.FILTER_FIR]), a, need - 1) == -1
     p = params([], transform=9)
     assert lib.bpv_window_spectrum(a, a, C.byref(p), 64, None, 0, None, None, a, a, a, a, None) == -2
