@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, WELCH_MINB) welch_warp_kernel(
     for (int j = 0; j < 5; ++j) {
       const int k = j < 4 ? lane + 32 * j : 128;
       if (j < 4 || lane == 0) {
-        const double v = facc[j] / (double)nseg;
+        const double v = nseg == 1 ? facc[j] : facc[j] / (double)nseg;     // mean over ONE segment (n < 384): x / 1 == x
         if (spec_mag && k < max_bins) {
           spec_f[sig * max_bins + k] = (float)((double)k * fval);
           spec_mag[sig * max_bins + k] = (float)v;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, WELCH_MINB) welch_warp_kernel(
     for (int jb = 0; jb < 4; ++jb) {
       const int k = lane + 32 * jb;
       if (k < F) {
-        const double v = dm[jb] / (double)nseg;
+        const double v = nseg == 1 ? dm[jb] : dm[jb] / (double)nseg;
         if (spec_mag && k < max_bins) {
           spec_f[sig * max_bins + k] = (float)((double)k * fval);
           spec_mag[sig * max_bins + k] = (float)v;
