@@ -362,9 +362,15 @@ __global__ void __launch_bounds__(32 * WELCH_WPB, WELCH_MINB) welch_warp_kernel(
   if (!fft) {
     for (int i = lane; i < N; i += 32) sincospi(2.0 * (double)i / (double)N, &ds[i], &dc[i]);
   }
-  double sw = 0.0;
-  for (int i = lane; i < N; i += 32) { const double wj = 0.5 - 0.5 * (fft ? tw[i].x : dc[i]); sw = fma(wj, wj, sw); }
-  const double scale = 1.0 / (fs * warp_sum(sw));
+  // density scaling 1 / (fs * sum(win^2)) (scipy.signal._spectral_helper).  For the periodic 256-point Hann window the sum is
+  // 256 * 3 / 8 = 96, and (win * win).sum() evaluates to exactly 96.0 in float64 (checked against scipy 1.18.1)
+  double swsum = 96.0;
+  if (!fft) {
+    double sw = 0.0;
+    for (int i = lane; i < N; i += 32) { const double wj = 0.5 - 0.5 * dc[i]; sw = fma(wj, wj, sw); }
+    swsum = warp_sum(sw);
+  }
+  const double scale = 1.0 / (fs * swsum);
   double facc[5] = {0, 0, 0, 0, 0};               // FFT path: power sums of the bins this lane owns (lane + 32 j; lane 0: bin 128)
   double dm[4] = {0, 0, 0, 0};                    // direct path: bins lane + 32 j (F <= 128)
   for (int sg = 0; sg < nseg; ++sg) {

@@ -184,18 +184,19 @@ __global__ void __launch_bounds__(128) xcorr_kernel(const double* __restrict__ p
 // XW_RT = 10 lag pairs (li, li + n) of one tile, so a 300-sample window (599 lags) is a single round of the register-tiled
 // circular sliding dot product (2 LDS + 2 predicated moves per 10 FFMA, n taps per lane), and the float64 re-evaluation of
 // the candidate lags is a warp-cooperative dot product.
-// smem per warp: doubles a64[W] | b64[W]; u16 pos[W]; floats cv[2W] | c[K] | XT[RT * LD]
+// smem per warp: doubles a64[W] | b64[W]; u16 pos[W]; floats cv[2W] (only when a lane owns more than one tile, W > 320) | c[K] | XT[RT * LD]
 // ---------------------------------------------------------------------------------------------
 constexpr int XW_RT = 10;
-struct XwLayout { int b64, pos, cv, c, xt, total, K, LD; };
-__host__ __device__ inline XwLayout xw_layout(int W) {
+struct XwLayout { int b64, pos, cv, c, xt, total, K, LD, one_round; };
+__host__ __device__ inline XwLayout xw_layout(int W, bool force_cv = false) {
   XwLayout L;
   L.K = (W + XW_RT - 1) / XW_RT * XW_RT;                 // taps, padded to the tile
   L.LD = (2 * (L.K / XW_RT) + 2) | 1;                    // columns of the de-interleaved periodic operand (odd: no bank conflicts)
   int o = W * 8;
   L.b64 = o; o += W * 8;
   L.pos = o; o += (W * 2 + 15) / 16 * 16;
-  L.cv = o; o += 2 * W * 4;
+  L.one_round = !force_cv && L.K / XW_RT <= 32;                       // every lane owns at most one tile: coarse values stay in registers
+  L.cv = o; o += L.one_round ? 0 : 2 * W * 4;
   L.c = o; o += L.K * 4;
   L.xt = o; o += XW_RT * L.LD * 4;
   L.total = (o + 15) / 16 * 16;
@@ -208,8 +209,12 @@ __host__ __device__ inline XwLayout xw_layout(int W) {
 // output pair for every lane (a 300-sample window: 30 lanes x 10 pairs, one round), where one tile of consecutive lags per
 // lane made the warp wait for the centre lanes' n taps per lag.
 // LDC = the operand buffer's leading dimension when it is one of the specialised window sizes (0 = run-time value)
-template <int LDC>
-__global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
+// ONE = every lane owns at most one tile (windows up to 320 samples): the 2 x RT coarse values of a lane never leave its
+// registers — the candidate lags are flagged from them as a 20-bit mask per lane — so the plan has no cv[] array (9.1 instead of
+// 11.5 KB per warp at W = 300) and the peak search does not re-read 2n - 1 values from shared memory.  Launch bound 5 CTAs per SM:
+// 88 registers keep the packed tile loop free of spills (ptxas settles on 72 without it and pays 60 register moves per 10 taps).
+template <int LDC, bool ONE>
+__global__ void __launch_bounds__(128, ONE ? 5 : 1) xcorr_warp_kernel(const double* __restrict__ proc_x, const double* __restrict__ proc_y,
                                                          const bpv_window_params p, const XwLayout Lw, long long npairs,
                                                          float* __restrict__ corr_lag, float* __restrict__ corr_val,
                                                          int32_t* __restrict__ num_lags, int32_t* __restrict__ lag_idx,
@@ -283,12 +288,14 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   // written completely (every storage index a tile can touch): periodic extension inside [-n, n), zeros outside.
   const double sa = amax > 0 ? 1.0 / amax : 1.0, sb = bmax > 0 ? 1.0 / bmax : 1.0;
   const int jtot = 2 * K + 2 * RT;              // storage indices [0, jtot): t = j - OFF in [-K - RT - 1, K + RT - 2]
-  for (int j = lane; j < jtot; j += 32) {
-    const int t = j - OFF;
-    float v = 0.f;
-    if (t >= -n && t < n) v = (float)(a64[t < 0 ? t + n : t] * sa);
-    XT[xt_index<RT>(j, LD)] = v;
+  // each sample is converted once and stored at its two periods (t = i and t = i - n); the few slots outside [-n, n) are zeroed
+  for (int i = lane; i < n; i += 32) {
+    const float v = (float)(a64[i] * sa);
+    XT[xt_index<RT>(i + OFF, LD)] = v;
+    XT[xt_index<RT>(i + OFF - n, LD)] = v;
   }
+  for (int j = lane; j < OFF - n; j += 32) XT[xt_index<RT>(j, LD)] = 0.f;
+  for (int j = OFF + n + lane; j < jtot; j += 32) XT[xt_index<RT>(j, LD)] = 0.f;
   for (int m = lane; m < K; m += 32) c[m] = m < n ? (float)(b64[n - 1 - m] * sb) : 0.f;
   __syncwarp();
   const float unscale = (float)(1.0 / (sa * sb * den));
@@ -297,21 +304,23 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   const double x_last = xa_g[pos[n - 1]];
   float cmax = -INFINITY; int cnt = 0;          // coarse maximum / finite count, gathered while the tiles are written
   const int tiles = K / RT;
+  unsigned okm = 0;                             // ONE: bit r = first lag of pair r is a lag of this window, bit RT + r = second lag
+  float acc[RT], first[RT];                     // ONE: after the tile, the lane's scaled coarse values (second | first lags)
   for (int tile = lane; tile < tiles; tile += 32) {
-    float acc[RT], first[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) { acc[r] = 0.f; first[r] = 0.f; }
     corr_tile_wrap_f32x2<RT, LDC>(acc, first, c, K, XT, LD, RT * tile + K + RT, tile);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int la = RT * tile - 1 + r;          // first lag of the pair; the second is la + n
+      first[r] *= unscale; acc[r] *= unscale;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int li = h ? la + n : la;
         const bool ok = h ? (la <= n - 2) : (la >= 0 && la <= n - 2);
         if (ok) {
-          const float cc = (h ? acc[r] : first[r]) * unscale;
-          cv[li] = cc;
+          const float cc = h ? acc[r] : first[r];
+          if (ONE) okm |= 1u << (h * RT + r); else cv[li] = cc;
           if (isfinite(cc)) { ++cnt; cmax = fmaxf(cmax, cc); }
           if (corr_val) {
             const int k = li - (n - 1), ak = k < 0 ? -k : k;
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
         }
       }
     }
+    if (ONE) break;                             // tiles <= 32: one tile per lane
   }
   __syncwarp();
   // PEAK in float64: every lag whose coarse value is within XC_DELTA of the coarse maximum is re-evaluated as a
@@ -329,29 +339,53 @@ __global__ void __launch_bounds__(128) xcorr_warp_kernel(const double* __restric
   for (int o = 16; o > 0; o >>= 1) { cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
   double bv = -INFINITY; int bi = 0x7fffffff;
   const float thr = cmax - XC_DELTA;
-  for (int li0 = 0; li0 < L; li0 += 128) {       // 4 consecutive lags per lane per step
-    const int lb = li0 + 4 * lane;
-    unsigned flags = 0;
+  auto refine = [&](int lc) {                    // whole warp: lag index lc -> float64 correlation, first-max update
+    const int k = lc - (n - 1);
+    const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
+    double acc = 0.0;
+    for (int l = l0 + lane; l < l1; l += 32) acc = fma(a64[l + k], b64[l], acc);
+    acc = warp_sum(acc);
+    const double cc = acc / den;
+    if (isfinite(cc) && (cc > bv || (cc == bv && lc < bi))) { bv = cc; bi = lc; }
+  };
+  if (ONE) {
+    unsigned cand = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int li = lb + e;
-      if (li < L) { const float v = cv[li]; if (cnt >= 2 ? (isfinite(v) && v >= thr) : true) flags |= 1u << e; }
+    for (int b = 0; b < 2 * RT; ++b) {
+      const float v = b < RT ? first[b] : acc[b - RT];
+      if (((okm >> b) & 1u) && (cnt >= 2 ? (isfinite(v) && v >= thr) : true)) cand |= 1u << b;
     }
-    unsigned m = __ballot_sync(0xffffffffu, flags != 0);
-    while (m) {                                  // lanes in increasing lag order, lags of a lane in increasing order
+    unsigned m = __ballot_sync(0xffffffffu, cand != 0);
+    while (m) {                                  // any order: the update keeps the largest value, ties to the smallest lag
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      unsigned f = __shfl_sync(0xffffffffu, flags, src);
+      unsigned f = __shfl_sync(0xffffffffu, cand, src);
       while (f) {
-        const int lc = li0 + 4 * src + __ffs(f) - 1;
+        const int b = __ffs(f) - 1;
         f &= f - 1;
-        const int k = lc - (n - 1);
-        const int l0 = k < 0 ? -k : 0, l1 = k > 0 ? n - k : n;
-        double acc = 0.0;
-        for (int l = l0 + lane; l < l1; l += 32) acc = fma(a64[l + k], b64[l], acc);
-        acc = warp_sum(acc);
-        const double cc = acc / den;
-        if (isfinite(cc) && (cc > bv || (cc == bv && lc < bi))) { bv = cc; bi = lc; }
+        const int la = RT * src - 1 + (b < RT ? b : b - RT);
+        refine(b < RT ? la : la + n);
+      }
+    }
+  } else {
+    for (int li0 = 0; li0 < L; li0 += 128) {       // 4 consecutive lags per lane per step
+      const int lb = li0 + 4 * lane;
+      unsigned flags = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int li = lb + e;
+        if (li < L) { const float v = cv[li]; if (cnt >= 2 ? (isfinite(v) && v >= thr) : true) flags |= 1u << e; }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, flags != 0);
+      while (m) {                                  // lanes in increasing lag order, lags of a lane in increasing order
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        unsigned f = __shfl_sync(0xffffffffu, flags, src);
+        while (f) {
+          const int lc = li0 + 4 * src + __ffs(f) - 1;
+          f &= f - 1;
+          refine(lc);
+        }
       }
     }
   }
@@ -381,21 +415,25 @@ extern "C" int bpv_window_xcorr(const double* proc_x, const double* proc_y, cons
   const long long n = (long long)p->S * p->jobs_per_stream * P;
   BPV_REQUIRE(W > 0 && n > 0, BPV_E_INVALID, "bpv_window_xcorr: bad sizes");
   {  // warp-per-pair kernel whenever one pair fits the shared memory of a CTA
-    const XwLayout Lw = xw_layout(W);
+    // BPV_XC_ONE=0 (measurement switch): coarse values through the cv[] array in shared memory, as before round 2's last change
+    static const bool force_cv = [] { const char* e = getenv("BPV_XC_ONE"); return e && e[0] == '0'; }();
+    const XwLayout Lw = xw_layout(W, force_cv);
     int wpb = (200 * 1024) / Lw.total;
     if (wpb > 4) wpb = 4;
     if (wpb >= 1) {
       const size_t smw = (size_t)wpb * Lw.total;
       const unsigned grid = (unsigned)((n + wpb - 1) / wpb);
-#define BPV_XW(LDC)                                                                                                   \
+#define BPV_XW(LDC, ONE)                                                                                              \
   do {                                                                                                                \
-    if (int rc = ensure_dyn_smem((const void*)xcorr_warp_kernel<LDC>, smw)) return rc;                                \
-    xcorr_warp_kernel<LDC><<<grid, wpb * 32, smw, (cudaStream_t)stream>>>(proc_x, proc_y, *p, Lw, n, corr_lag,       \
-                                                                         corr_val, num_lags, lag_idx, lag_sec, lag_corr); \
+    if (int rc = ensure_dyn_smem((const void*)xcorr_warp_kernel<LDC, ONE>, smw)) return rc;                           \
+    xcorr_warp_kernel<LDC, ONE><<<grid, wpb * 32, smw, (cudaStream_t)stream>>>(proc_x, proc_y, *p, Lw, n, corr_lag,  \
+                                                                              corr_val, num_lags, lag_idx, lag_sec, lag_corr); \
   } while (0)
-      if (Lw.LD == 63) BPV_XW(63);            // windows of 291..300 samples (the 10 s window at 30 fps)
-      else if (Lw.LD == 53) BPV_XW(53);       // 241..250 (the reference's default signal_max_samples)
-      else BPV_XW(0);
+      if (Lw.LD == 63 && Lw.one_round) BPV_XW(63, true);      // windows of 291..300 samples (the 10 s window at 30 fps)
+      else if (Lw.LD == 53 && Lw.one_round) BPV_XW(53, true); // 241..250 (the reference's default signal_max_samples)
+      else if (Lw.LD == 63) BPV_XW(63, false);
+      else if (Lw.one_round) BPV_XW(0, true);
+      else BPV_XW(0, false);
 #undef BPV_XW
       return check_launch("bpv_window_xcorr");
     }
