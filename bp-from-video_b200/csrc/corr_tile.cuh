@@ -21,10 +21,13 @@ __device__ __forceinline__ int xt_index(int j, int LD) { return (j % RT) * LD + 
 // computation: 29 integer instructions and ~17 % of the stall samples of the FIR loop (profiles/r2l_c2 source view).
 // CVALID > 0 (run-time c_valid): c holds only c_valid coefficients (e.g. the taps as the design kernel left them in global
 // memory) and the padding up to K is supplied as zeros here instead of by a zero-padded copy.
-template <int RT, typename T, int LDC = 0, int KC = 0, bool CGUARD = false>
+// C2: c is 16-byte aligned (T = double, RT even): the coefficients are fetched two at a time (LDS.128; the loads are
+// warp-uniform, so this halves the coefficient wavefronts of a tap block).
+template <int RT, typename T, int LDC = 0, int KC = 0, bool CGUARD = false, bool C2 = false>
 __device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c, int K_rt,
                                           const T* __restrict__ XT, int LD_rt, int j0,
                                           int kb_begin = 0, int kb_end = 0x7fffffff, int c_valid = 0) {
+  static_assert(!C2 || (sizeof(T) == 8 && RT % 2 == 0 && !CGUARD), "paired coefficient loads: double, even tile, no guard");
   const int LD = LDC ? LDC : LD_rt;
   const int K = KC ? KC : K_rt;
   const int col0 = j0 / RT;
@@ -38,7 +41,13 @@ __device__ __forceinline__ void corr_tile(T (&acc)[RT], const T* __restrict__ c,
   for (int kb = kb_begin; kb < kb_end; ++kb) {
 #pragma unroll
     for (int kk = 0; kk < RT; ++kk) {
-      const T ck = (!CGUARD || kb * RT + kk < c_valid) ? cc[kk] : (T)0;
+      T ck;
+      if constexpr (C2) {
+        const double2 cp = reinterpret_cast<const double2*>(cc)[kk >> 1];
+        ck = (kk & 1) ? cp.y : cp.x;
+      } else {
+        ck = (!CGUARD || kb * RT + kk < c_valid) ? cc[kk] : (T)0;
+      }
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r] = fma(ck, w[(r - kk + RT) % RT], acc[r]);
       w[RT - 1 - kk] = xn[(RT - 1 - kk) * LD];      // X[j0 - k - 1] replaces X[j0 - k + RT - 1]

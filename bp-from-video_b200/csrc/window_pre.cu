@@ -88,21 +88,24 @@ __host__ __device__ inline PreLayout pre_layout(const bpv_window_params& p, bool
     int need = L.fir_b;                                              // taps / zi stay in global memory (fir_filtfilt)
     if (W >= T) {
       const int x8 = 8 * fir_merged_ld(W, T, 8), x10 = 10 * fir_merged_ld(W, T, 10);
-      L.fir_c = x8 > x10 ? x8 : x10;
+      L.fir_c = ((x8 > x10 ? x8 : x10) + 1) & ~1;                    // even: c[] 16-byte aligned inside buf0
       const int k8 = fir_merged_k(T, 8), k10 = fir_merged_k(T, 10);
       const int m = L.fir_c + (taps_global ? 0 : (k8 > k10 ? k8 : k10));
       if (m > need) need = m;
     }
     if (need > L.buf_len) L.buf_len = need;
   }
+  // every section starts on a 16-byte boundary (the merged FIR fetches its taps with 128-bit loads), and so does the next
+  // warp's slice
   int o = 0;
-  L.yv = o; o += W * 8;
-  L.xv = o; o += interp ? W * 8 : 0;
-  L.buf0 = o; o += L.buf_len * 8;
-  L.buf1 = o; o += cubic ? W * 8 : 0;                  // knot slopes of the spline
-  L.coef = o; o += butter ? 128 * 8 : 0;               // sos [16][6] | sosfilt_zi [16][2]
-  L.posv = o; o += ((W * 2 + 7) / 8) * 8;
-  L.posb = o; o += interp ? ((W * 2 + 7) / 8) * 8 : 0;
+  auto sect = [&o](int bytes) { const int at = o; o += (bytes + 15) / 16 * 16; return at; };
+  L.yv = sect(W * 8);
+  L.xv = sect(interp ? W * 8 : 0);
+  L.buf0 = sect(L.buf_len * 8);
+  L.buf1 = sect(cubic ? W * 8 : 0);                    // knot slopes of the spline
+  L.coef = sect(butter ? 128 * 8 : 0);                 // sos [16][6] | sosfilt_zi [16][2]
+  L.posv = sect(W * 2);
+  L.posb = sect(interp ? W * 2 : 0);
   L.total = o;
   return L;
 }
@@ -679,7 +682,7 @@ __device__ void fir_merged(Warp& w, const double* __restrict__ c_g, int T) {
     double acc[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-    corr_tile<RT, double, LDC, KC>(acc, c, K, XT, LD, K + RT * t);
+    corr_tile<RT, double, LDC, KC, false, CS>(acc, c, K, XT, LD, K + RT * t);     // staged taps are 16-byte aligned (pre_layout)
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int m = RT * t + r;
