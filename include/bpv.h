@@ -201,8 +201,8 @@ int bpv_window_preprocess(const double* ring_t, const double* ring_y, const bpv_
 /* The two halves of bpv_window_preprocess, for callers that overlap them or keep a design cache:
  * bpv_window_design — make_filter for every window job (signal_processor.py:158-173, called per frame and signal at
  *   :226, :232): needs only the timestamps (ring_t), so it can run on another stream as soon as they are pushed, beside
- *   the ROI sampling of the same frames.  Fills `workspace` (per job: Butterworth sos | FIR taps | lfilter_zi | tap
- *   autocorrelation).
+ *   the ROI sampling of the same frames.  Fills `workspace` (per job: Butterworth sos | FIR taps | lfilter_zi | the
+ *   2T-1 taps of the merged forward.backward filter, i.e. the tap autocorrelation laid out symmetrically).
  * bpv_window_filter — process_signal given the designs (same stream, or after an event on the design).
  * cache (optional, may be NULL): caller-owned device memory of bpv_design_cache_bytes() bytes, zero-initialised, kept
  *   across calls.  make_filter is a pure function of the window's sampling rate; the cache is a table keyed by the 64 bits

@@ -106,7 +106,7 @@ def test_signal_data_differential_vs_reference():
     import signal_data as ours
     ref = _load_ref('signal_data')
     rng = np.random.default_rng(0)
-    for trial in range(40):
+    for trial in range(80):
         maxlen = int(rng.integers(1, 7))
         vec = trial % 3 == 0
         yi = (np.nan,) * 6 if vec else np.nan
@@ -117,6 +117,8 @@ def test_signal_data_differential_vs_reference():
             for _ in range(2):
                 if rng.uniform() < 0.25:
                     ys.append((np.nan,) * 6 if vec else np.nan)
+                elif not vec and rng.uniform() < 0.08:
+                    ys.append(float(rng.choice([np.inf, -np.inf])))      # non-finite but not NaN: masked out, yet seen by the ranges
                 else:
                     ys.append(tuple(int(v) for v in rng.integers(0, 50, 6)) if vec else float(rng.integers(0, 5)))
             a.add_samples(t, ys)
