@@ -391,7 +391,7 @@ def time_family_wrappers(torch, ops, fam, only=None):
     """Wrap the ops launchers (all, or those named in `only`) so every call is bracketed by CUDA events on the stream it
     launches on."""
     names = dict(roi_sample='roi', ring_push='push', window_preprocess='preprocess', window_design='design',
-                 window_filter='preprocess', window_spectrum='spectrum', window_xcorr='xcorr')
+                 window_filter='preprocess', window_spectrum='spectrum', window_xcorr='xcorr', window_welch_xcorr='spectrum_xcorr')
     if only is not None:
         names = {k: v for k, v in names.items() if k in only}
     orig = {k: getattr(ops, k) for k in names}
@@ -755,11 +755,12 @@ def run_gpu(args, wl):
     alg = {
         'roi': alg_roi_bytes + S * T * 2 * (16 + 8),
         'push': S * T * 3 * 8 * 2,
-        'design': jobs * (win * 8 + 384 * 8),
+        'design': jobs * (win * 8 + 520 * 8),
         'preprocess': nsig * win * (8 + 8 + 8 + 8),          # ring t,y in + proc x,y out (float64)
         'spectrum': nsig * win * 16 + nsig * 24,
         'xcorr': jobs * (3 * win * 8 + 24),
     }
+    alg['spectrum_xcorr'] = alg['spectrum'] + alg['xcorr']       # overlap bit 4: both in one grid
     if 'design' not in fam_ms and 'preprocess' in fam_ms:
         alg['preprocess'] += alg['design']
     total_fam = sum(fam_ms.values())
@@ -844,7 +845,8 @@ def run_gpu(args, wl):
         # spectrum, xcorr) + pack_records32 for the result record
         'gpu_launches': launches_per_step * args.steps,
         'schedule': dict(sched, note='bpv/engine.py: overlap bit 1 = filter design beside F1, bit 2 = xcorr beside the spectrum (their '
-                                     'family times then overlap); design_cache = filter designs looked up by the bits of fs'),
+                                     'family times then overlap), bit 4 = Welch + xcorr as ONE grid of interleaved CTAs (family '
+                                     'spectrum_xcorr); design_cache = filter designs looked up by the bits of fs'),
         'record_bytes_per_job': 4 * rec_cols,
         'numa': numa,
         'clocks': clk,

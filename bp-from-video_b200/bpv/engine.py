@@ -21,6 +21,8 @@ overwritten by the one after; hold results longer by cloning them or by raising 
 Overlap (`overlap`, bit mask; default from the environment variable BPV_OVERLAP, else OVERLAP_DEFAULT):
   1  the filter design of the step (it needs only the timestamps) runs on a side stream beside F1
   2  F4 (cross-correlation) runs on a side stream beside F3 (spectrum): both only read the processed windows
+  4  F3 + F4 as ONE grid of interleaved Welch / xcorr CTAs (PGRAM_WELCH, windows up to 320 samples, >= 2 ROIs): the two
+     kernels are bound by different things and mix poorly as two launches (takes precedence over 2 where it applies)
 """
 from __future__ import annotations
 
@@ -33,7 +35,7 @@ import torch
 from . import _cabi, ops
 
 EVERY_FRAME, LAST = 'every_frame', 'last'
-OVERLAP_DESIGN, OVERLAP_XCORR = 1, 2
+OVERLAP_DESIGN, OVERLAP_XCORR, OVERLAP_FUSED = 1, 2, 4
 OVERLAP_DEFAULT = OVERLAP_DESIGN | OVERLAP_XCORR    # measured on c2 (profiles/r2k_overlap_ab.txt): 0.474 ms serial, 0.467 xcorr only, 0.461 both
 STATE_VERSION = 1
 
@@ -319,7 +321,11 @@ class BatchedSignalProcessor:
         spo, xco = self._spec[turn], self._xc[turn]
         spo = None if spo is None or spo['peak_idx'].shape[0] != J else spo
         xco = None if xco is None or xco['lag_idx'].shape[0] != J else xco
-        if (self.overlap & OVERLAP_XCORR) and self.P:
+        # (windows over 320 samples: the entry point itself runs the two stand-alone launches, on this stream)
+        fused = bool(self.overlap & OVERLAP_FUSED) and self.P > 0 and self.transform == _cabi.PGRAM_WELCH
+        if fused:
+            sp, xc = ops.window_welch_xcorr(px, py, p, store=self.store_arrays, out_spectrum=spo, out_xcorr=xco)
+        elif (self.overlap & OVERLAP_XCORR) and self.P:
             # launch order matters for co-residency: the spectrum kernels' CTAs are small (Welch: 24 KB of shared memory),
             # the xcorr CTAs large (51 KB); with xcorr first its 4 CTAs fill an SM's shared memory and the spectrum only
             # gets in as they retire (168 us for the pair against 103 + 75 serial); spectrum first leaves room for two xcorr
@@ -356,7 +362,7 @@ class BatchedSignalProcessor:
             if (env[:1] == '1') if env is not None else interp:
                 n_spec = 6              # dft_image + seal + dft_split + dft_tc_tma2 + dft_peak kernels + spectrum_dense_kernel for the flagged windows
         n_push = 2 if _designed else 1
-        self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P else 0)
+        self.launches_per_step = (1 + self._extra_launches if _count_roi else 0) + n_push + n_pre + n_spec + (1 if self.P and not (fused and self.W <= 320) else 0)
         if not self.store_arrays and self.discard_scratch:
             self.launches_per_step += 1 if J == self._Jmax else 2
         arrays = {}

@@ -187,12 +187,10 @@ def max_bins(p: WindowParams) -> int:
     return min(256, p.window) // 2 + 1
 
 
-def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=None, workspace=None):
-    """F3 + HR peak (signal_processor.py:248-277, 310).  Returns dict(freqs, mags f32 [J,R,max_bins] | None,
-    num_bins i32, peak_idx i32, peak_freq f64, peak_mag f64 [J,R])."""
-    J = p.S * p.jobs_per_stream
-    dev = proc_y.device
-    mb = max_bins(p)
+def _spectrum_out(p: WindowParams, store: bool, out, dev) -> dict:
+    """Result tensors of F3 (missing ones are allocated): freqs, mags f32 [J,R,max_bins] | None, num_bins i32, peak_idx i32,
+    peak_freq f64, peak_mag f64 [J,R]."""
+    J, mb = p.S * p.jobs_per_stream, max_bins(p)
     o = out or {}
     if store:
         if 'freqs' not in o:
@@ -209,24 +207,13 @@ def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=Non
         o['peak_freq'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
     if 'peak_mag' not in o:
         o['peak_mag'] = torch.empty((J, p.R), dtype=torch.float64, device=dev)
-    # scratch for the coarse spectrum when it is not stored; for DFT_RFFT also the persistent twiddle operand images of the
-    # tensor-core kernel (zero-initialised: a header tells the kernel whether they are built) — pass the same workspace
-    # every call to build them once
-    need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if (not store or p.transform == _cabi.DFT_RFFT) else 0
-    if need and (workspace is None or workspace.numel() < need):
-        workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
-    _run(proc_y.device, 'bpv_window_spectrum', ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
-                                    ptr(o['freqs']), ptr(o['mags']),
-                                    ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']))
     return o
 
 
-def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
-    """F4 pairwise xcorr + lag peak (signal_processor.py:280-299, 312)."""
-    J = p.S * p.jobs_per_stream
-    P = p.R * (p.R - 1) // 2
-    dev = proc_y.device
-    L = 2 * p.window - 1
+def _xcorr_out(p: WindowParams, store: bool, out, dev) -> dict:
+    """Result tensors of F4 (missing ones are allocated): lags, corr f32 [J,P,2W-1] | None, num_lags, lag_idx i32,
+    lag_sec, lag_corr f64 [J,P]."""
+    J, P, L = p.S * p.jobs_per_stream, p.R * (p.R - 1) // 2, 2 * p.window - 1
     o = out or {}
     if store:
         if 'lags' not in o:
@@ -243,6 +230,44 @@ def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
         o['lag_sec'] = torch.empty((J, P), dtype=torch.float64, device=dev)
     if 'lag_corr' not in o:
         o['lag_corr'] = torch.empty((J, P), dtype=torch.float64, device=dev)
+    return o
+
+
+def window_welch_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out_spectrum=None, out_xcorr=None):
+    """F3 (PGRAM_WELCH) + F4 of the same window jobs in ONE grid of interleaved Welch / xcorr CTAs (include/bpv.h
+    bpv_window_welch_xcorr).  Returns the dicts of window_spectrum and window_xcorr; same values bit for bit."""
+    if p.transform != _cabi.PGRAM_WELCH or p.R < 2:
+        raise ValueError('window_welch_xcorr: PGRAM_WELCH and at least two ROIs')
+    dev = proc_y.device
+    sp, xc = _spectrum_out(p, store, out_spectrum, dev), _xcorr_out(p, store, out_xcorr, dev)
+    _run(dev, 'bpv_window_welch_xcorr', ptr(proc_x), ptr(proc_y), C.byref(p), max_bins(p), ptr(sp['freqs']), ptr(sp['mags']),
+         ptr(sp['num_bins']), ptr(sp['peak_idx']), ptr(sp['peak_freq']), ptr(sp['peak_mag']), ptr(xc['lags']), ptr(xc['corr']),
+         ptr(xc['num_lags']), ptr(xc['lag_idx']), ptr(xc['lag_sec']), ptr(xc['lag_corr']))
+    return sp, xc
+
+
+def window_spectrum(proc_x, proc_y, p: WindowParams, store: bool = True, out=None, workspace=None):
+    """F3 + HR peak (signal_processor.py:248-277, 310).  Returns dict(freqs, mags f32 [J,R,max_bins] | None,
+    num_bins i32, peak_idx i32, peak_freq f64, peak_mag f64 [J,R])."""
+    dev = proc_y.device
+    mb = max_bins(p)
+    o = _spectrum_out(p, store, out, dev)
+    # scratch for the coarse spectrum when it is not stored; for DFT_RFFT also the persistent twiddle operand images of the
+    # tensor-core kernel (zero-initialised: a header tells the kernel whether they are built) — pass the same workspace
+    # every call to build them once
+    need = lib().bpv_spectrum_workspace_bytes(C.byref(p), mb) if (not store or p.transform == _cabi.DFT_RFFT) else 0
+    if need and (workspace is None or workspace.numel() < need):
+        workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
+    _run(proc_y.device, 'bpv_window_spectrum', ptr(proc_x), ptr(proc_y), C.byref(p), mb, ptr(workspace) if need else None, need,
+                                    ptr(o['freqs']), ptr(o['mags']),
+                                    ptr(o['num_bins']), ptr(o['peak_idx']), ptr(o['peak_freq']), ptr(o['peak_mag']))
+    return o
+
+
+def window_xcorr(proc_x, proc_y, p: WindowParams, store: bool = True, out=None):
+    """F4 pairwise xcorr + lag peak (signal_processor.py:280-299, 312)."""
+    P = p.R * (p.R - 1) // 2
+    o = _xcorr_out(p, store, out, proc_y.device)
     if P > 0:
         _run(proc_y.device, 'bpv_window_xcorr', ptr(proc_x), ptr(proc_y), C.byref(p), ptr(o['lags']), ptr(o['corr']),
                                      ptr(o['num_lags']), ptr(o['lag_idx']), ptr(o['lag_sec']), ptr(o['lag_corr']))

@@ -243,6 +243,16 @@ int bpv_window_xcorr(const double* proc_x, const double* proc_y, const bpv_windo
                      float* corr_lag, float* corr_val, int32_t* num_lags,
                      int32_t* lag_idx, double* lag_sec, double* lag_corr, void* stream);
 
+/* F3 + F4 of the same window jobs in ONE grid (PGRAM_WELCH only): CTAs of the Welch kernel and of the cross-correlation
+ *     kernel interleaved in the ratio of their counts, so that every SM holds both for the whole launch (the two are bound
+ *     by different things — shared-memory wavefronts vs FP32 issue — and mix poorly when launched as two kernels).
+ *     Same arguments and results, bit for bit, as bpv_window_spectrum followed by bpv_window_xcorr; shapes the fused grid
+ *     does not cover (windows over 320 samples, R = 1) run as those two launches on `stream`. */
+int bpv_window_welch_xcorr(const double* proc_x, const double* proc_y, const bpv_window_params* p, int32_t max_bins,
+                           float* spec_f, float* spec_mag, int32_t* num_bins, int32_t* peak_idx, double* peak_freq,
+                           double* peak_mag, float* corr_lag, float* corr_val, int32_t* num_lags, int32_t* lag_idx,
+                           double* lag_sec, double* lag_corr, void* stream);
+
 /* Filter design alone (debug / parity of make_filter, signal_processor.py:158-173).
  * fs float64 [n]; sos_out float64 [n, order, 6]; taps_out float64 [n, fir_taps]. */
 int bpv_butter_sos_design(const double* fs, int32_t n, const bpv_window_params* p, double* sos_out, void* stream);

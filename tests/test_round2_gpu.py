@@ -365,3 +365,41 @@ def test_design_cache_is_dropped_when_filter_parameters_change():
             for e in (a, b):
                 e.kw = dict(e.kw, min_freq=1.1, fir_df=0.25)
         assert _same(_snap(a.step_signals(*f)), _snap(b.step_signals(*f))), k
+
+
+@pytest.mark.parametrize('R,W,T,store', [(2, 48, 4, False), (2, 300, 3, True), (3, 64, 4, False), (2, 250, 2, False), (2, 400, 2, False)])
+def test_fused_welch_xcorr_grid_equals_the_two_launches(R, W, T, store):
+    """overlap bit 4 (include/bpv.h bpv_window_welch_xcorr): Welch and xcorr CTAs interleaved in ONE grid give the bits of
+    the two stand-alone launches — warm-up windows, holes, irregular timestamps, three ROIs (3 pairs per job: another CTA
+    ratio), stored arrays, and a window over 320 samples (the entry point then runs the two launches itself)."""
+    from bpv import synth
+    from bpv.engine import BatchedSignalProcessor
+    S, steps = 7, (W + 40) // T
+    rng = np.random.default_rng(1000 * R + W)
+    ts = np.stack([synth.timestamps(rng, T * steps, 30.0, irregular=True, drop=0.03, origin=rng.uniform(0, 9)) for _ in range(S)])
+    raw = np.stack([synth.raw_signals(rng, ts[s], R=R, p_nan=0.03).T for s in range(S)])
+    keys = ('peak_freq', 'peak_idx', 'peak_mag', 'lag_sec', 'lag_idx', 'lag_corr', 'status')
+    runs = []
+    for ov in (0, 4, 7):
+        eng = BatchedSignalProcessor(S, R, signal_max_samples=W, max_frames_per_step=T, color_channel=orc.CHROM_GREEN,
+                                     processing_methods=[orc.DETREND_LINEAR, orc.FILTER_FIR], spectrum_transform=orc.PGRAM_WELCH,
+                                     store_arrays=store, overlap=ov)
+        out = []
+        for k in range(steps):
+            res = eng.step_signals(torch.from_numpy(raw[:, k * T:(k + 1) * T].copy()).cuda(),
+                                   torch.from_numpy(ts[:, k * T:(k + 1) * T].copy()).cuda())
+            snap = {k2: getattr(res, k2).clone() for k2 in keys}
+            if store:
+                nb, nl = res.arrays['num_bins'], res.arrays['num_lags']
+                snap.update(num_bins=nb.clone(), num_lags=nl.clone())
+                # entries past num_bins / num_lags are undefined: compare the defined ones
+                mb = torch.arange(res.arrays['mags'].shape[-1], device='cuda')[None, None, :] < nb[..., None]
+                ml = torch.arange(res.arrays['corr'].shape[-1], device='cuda')[None, None, :] < nl[..., None]
+                for name, m in (('freqs', mb), ('mags', mb), ('lags', ml), ('corr', ml)):
+                    snap[name] = torch.where(m, res.arrays[name], torch.zeros_like(res.arrays[name])).view(torch.int32).clone()
+            out.append(snap)
+        torch.cuda.synchronize()
+        runs.append(out)
+    for other in runs[1:]:
+        assert all(_same(x, y) for x, y in zip(runs[0], other))
+    assert any(bool(torch.isfinite(x['lag_sec']).any()) for x in runs[0]) and any(bool((x['peak_idx'] >= 0).any()) for x in runs[0])
