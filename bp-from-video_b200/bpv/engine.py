@@ -21,8 +21,9 @@ overwritten by the one after; hold results longer by cloning them or by raising 
 Overlap (`overlap`, bit mask; default from the environment variable BPV_OVERLAP, else OVERLAP_DEFAULT):
   1  the filter design of the step (it needs only the timestamps) runs on a side stream beside F1
   2  F4 (cross-correlation) runs on a side stream beside F3 (spectrum): both only read the processed windows
-  4  F3 + F4 as ONE grid of interleaved Welch / xcorr CTAs (PGRAM_WELCH, windows up to 320 samples, >= 2 ROIs): the two
-     kernels are bound by different things and mix poorly as two launches (takes precedence over 2 where it applies)
+  4  F3 + F4 as ONE grid of interleaved Welch / xcorr CTAs (PGRAM_WELCH, windows up to 320 samples, >= 2 ROIs; takes precedence
+     over 2 where it applies).  Measured SLOWER than bit 2 (profiles/r4g: 272.9 against 227.5 us for the pair, step 0.7255 against
+     0.6840 ms) although the two kernels are bound by different things: not in the default mask, kept as a measurement switch
 """
 from __future__ import annotations
 

@@ -8,6 +8,12 @@
 // of the two roles are INTERLEAVED in one grid in the ratio of their counts (R = 2: two Welch CTAs of four signals per xcorr
 // CTA of four pairs), so every SM holds a mix of both for the whole launch.  The role of a CTA is a function of its index;
 // each role runs the unmodified body of its stand-alone kernel (welch.cuh, xcorr_warp.cuh): results are identical bit for bit.
+//
+// MEASURED (profiles/r4g_bench_c2_fused.json against r4g_bench_c2.json, 16 384 window jobs): 272.9 us for the fused grid against
+// 227.5 us for the two kernels on two streams (240 one after the other) — the mix is SLOWER.  What it costs: both roles at the
+// larger role's footprint (96 registers, 36 KB), 41 instead of 26 register moves per 10 taps of the packed xcorr tile under
+// the joint register allocation, and two large unrolled bodies (6.6 k instructions) resident on every SM at once.  Not used by
+// default (engine overlap bit 4); kept as a tested experiment.
 #include "welch.cuh"
 #include "xcorr_warp.cuh"
 

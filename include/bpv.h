@@ -247,7 +247,9 @@ int bpv_window_xcorr(const double* proc_x, const double* proc_y, const bpv_windo
  *     kernel interleaved in the ratio of their counts, so that every SM holds both for the whole launch (the two are bound
  *     by different things — shared-memory wavefronts vs FP32 issue — and mix poorly when launched as two kernels).
  *     Same arguments and results, bit for bit, as bpv_window_spectrum followed by bpv_window_xcorr; shapes the fused grid
- *     does not cover (windows over 320 samples, R = 1) run as those two launches on `stream`. */
+ *     does not cover (windows over 320 samples, R = 1) run as those two launches on `stream`.
+ *     MEASURED SLOWER on B200 than the two kernels on two streams (272.9 against 227.5 us per 16 384 window jobs,
+ *     profiles/r4g_*): an experiment kept for reference — the engine does not use it unless asked (overlap bit 4). */
 int bpv_window_welch_xcorr(const double* proc_x, const double* proc_y, const bpv_window_params* p, int32_t max_bins,
                            float* spec_f, float* spec_mag, int32_t* num_bins, int32_t* peak_idx, double* peak_freq,
                            double* peak_mag, float* corr_lag, float* corr_val, int32_t* num_lags, int32_t* lag_idx,
