@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const doub
                                                                       const bpv_window_params p, const PreLayout L,
                                                                       const DesignRef dr,
                                                                       double* __restrict__ proc_x, double* __restrict__ proc_y,
-                                                                      int32_t* __restrict__ status, int spw) {
+                                                                      int32_t* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long unit = (long long)blockIdx.x * wpb + wib;
@@ -892,22 +892,17 @@ __global__ void __launch_bounds__(128, MINB) window_preprocess_kernel(const doub
   const int W = p.window;
   const int lane = threadIdx.x & 31;
   if (!DUAL) {
-    // spw consecutive signals per warp, one after the other: the CTA's start-up (7 % of the stall samples of the one-signal
-    // kernel sat on its first instructions: 32 768 one-warp CTAs per launch) is paid once per spw signals
-    for (int it = 0; it < spw; ++it) {
-      const long long sig = unit * spw + it;                       // job * R + r
-      if (sig >= nsig) return;
-      Warp w;
-      w.lane = lane;
-      const long long job = sig / p.R;
-      prefetch_filters(FEAT, lane, p, dr, job);
-      double* ox = proc_x + sig * W;
-      double* oy = proc_y + sig * W;
-      int st = gather_window<FEAT>(w, smem_raw + (size_t)wib * L.total, L, p, ring_t, ring_y, sig, ox, oy);
-      for (int mi = 0; mi < p.num_methods && st == ST_OK; ++mi) st = apply_method<FEAT>(w, p.methods[mi], p, dr, job);
-      scatter_window(w, st, W, ox, oy, status, sig);
-      __syncwarp();                                                // the next signal reuses the warp's shared-memory slice
-    }
+    const long long sig = unit;                                    // job * R + r
+    if (sig >= nsig) return;
+    Warp w;
+    w.lane = lane;
+    const long long job = sig / p.R;
+    prefetch_filters(FEAT, lane, p, dr, job);
+    double* ox = proc_x + sig * W;
+    double* oy = proc_y + sig * W;
+    int st = gather_window<FEAT>(w, smem_raw + (size_t)wib * L.total, L, p, ring_t, ring_y, sig, ox, oy);
+    for (int mi = 0; mi < p.num_methods && st == ST_OK; ++mi) st = apply_method<FEAT>(w, p.methods[mi], p, dr, job);
+    scatter_window(w, st, W, ox, oy, status, sig);
   } else {
     const long long sa = 2 * unit, sb = sa + 1;
     if (sa >= nsig) return;
@@ -967,13 +962,8 @@ static int launch_preprocess(const double* ring_t, const double* ring_y, const b
   auto kern = window_preprocess_kernel<FEAT, MINB, DUAL>;
   if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
   const long long nsig = (long long)p.S * p.jobs_per_stream * p.R;
-  // signals per warp (one-signal kernels): BPV_F2_SPW = 1..8; 2 while that still leaves every warp slot of the GPU several
-  // CTAs to run (the block scheduler balances the tail), else 1
-  static const int spw_env = [] { const char* e = getenv("BPV_F2_SPW"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 0; }();
-  int spw = 1;
-  if (!DUAL) spw = spw_env ? spw_env : (nsig >= 8LL * 148 * reg_warps ? 2 : 1);
-  const long long units = DUAL ? (nsig + 1) / 2 : (nsig + spw - 1) / spw;
-  kern<<<(unsigned)((units + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, p, L, dr, proc_x, proc_y, status, spw);
+  const long long units = DUAL ? (nsig + 1) / 2 : nsig;
+  kern<<<(unsigned)((units + wpb - 1) / wpb), wpb * 32, smem, st>>>(ring_t, ring_y, p, L, dr, proc_x, proc_y, status);
   return check_launch("bpv_window_preprocess");
 }
 
