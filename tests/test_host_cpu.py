@@ -32,6 +32,32 @@ def test_cabi_exports_every_declared_symbol():
     assert ctypes.sizeof(_cabi.WindowParams) == lib.bpv_sizeof_window_params() == 120
 
 
+def test_ctypes_signatures_follow_the_header():
+    """Every prototype of include/bpv.h and its ctypes binding agree on the number of arguments and on which of them
+    are pointers / 64-bit / 32-bit / double (a mismatch would corrupt the call silently)."""
+    import ctypes
+    from bpv import _cabi
+    hdr = open(os.path.join(ROOT, 'include', 'bpv.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    protos = re.findall(r'\b([a-z_0-9]+(?:\s*\*)?)\s*\b(bpv_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', hdr)
+    assert {n for _, n, _ in protos} == set(_cabi.EXPORTS)
+
+    def kind(decl):
+        decl = decl.strip()
+        if '*' in decl:
+            return 'p'
+        base = decl.rsplit(' ', 1)[0] if ' ' in decl else decl
+        return {'int64_t': 'q', 'int32_t': 'i', 'int': 'i', 'double': 'd'}[base.replace('const', '').strip()]
+
+    ckind = {ctypes.c_void_p: 'p', ctypes.c_char_p: 'p', ctypes.c_int64: 'q', ctypes.c_int32: 'i', ctypes.c_int: 'i',
+             ctypes.c_double: 'd'}
+    for _, name, args in protos:
+        want = [] if args.strip() in ('', 'void') else [kind(a) for a in args.split(',')]
+        _, bound = _cabi._SIGS[name]
+        got = ['p' if (isinstance(t, type) and issubclass(t, ctypes._Pointer)) else ckind[t] for t in bound]
+        assert got == want, (name, got, want)
+
+
 def test_no_cpu_fallback_without_library(monkeypatch):
     from bpv import _cabi
     monkeypatch.setattr(_cabi, '_lib', None)
